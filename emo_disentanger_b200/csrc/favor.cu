@@ -1,0 +1,480 @@
+// K4+K5: FAVOR+ random-feature map fused with the causal prefix-sum (linear attention).
+//
+// Replaces fast_transformers Favor.forward + CausalLinearAttention.forward + the native
+// causal_dot_product extension (stage2_accompaniment/model/fast_transformer_decoder.py:28-38).
+// One CTA per (batch, head) walks the sequence in chunks of C tokens; phi(q), phi(k) are recomputed
+// per chunk in shared memory and never written to HBM.  Per chunk (V' = [v | 1 | 0..] is 80 wide so
+// the normaliser rides along with the values):
+//     U   = X . Om_s                 phi = [exp(U - o), exp(-U - o)],  o = |x|^2 s^2/2 + ln(128)/2
+//     A   = tril(Phi_q Phi_k^T)                                  (intra-chunk causal part)
+//     O'  = A V' + Phi_q S'          out = O'[:, :64] / (O'[:, 64] + 1e-6)
+//     S' += Phi_k^T V'                                           (prefix state, fp32 registers)
+// Backward is ONE reverse pass: it starts from the saved final state, un-does the state update
+// chunk by chunk (S'_{c-1} = S'_c - Phi_k^T V'), and carries the reverse state R' = sum Phi_q^T G.
+// All small products run through BlockGemm (tensor-core mma for bf16, fp32 FMA for the parity mode).
+#include "block_gemm.cuh"
+
+constexpr int FE = 64;    // head dim
+constexpr int FM = 128;   // feature dim (n_dims)
+constexpr int FV = 80;    // padded value width: 64 values + ones column + zero pad
+constexpr float F_EPS = 1e-6f;
+constexpr float F_S2 = 0.125f;                 // softmax_temp = 1/sqrt(64); x is scaled by sqrt(temp)
+constexpr float F_HALF_LOG_M = 2.4260151319598084f;   // 0.5 * ln(128)
+
+template <typename T> struct FavorCfg;
+template <> struct FavorCfg<bf16> { static constexpr int C = 64; };
+template <> struct FavorCfg<float> { static constexpr int C = 32; };
+
+template <typename T> __device__ __forceinline__ float f_exp(float x);
+template <> __device__ __forceinline__ float f_exp<bf16>(float x) { return __expf(x); }
+template <> __device__ __forceinline__ float f_exp<float>(float x) { return expf(x); }
+
+template <typename T, int C> struct FavorSmemFwd {
+  T xq[C][bg_ld<T>(FE)];
+  T xk[C][bg_ld<T>(FE)];
+  T om[FE][bg_ld<T>(FE)];
+  T v[C][bg_ld<T>(FV)];
+  T pq[C][bg_ld<T>(FM)];
+  T pk[C][bg_ld<T>(FM)];
+  T a[C][bg_ld<T>(C)];
+  T s[FM][bg_ld<T>(FV)];
+  float oq[C], ok[C], den[C];
+};
+
+template <typename T, int C> struct FavorSmemBwd {
+  T xq[C][bg_ld<T>(FE)];
+  T xk[C][bg_ld<T>(FE)];
+  T om[FE][bg_ld<T>(FE)];
+  T du[C][bg_ld<T>(FE)];
+  T st[C][bg_ld<T>(FE)];
+  T v[C][bg_ld<T>(FV)];
+  T g[C][bg_ld<T>(FV)];
+  T pq[C][bg_ld<T>(FM)];
+  T pk[C][bg_ld<T>(FM)];
+  T w[C][bg_ld<T>(FM)];
+  T a[C][bg_ld<T>(C)];
+  T p[C][bg_ld<T>(C)];
+  T s[FM][bg_ld<T>(FV)];
+  T r[FM][bg_ld<T>(FV)];
+  float oq[C], ok[C], dof[C];
+};
+
+// load a [C x 64] tile of rows (token stride ld) into smem, returning per-row sum of squares
+// (rows >= valid are zero-filled).  VPR threads share a row.
+template <typename T, int C, int LD>
+__device__ __forceinline__ void load_rows(const T* __restrict__ src, int64_t ld, int valid, T (*dst)[LD],
+                                          float* sumsq /* may be null */, float hs, float add) {
+  constexpr int N = Vec<T>::N;
+  constexpr int VPR = FE / N;
+  for (int i = threadIdx.x; i < C * VPR; i += BG_THREADS) {
+    int row = i / VPR, part = i % VPR;
+    Vec<T> t;
+    if (row < valid) t.load(src + (int64_t)row * ld + part * N);
+    else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) t.v[j] = 0.f;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { dst[row][part * N + j] = from_f<T>(t.v[j]); ss += t.v[j] * t.v[j]; }
+    if (sumsq) {
+#pragma unroll
+      for (int o = VPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (part == 0) sumsq[row] = ss * hs + add;
+    }
+  }
+}
+
+template <typename T, int C, int LD>
+__device__ __forceinline__ void store_rows(T* __restrict__ dst, int64_t ld, int valid, T (*src)[LD]) {
+  constexpr int N = Vec<T>::N;
+  constexpr int VPR = FE / N;
+  for (int i = threadIdx.x; i < C * VPR; i += BG_THREADS) {
+    int row = i / VPR, part = i % VPR;
+    if (row < valid) {
+      Vec<T> t;
+#pragma unroll
+      for (int j = 0; j < N; ++j) t.v[j] = to_f(src[row][part * N + j]);
+      t.store(dst + (int64_t)row * ld + part * N);
+    }
+  }
+}
+
+template <typename T, int LD>
+__device__ __forceinline__ void load_omega(const float* __restrict__ omega, T (*om)[LD]) {
+  const float s = 0.35355339059327373f;   // 64^(-1/4) folded into omega
+  for (int i = threadIdx.x; i < FE * FE; i += BG_THREADS) om[i / FE][i % FE] = from_f<T>(omega[i] * s);
+}
+
+// U = X . Om_s -> phi rows in smem (rows >= valid zeroed)
+template <typename T, int C, int LDX, int LDO, int LDP>
+__device__ __forceinline__ void phi_rows(T (*x)[LDX], T (*om)[LDO], const float* off, int valid, T (*phi)[LDP]) {
+  BlockGemm<C, FE, T> g;
+  g.clear();
+  g.template mma<true, false>(&x[0][0], LDX, &om[0][0], LDO, FE);
+  g.foreach ([&](int row, int col, float& u) {
+    float o = off[row];
+    bool ok = row < valid;
+    phi[row][col] = from_f<T>(ok ? f_exp<T>(u - o) : 0.f);
+    phi[row][FE + col] = from_f<T>(ok ? f_exp<T>(-u - o) : 0.f);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BG_THREADS, 1)
+favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
+                 const float* __restrict__ omega, T* __restrict__ out, int64_t ld_out, float* __restrict__ den_out,
+                 float* __restrict__ state_out, int Tlen, int H) {
+  constexpr int C = FavorCfg<T>::C;
+  using S = FavorSmemFwd<T, C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
+  const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
+
+  load_omega<T>(omega, sm.om);
+  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
+  BlockGemm<FM, FV, T> gs;   // running prefix state S' (fp32 master)
+  gs.clear();
+  __syncthreads();
+
+  for (int t0 = 0; t0 < Tlen; t0 += C) {
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    load_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
+    load_rows<T, C>(k + base + (int64_t)t0 * ld, ld, valid, sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
+    load_rows<T, C>(v + base + (int64_t)t0 * ld, ld, valid, sm.v, (float*)nullptr, 0.f, 0.f);
+    for (int i = threadIdx.x; i < C * (FV - FE); i += BG_THREADS) {
+      int row = i / (FV - FE), col = FE + i % (FV - FE);
+      sm.v[row][col] = from_f<T>((col == FE && row < valid) ? 1.f : 0.f);
+    }
+    __syncthreads();
+    phi_rows<T, C>(sm.xq, sm.om, sm.oq, valid, sm.pq);
+    phi_rows<T, C>(sm.xk, sm.om, sm.ok, valid, sm.pk);
+    __syncthreads();
+    {
+      BlockGemm<C, C, T> ga;
+      ga.clear();
+      ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
+      ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
+    }
+    __syncthreads();
+    {
+      BlockGemm<C, FV, T> go;
+      go.clear();
+      go.template mma<true, false>(&sm.a[0][0], bg_ld<T>(C), &sm.v[0][0], bg_ld<T>(FV), C);
+      go.template mma<true, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.s[0][0], bg_ld<T>(FV), FM);
+      go.foreach ([&](int row, int col, float& x) { if (col == FE) sm.den[row] = x + F_EPS; });
+      __syncthreads();
+      go.foreach ([&](int row, int col, float& x) { if (col < FE) sm.xq[row][col] = from_f<T>(x / sm.den[row]); });
+    }
+    __syncthreads();
+    store_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.xq);
+    if (den_out)
+      for (int i = threadIdx.x; i < valid; i += BG_THREADS) den_out[((int64_t)b * Tlen + t0 + i) * H + h] = sm.den[i];
+    gs.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
+    gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
+    __syncthreads();
+  }
+  if (state_out) {
+    float* so = state_out + (int64_t)blockIdx.x * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (single reverse pass)
+// ---------------------------------------------------------------------------------------------
+// dphi (already multiplied by phi, in sm.w) -> du (smem, T) and do (per row, fp32)
+template <typename T, int C, typename SM>
+__device__ __forceinline__ void phi_bwd_reduce(SM& sm) {
+  constexpr int TPR = BG_THREADS / C;     // threads per row
+  constexpr int FPT = FE / TPR;           // features per thread
+  int row = threadIdx.x / TPR, part = threadIdx.x % TPR;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < FPT; ++j) {
+    int f = part * FPT + j;
+    float wp = to_f(sm.w[row][f]), wm = to_f(sm.w[row][FE + f]);
+    sm.du[row][f] = from_f<T>(wp - wm);
+    acc += wp + wm;
+  }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (part == 0) sm.dof[row] = -acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BG_THREADS, 1)
+favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
+                 const float* __restrict__ omega, const T* __restrict__ out, const T* __restrict__ dout,
+                 int64_t ld_out, const float* __restrict__ den_in, const float* __restrict__ state_in,
+                 T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t ld_d, int Tlen, int H) {
+  constexpr int C = FavorCfg<T>::C;
+  using S = FavorSmemBwd<T, C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
+  const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
+  const int64_t dbase = (int64_t)b * Tlen * ld_d + (int64_t)h * FE;
+
+  load_omega<T>(omega, sm.om);
+  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.r[0][0])[i] = from_f<T>(0.f);
+  BlockGemm<FM, FV, T> gs, gr;   // forward prefix state (rolled back) and reverse state
+  gr.clear();
+  {
+    const float* si = state_in + (int64_t)blockIdx.x * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
+  }
+  __syncthreads();
+
+  const int nchunk = (Tlen + C - 1) / C;
+  for (int c = nchunk - 1; c >= 0; --c) {
+    const int t0 = c * C;
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    load_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
+    load_rows<T, C>(k + base + (int64_t)t0 * ld, ld, valid, sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
+    load_rows<T, C>(v + base + (int64_t)t0 * ld, ld, valid, sm.v, (float*)nullptr, 0.f, 0.f);
+    for (int i = threadIdx.x; i < C * (FV - FE); i += BG_THREADS) {
+      int row = i / (FV - FE), col = FE + i % (FV - FE);
+      sm.v[row][col] = from_f<T>((col == FE && row < valid) ? 1.f : 0.f);
+    }
+    {  // G = [dout/den | -(dout.out)/den | 0]
+      constexpr int N = Vec<T>::N;
+      constexpr int VPR = FE / N;
+      for (int i = threadIdx.x; i < C * VPR; i += BG_THREADS) {
+        int row = i / VPR, part = i % VPR;
+        Vec<T> o_, d_;
+        float inv = 0.f;
+        if (row < valid) {
+          o_.load(out + obase + (int64_t)(t0 + row) * ld_out + part * N);
+          d_.load(dout + obase + (int64_t)(t0 + row) * ld_out + part * N);
+          inv = 1.f / den_in[((int64_t)b * Tlen + t0 + row) * H + h];
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) { o_.v[j] = 0.f; d_.v[j] = 0.f; }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { dot += o_.v[j] * d_.v[j]; sm.g[row][part * N + j] = from_f<T>(d_.v[j] * inv); }
+#pragma unroll
+        for (int o = VPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (part == 0) {
+          sm.g[row][FE] = from_f<T>(-dot * inv);
+#pragma unroll
+          for (int j = FE + 1; j < FV; ++j) sm.g[row][j] = from_f<T>(0.f);
+        }
+      }
+    }
+    __syncthreads();
+    phi_rows<T, C>(sm.xq, sm.om, sm.oq, valid, sm.pq);
+    phi_rows<T, C>(sm.xk, sm.om, sm.ok, valid, sm.pk);
+    __syncthreads();
+    {  // roll the prefix state back to the start of this chunk
+      BlockGemm<FM, FV, T> tmp;
+      tmp.clear();
+      tmp.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
+      constexpr int NA = sizeof(gs.acc) / sizeof(float);
+      float* a = reinterpret_cast<float*>(gs.acc);
+      const float* t = reinterpret_cast<const float*>(tmp.acc);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) a[i] -= t[i];
+      gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
+    }
+    {
+      BlockGemm<C, C, T> ga;
+      ga.clear();
+      ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
+      ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
+      ga.clear();
+      ga.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &sm.v[0][0], bg_ld<T>(FV), FV);
+      ga.foreach ([&](int row, int col, float& x) { sm.p[row][col] = from_f<T>(col <= row ? x : 0.f); });
+    }
+    __syncthreads();
+    // ---- dq ----
+    {
+      BlockGemm<C, FM, T> gd;
+      gd.clear();
+      gd.template mma<true, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pk[0][0], bg_ld<T>(FM), C);
+      gd.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &sm.s[0][0], bg_ld<T>(FV), FV);
+      gd.foreach ([&](int row, int col, float& x) { sm.w[row][col] = from_f<T>(x * to_f(sm.pq[row][col])); });
+    }
+    __syncthreads();
+    phi_bwd_reduce<T, C>(sm);
+    __syncthreads();
+    {
+      BlockGemm<C, FE, T> gx;
+      gx.clear();
+      gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      gx.foreach ([&](int row, int col, float& x) {
+        sm.st[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(sm.xq[row][col]));
+      });
+    }
+    __syncthreads();
+    store_rows<T, C>(dq + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    // ---- dk ----
+    {
+      BlockGemm<C, FM, T> gd;
+      gd.clear();
+      gd.template mma<false, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pq[0][0], bg_ld<T>(FM), C);
+      gd.template mma<true, true>(&sm.v[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV), FV);
+      gd.foreach ([&](int row, int col, float& x) { sm.w[row][col] = from_f<T>(x * to_f(sm.pk[row][col])); });
+    }
+    __syncthreads();
+    phi_bwd_reduce<T, C>(sm);
+    __syncthreads();
+    {
+      BlockGemm<C, FE, T> gx;
+      gx.clear();
+      gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      gx.foreach ([&](int row, int col, float& x) {
+        sm.st[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(sm.xk[row][col]));
+      });
+    }
+    __syncthreads();
+    store_rows<T, C>(dk + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    __syncthreads();
+    // ---- dv ----
+    {
+      BlockGemm<C, FV, T> gv;
+      gv.clear();
+      gv.template mma<false, false>(&sm.a[0][0], bg_ld<T>(C), &sm.g[0][0], bg_ld<T>(FV), C);
+      gv.template mma<true, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.r[0][0], bg_ld<T>(FV), FM);
+      gv.foreach ([&](int row, int col, float& x) { if (col < FE) sm.st[row][col] = from_f<T>(x); });
+    }
+    __syncthreads();
+    store_rows<T, C>(dv + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    // ---- reverse state ----
+    gr.template mma<false, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.g[0][0], bg_ld<T>(FV), C);
+    gr.foreach ([&](int row, int col, float& x) { sm.r[row][col] = from_f<T>(x); });
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode step (recurrent form): one CTA of 128 threads per (sequence, head)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                         const T* __restrict__ v, int64_t ld,
+                                                         const float* __restrict__ omega, float* __restrict__ state,
+                                                         T* __restrict__ out, int64_t ld_out, int H) {
+  __shared__ float xq[FE], xk[FE], vv[FE + 1], pq[FM], pk[FM], red[4][FE + 1];
+  const int b = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x;
+  const float s = 0.35355339059327373f;
+  if (tid < FE) {
+    xq[tid] = to_f(q[(int64_t)b * ld + h * FE + tid]) * s;
+    xk[tid] = to_f(k[(int64_t)b * ld + h * FE + tid]) * s;
+    vv[tid] = to_f(v[(int64_t)b * ld + h * FE + tid]);
+  }
+  if (tid == 0) vv[FE] = 1.f;
+  __syncthreads();
+  {  // thread f<64 -> q feature f ; thread 64+f -> k feature f
+    const float* x = (tid < FE) ? xq : xk;
+    int f = tid & (FE - 1);
+    float u = 0.f, n2 = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < FE; ++e) { u = fmaf(x[e], omega[e * FE + f], u); n2 = fmaf(x[e], x[e], n2); }
+    float o = 0.5f * n2 + F_HALF_LOG_M;
+    float* p = (tid < FE) ? pq : pk;
+    p[f] = expf(u - o);
+    p[FE + f] = expf(-u - o);
+  }
+  __syncthreads();
+  // thread i owns state row i (feature i): update, then contribute to the output reduction
+  float* srow = state + ((int64_t)blockIdx.x * FM + tid) * FV;
+  float pki = pk[tid], pqi = pq[tid];
+  float part[FE + 1];
+#pragma unroll
+  for (int c = 0; c <= FE; ++c) {
+    float sv = srow[c] + pki * vv[c];
+    srow[c] = sv;
+    part[c] = pqi * sv;
+  }
+  // reduce over the 128 features: warp shuffle then across 4 warps
+#pragma unroll
+  for (int c = 0; c <= FE; ++c) {
+    float x = warp_sum(part[c]);
+    if ((tid & 31) == 0) red[tid >> 5][c] = x;
+  }
+  __syncthreads();
+  if (tid < FE) {
+    float num = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    float den = red[0][FE] + red[1][FE] + red[2][FE] + red[3][FE] + F_EPS;
+    out[(int64_t)b * ld_out + h * FE + tid] = from_f<T>(num / den);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
+                            int64_t ld_out, float* den, float* state_out, int B, int T_, int H, cudaStream_t s) {
+  constexpr int C = FavorCfg<T>::C;
+  size_t smem = sizeof(FavorSmemFwd<T, C>);
+  EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  favor_fwd_kernel<T><<<B * H, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
+                                                      den, state_out, T_, H);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+template <typename T>
+static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega,
+                            const void* out, const void* dout, int64_t ld_out, const float* den,
+                            const float* state_in, void* dq, void* dk, void* dv, int64_t ld_d, int B, int T_, int H,
+                            cudaStream_t s) {
+  constexpr int C = FavorCfg<T>::C;
+  size_t smem = sizeof(FavorSmemBwd<T, C>);
+  EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  favor_bwd_kernel<T><<<B * H, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (const T*)out,
+                                                      (const T*)dout, ld_out, den, state_in, (T*)dq, (T*)dk, (T*)dv,
+                                                      ld_d, T_, H);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                             void* out, int64_t ld_out, float* den, float* state_out, int B, int T, int H, int dtype,
+                             void* stream) {
+  int esz = dtype == EMO_BF16 ? 2 : 4;
+  EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "emo_favor_fwd: pointers must be 16-byte aligned");
+  EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0, "emo_favor_fwd: row strides must be 16-byte multiples");
+  if (B * H == 0 || T == 0) return EMO_OK;
+  if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_out, B, T, H, (cudaStream_t)stream);
+  return favor_fwd_launch<float>(q, k, v, ld_qkv, omega, out, ld_out, den, state_out, B, T, H, (cudaStream_t)stream);
+}
+
+extern "C" int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                             const void* out, const void* dout, int64_t ld_out, const float* den,
+                             const float* state_in, void* dq, void* dk, void* dv, int64_t ld_dqkv, int B, int T,
+                             int H, int dtype, void* stream) {
+  int esz = dtype == EMO_BF16 ? 2 : 4;
+  EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out) && aligned16(dout) && aligned16(dq) &&
+                  aligned16(dk) && aligned16(dv), "emo_favor_bwd: pointers must be 16-byte aligned");
+  EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0 && (ld_dqkv * esz) % 16 == 0,
+              "emo_favor_bwd: row strides must be 16-byte multiples");
+  EMO_REQUIRE(den != nullptr && state_in != nullptr, "emo_favor_bwd: den and state_in are required");
+  if (B * H == 0 || T == 0) return EMO_OK;
+  if (dtype == EMO_BF16)
+    return favor_bwd_launch<bf16>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, state_in, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
+  return favor_bwd_launch<float>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, state_in, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
+}
+
+extern "C" int emo_favor_step(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                              float* state, void* out, int64_t ld_out, int B, int H, int dtype, void* stream) {
+  if (B * H == 0) return EMO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == EMO_BF16)
+    favor_step_kernel<bf16><<<B * H, 128, 0, s>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, ld_qkv, omega, state, (bf16*)out, ld_out, H);
+  else
+    favor_step_kernel<float><<<B * H, 128, 0, s>>>((const float*)q, (const float*)k, (const float*)v, ld_qkv, omega, state, (float*)out, ld_out, H);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}

@@ -1,0 +1,250 @@
+"""Thin tensor->pointer wrappers over the C ABI (include/emo_b200.h).  torch tensors are storage
+only: every function here launches hand-written sm_100a kernels on torch's current stream."""
+import ctypes as C
+import torch
+
+from . import _lib as L
+from ._lib import F32, BF16, GEMM_NT, GEMM_NN, GEMM_TN, ACT_NONE, ACT_RELU, ACT_GELU_NEW, \
+    ACT_RELU_MASK_BWD, ACT_GELU_NEW_BWD  # noqa: F401
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("emo ops take float32 or bfloat16 tensors, got %s" % t.dtype)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.EmoError("emo ops need CUDA tensors: the hot path has no CPU implementation")
+
+
+def embed_fwd(tok, seg, e_tok, e_seg, pe, out, scale, drop_p=0.0, seed=0, batch_first=True):
+    """tok/seg int64 [B,T] (batch_first) or [T,B]; out [B,T,d]."""
+    _need_cuda(tok, e_tok, out)
+    if batch_first:
+        B, T = tok.shape
+        sb, st = tok.stride(0), tok.stride(1)
+    else:
+        T, B = tok.shape
+        sb, st = tok.stride(1), tok.stride(0)
+    if seg is not None:
+        assert seg.stride() == tok.stride() and seg.dtype == torch.int64
+    assert tok.dtype == torch.int64
+    d = e_tok.shape[1]
+    L.check(L.lib().emo_embed_fwd(_p(tok), _p(seg), sb, st, _p(e_tok), _p(e_seg), _p(pe), _p(out), B, T, d,
+                                  float(scale), float(drop_p), int(seed), _dt(out), _stream()), "emo_embed_fwd")
+    return out
+
+
+def embed_bwd(tok, seg, dout, d_e_tok, d_e_seg, scale, drop_p=0.0, seed=0, pad_idx=-1, batch_first=True):
+    if batch_first:
+        B, T = tok.shape
+        sb, st = tok.stride(0), tok.stride(1)
+    else:
+        T, B = tok.shape
+        sb, st = tok.stride(1), tok.stride(0)
+    d = d_e_tok.shape[1]
+    L.check(L.lib().emo_embed_bwd(_p(tok), _p(seg), sb, st, _p(dout), _p(d_e_tok), _p(d_e_seg), B, T, d,
+                                  float(scale), float(drop_p), int(seed), int(pad_idx), _dt(dout), _stream()),
+            "emo_embed_bwd")
+
+
+def ln_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
+    rows = x.numel() // x.shape[-1]
+    L.check(L.lib().emo_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, x.shape[-1], eps,
+                               _dt(x), _stream()), "emo_ln_fwd")
+    return y
+
+
+def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0):
+    rows = x.numel() // x.shape[-1]
+    L.check(L.lib().emo_ln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(add_in), _p(dx), _p(dx_drop),
+                               float(drop_p), int(seed), _p(dgamma), _p(dbeta), rows, x.shape[-1], _dt(x),
+                               _stream()), "emo_ln_bwd")
+
+
+def dropout_apply(x, y, drop_p, seed):
+    L.check(L.lib().emo_dropout_apply(_p(x), _p(y), x.numel(), float(drop_p), int(seed), _dt(x), _stream()),
+            "emo_dropout_apply")
+    return y
+
+
+def gemm(op, M, N, K, A, lda, B, ldb, Cmat, ldc, bias=None, act=ACT_NONE, aux=None, aux_out=None, ld_aux=0,
+         aux_scale=1.0, drop_p=0.0, seed=0, residual=None, ld_res=0, alpha=1.0, accumulate=False):
+    """Raw GEMM call; A/B/Cmat are tensors (or (tensor, element_offset) handled by the caller via views)."""
+    _need_cuda(A, B, Cmat)
+    e = L.Epilogue(_p(bias), act, _p(aux), _p(aux_out), ld_aux, aux_scale, drop_p, int(seed), _p(residual), ld_res,
+                   alpha, 1 if accumulate else 0, None)
+    assert A.dtype == B.dtype
+    L.check(L.lib().emo_gemm(op, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, _dt(A), _dt(Cmat), C.byref(e),
+                             _stream()), "emo_gemm")
+    return Cmat
+
+
+def linear_fwd(x, w, out, bias=None, **kw):
+    """out[M,N] = x[M,K] . w[N,K]^T (+epilogue); 2-D row-major views (last stride 1)."""
+    M, K = x.shape
+    N = w.shape[0]
+    return gemm(GEMM_NT, M, N, K, x, x.stride(0), w, w.stride(0), out, out.stride(0), bias=bias, **kw)
+
+
+def linear_fwd_t(x, w_t, out, bias=None, **kw):
+    """out[M,N] = x[M,K] . w_t[K,N]  (HF Conv1D weight layout [in,out])."""
+    M, K = x.shape
+    N = w_t.shape[1]
+    return gemm(GEMM_NN, M, N, K, x, x.stride(0), w_t, w_t.stride(0), out, out.stride(0), bias=bias, **kw)
+
+
+def linear_dgrad(dy, w, dx, **kw):
+    """dx[M,K] = dy[M,N] . w[N,K]."""
+    M, N = dy.shape
+    K = w.shape[1]
+    return gemm(GEMM_NN, M, K, N, dy, dy.stride(0), w, w.stride(0), dx, dx.stride(0), **kw)
+
+
+def linear_dgrad_t(dy, w_t, dx, **kw):
+    """dx[M,K] = dy[M,N] . w_t[K,N]^T  (Conv1D layout)."""
+    M, N = dy.shape
+    K = w_t.shape[0]
+    return gemm(GEMM_NT, M, K, N, dy, dy.stride(0), w_t, w_t.stride(0), dx, dx.stride(0), **kw)
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] (fp32) += dy[M,N]^T . x[M,K]."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return gemm(GEMM_TN, N, K, M, dy, dy.stride(0), x, x.stride(0), dw, dw.stride(0), accumulate=True)
+
+
+def linear_wgrad_t(dy, x, dw_t):
+    """dw_t[K,N] (fp32) += x[M,K]^T . dy[M,N]  (Conv1D layout)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return gemm(GEMM_TN, K, N, M, x, x.stride(0), dy, dy.stride(0), dw_t, dw_t.stride(0), accumulate=True)
+
+
+def colsum(x, out, n=None):
+    M = x.shape[0]
+    N = x.shape[1] if n is None else n
+    L.check(L.lib().emo_colsum(_p(x), x.stride(0), M, N, _p(out), _dt(x), _stream()), "emo_colsum")
+
+
+def favor_fwd(q, k, v, omega, out, den=None, state_out=None):
+    """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view."""
+    B, T, H, E = q.shape
+    assert E == 64 and q.stride(3) == 1 and q.stride(2) == 64 and q.stride(0) == T * q.stride(1)
+    assert k.stride() == q.stride() and v.stride() == q.stride()
+    L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), out.stride(-2), _p(den),
+                                  _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
+    return out
+
+
+def favor_bwd(q, k, v, omega, out, dout, den, state, dq, dk, dv):
+    B, T, H, E = q.shape
+    assert dq.stride() == dk.stride() == dv.stride()
+    L.check(L.lib().emo_favor_bwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), _p(dout), out.stride(-2),
+                                  _p(den), _p(state), _p(dq), _p(dk), _p(dv), dq.stride(1), B, T, H, _dt(q),
+                                  _stream()), "emo_favor_bwd")
+
+
+def favor_step(q, k, v, omega, state, out):
+    """q,k,v: [B,H,64] views (sequence stride = stride(0)); state [B,H,128,80] fp32; out [B,H*64]."""
+    B, H, E = q.shape
+    L.check(L.lib().emo_favor_step(_p(q), _p(k), _p(v), q.stride(0), _p(omega), _p(state), _p(out), out.stride(0),
+                                   B, H, _dt(q), _stream()), "emo_favor_step")
+    return out
+
+
+def attn_fwd(q, k, v, out, lse, scale, drop_p=0.0, seed=0):
+    B, Tq, H, E = q.shape
+    Tk = k.shape[1]
+    L.check(L.lib().emo_attn_fwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), out.stride(-2), _p(lse),
+                                 B, Tq, Tk, H, scale, drop_p, int(seed), _dt(q), _stream()), "emo_attn_fwd")
+    return out
+
+
+def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale, drop_p=0.0, seed=0):
+    B, Tq, H, E = q.shape
+    Tk = k.shape[1]
+    L.check(L.lib().emo_attn_bwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), _p(dout), out.stride(-2),
+                                 _p(lse), _p(dq), _p(dk), _p(dv), dq.stride(1), dk.stride(1), B, Tq, Tk, H, scale,
+                                 drop_p, int(seed), _dt(q), _stream()), "emo_attn_bwd")
+
+
+def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale):
+    B, Tq, H, E = q.shape
+    Tk = k.shape[1]
+    L.check(L.lib().emo_relattn_fwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
+                                    _p(r_r_bias), _p(out), out.stride(-2), _p(lse), B, Tq, Tk, H, scale, _dt(q),
+                                    _stream()), "emo_relattn_fwd")
+    return out
+
+
+def relattn_bwd(q, k, v, r, r_w_bias, r_r_bias, out, dout, lse, dq, dk, dv, dr, d_rw, d_rr, scale):
+    B, Tq, H, E = q.shape
+    Tk = k.shape[1]
+    L.check(L.lib().emo_relattn_bwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
+                                    _p(r_r_bias), _p(out), _p(dout), out.stride(-2), _p(lse), _p(dq), _p(dk), _p(dv),
+                                    dq.stride(1), dk.stride(1), _p(dr), _p(d_rw), _p(d_rr), B, Tq, Tk, H, scale,
+                                    _dt(q), _stream()), "emo_relattn_bwd")
+
+
+def _tgt_layout(tgt, batch_first):
+    """rows are enumerated batch-major (r = b*T + t) to match the [B,T,.] activations."""
+    if batch_first:
+        B, T = tgt.shape
+        return B * T, T, tgt.stride(0), tgt.stride(1)
+    T, B = tgt.shape
+    return B * T, T, tgt.stride(1), tgt.stride(0)
+
+
+def ce_count(tgt, ignore_index, count, batch_first=True):
+    rows, inner, so, si = _tgt_layout(tgt, batch_first)
+    L.check(L.lib().emo_ce_count(_p(tgt), rows, inner, so, si, int(ignore_index), _p(count), _stream()),
+            "emo_ce_count")
+
+
+def ce_fwd_bwd(logits, tgt, V, ignore_index, count, loss_sum, ncorrect=None, pred=None, dlogits=None, gscale=1.0,
+               batch_first=True):
+    """logits fp32 [rows, ld] (rows batch-major); dlogits [rows, ld_dl] or None."""
+    rows, inner, so, si = _tgt_layout(tgt, batch_first)
+    assert logits.dtype == torch.float32 and logits.shape[0] == rows
+    L.check(L.lib().emo_ce_fwd_bwd(_p(logits), logits.stride(0), _p(tgt), rows, inner, so, si, V, int(ignore_index),
+                                   _p(count), float(gscale), _p(loss_sum), _p(ncorrect), _p(pred), _p(dlogits),
+                                   0 if dlogits is None else dlogits.stride(0),
+                                   F32 if dlogits is None else _dt(dlogits), _stream()), "emo_ce_fwd_bwd")
+
+
+def sumsq(g, out):
+    L.check(L.lib().emo_sumsq(_p(g), g.numel(), _p(out), _stream()), "emo_sumsq")
+
+
+def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0,
+              zero_grad=False):
+    L.check(L.lib().emo_adam_step(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), p.numel(), lr, beta1, beta2, eps,
+                                  int(step), _p(gnorm_sq), float(max_norm), float(grad_scale), 1 if zero_grad else 0,
+                                  _stream()), "emo_adam_step")
+
+
+def cast(src, dst):
+    L.check(L.lib().emo_cast(_p(src), _p(dst), src.numel(), _dt(src), _dt(dst), _stream()), "emo_cast")
+    return dst
+
+
+def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False):
+    rows = logits.shape[0]
+    L.check(L.lib().emo_sample(_p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
+                               1 if greedy else 0, _p(out), _p(status), _stream()), "emo_sample")
+    return out

@@ -1,0 +1,197 @@
+/* libemo_b200.so -- C ABI of the B200-native EMO-Disentanger hot path.
+ *
+ * The reference (Yuer867/EMO-Disentanger) has no FFI of its own: its operator boundary is the
+ * Python nn.Module surface plus the third-party ops it calls.  Each entry point below replaces
+ * one such operator; the citation gives the reference call site (paths relative to the
+ * reference repo) or the third-party operator it stands in for.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the caller
+ *     (PyTorch tensors used as storage), including workspaces; the library keeps no tensor memory.
+ *   - stream-ordered and asynchronous: no internal synchronisation; `stream` is a cudaStream_t
+ *     passed as void*.
+ *   - returns 0 on success, non-zero emo_status otherwise; message via emo_last_error()
+ *     (thread-local).  Never throws, never exits.
+ *   - dtype: EMO_F32 or EMO_BF16 for activations; parameters / optimizer state are fp32 masters
+ *     (bf16 shadow copies are produced by emo_adam_step / emo_cast).
+ *   - model geometry is the reference's: d_model 512, 8 heads x 64, FAVOR n_dims 128.
+ */
+#ifndef EMO_B200_H
+#define EMO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { EMO_OK = 0, EMO_ERR_ARG = 1, EMO_ERR_CUDA = 2, EMO_ERR_UNSUPPORTED = 3 } emo_status;
+typedef enum { EMO_F32 = 0, EMO_BF16 = 1 } emo_dtype;
+
+int emo_version(void);
+const char* emo_last_error(void);
+
+/* ---- A1: embedding front-end --------------------------------------------------------------
+ * stage2_accompaniment/model/music_performer.py:51-62 + transformer_helpers.py:57-63,81-87
+ * (identical in music_gpt2.py:71-82); stage1_compose/model/plain_transformer.py:61-62.
+ * out[b,t,:] = dropout( (E_tok[tok] + E_seg[seg]) * scale + pe[t] ).  tok/seg are int64 with
+ * element (b,t) at tok[b*stride_b + t*stride_t] (stage 1 passes its [T,B] layout by strides).
+ * e_seg / seg / pe may be NULL.  out is [B,T,d] contiguous. */
+int emo_embed_fwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
+                  const float* e_tok, const float* e_seg, const float* pe, void* out,
+                  int B, int T, int d, float scale, float drop_p, uint64_t seed,
+                  int out_dtype, void* stream);
+/* d_e_tok[tok] += dout*scale*mask (fp32 atomics); rows == pad_idx get no gradient (pass -1 for
+ * none: nn.Embedding(padding_idx) in stage1 transformer_helpers.py:104-108). */
+int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
+                  const void* dout, float* d_e_tok, float* d_e_seg, int B, int T, int d,
+                  float scale, float drop_p, uint64_t seed, int64_t pad_idx, int dtype,
+                  void* stream);
+
+/* ---- A3/A7/A9: LayerNorm (eps 1e-5) over the last dim d=512 -------------------------------
+ * fast_transformers TransformerEncoderLayer.norm1/norm2, HF GPT2Block.ln_1/ln_2,
+ * optimus_txl_decoder.py:52,318.  Saves mean/rstd (fp32 [rows]) for backward. */
+int emo_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+               float* rstd, int64_t rows, int d, float eps, int dtype, void* stream);
+/* dx = LNgrad(dy) (+ add_in if non-NULL).  If dx_drop != NULL also writes
+ * dx_drop = dx * dropmask(seed)/(1-p) (gradient entering a `x + dropout(proj)` branch).
+ * dgamma/dbeta (fp32 [d]) are ACCUMULATED (atomics). */
+int emo_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+               const float* gamma, const void* add_in, void* dx, void* dx_drop, float drop_p,
+               uint64_t seed, float* dgamma, float* dbeta, int64_t rows, int d, int dtype,
+               void* stream);
+/* y = dropmask(seed)/(1-p) * x  (elementwise helper for branches without an LN in between) */
+int emo_dropout_apply(const void* x, void* y, int64_t n, float drop_p, uint64_t seed, int dtype,
+                      void* stream);
+
+/* ---- A3/A4/A7/A8/A9: dense projections -----------------------------------------------------
+ * nn.Linear / HF Conv1D call sites: AttentionLayer.{query,key,value,out}_projection,
+ * TransformerEncoderLayer.linear1/2, GPT2 c_attn/c_proj/c_fc, qkv_net/r_net/o_net/CoreNet,
+ * dec_out_proj (music_performer.py:65).  bf16 inputs run on tcgen05 tensor cores
+ * (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue); fp32 inputs run a SIMT fp32 kernel (the
+ * 1e-3 parity mode).  Three contractions, row-major operands, leading dims in elements:
+ *   EMO_GEMM_NT: C[M,N] = A[M,K] . B[N,K]^T     (forward with nn.Linear weight [out,in])
+ *   EMO_GEMM_NN: C[M,N] = A[M,K] . B[K,N]       (dgrad; forward with Conv1D weight [in,out])
+ *   EMO_GEMM_TN: C[M,N] = A[K,M]^T . B[K,N]     (wgrad: reduction over tokens)
+ * Epilogue, in this order: v = alpha*acc + bias[n]; activation; dropout(seed); + residual;
+ * then either store (out_dtype) or atomically accumulate into fp32 C (accumulate=1). */
+typedef enum { EMO_GEMM_NT = 0, EMO_GEMM_NN = 1, EMO_GEMM_TN = 2 } emo_gemm_op;
+typedef enum {
+  EMO_ACT_NONE = 0,
+  EMO_ACT_RELU = 1,
+  EMO_ACT_GELU_NEW = 2,      /* writes pre-activation to aux_out if non-NULL               */
+  EMO_ACT_RELU_MASK_BWD = 3, /* v *= (aux[m,n] != 0) ? aux_scale : 0   (relu+dropout bwd)    */
+  EMO_ACT_GELU_NEW_BWD = 4   /* v *= gelu_new'(aux[m,n])                                     */
+} emo_act;
+typedef struct {
+  const float* bias;    /* [N] fp32 or NULL                                                   */
+  int act;              /* emo_act                                                            */
+  const void* aux;      /* [M, ld_aux] in the input dtype (acts 3, 4)                         */
+  void* aux_out;        /* [M, ld_aux] in the output dtype (act 2), may be NULL               */
+  int64_t ld_aux;
+  float aux_scale;      /* act 3: 1/(1-p)                                                     */
+  float drop_p;         /* forward dropout after the activation (0 = off)                     */
+  uint64_t seed;
+  const void* residual; /* [M, ld_res] in the output dtype, added last; may be NULL           */
+  int64_t ld_res;
+  float alpha;
+  int accumulate;       /* 1: C (fp32) += result                                             */
+  const void* rowscale; /* optional fp32 [M]: v *= rowscale[m] before bias (unused = NULL)    */
+} emo_epilogue;
+int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+             int64_t ldb, void* C, int64_t ldc, int in_dtype, int out_dtype,
+             const emo_epilogue* epi, void* stream);
+/* column sums: out[n] += sum_m x[m,n]  (bias gradients), fp32 accumulate with atomics */
+int emo_colsum(const void* x, int64_t ld, int64_t M, int64_t N, float* out, int dtype,
+               void* stream);
+
+/* ---- A5/A6: FAVOR+ feature map + causal linear attention ----------------------------------
+ * fast_transformers.feature_maps.Favor.forward + attention.CausalLinearAttention.forward +
+ * causal_product.causal_dot_product (the only native extension on the reference path), as
+ * built by stage2_accompaniment/model/fast_transformer_decoder.py:28-38.
+ * q,k,v: [B,T,H,64] with token row stride ld_qkv (slices of one packed [B*T, 3*512] buffer);
+ * omega [64,64] fp32 (row = input dim, col = feature); phi is recomputed in-kernel and never
+ * written to HBM.  out [B,T,H*64] (ld_out); den [B,T,H] fp32 = phi(q).cumsum(phi(k)) + 1e-6;
+ * state_out (may be NULL) [B,H,128,80] fp32: final prefix state [sum phi(k) v^T | sum phi(k) | 0]. */
+int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                  void* out, int64_t ld_out, float* den, float* state_out, int B, int T, int H,
+                  int dtype, void* stream);
+/* reverse-scan backward; state_in = state_out of the forward call. */
+int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                  const void* out, const void* dout, int64_t ld_out, const float* den,
+                  const float* state_in, void* dq, void* dk, void* dv, int64_t ld_dqkv, int B,
+                  int T, int H, int dtype, void* stream);
+/* one decode step per sequence (recurrent form): state [B,H,128,80] fp32 updated in place;
+ * q,k,v rows for the new token [B,H,64] (row stride ld_qkv per sequence). */
+int emo_favor_step(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
+                   float* state, void* out, int64_t ld_out, int B, int H, int dtype, void* stream);
+
+/* ---- A7: GPT-2 causal softmax attention ---------------------------------------------------
+ * HF GPT2Attention._attn (4.28.0): softmax(q k^T / 8 + causal) v with attention-prob dropout.
+ * q [B,Tq,H,64], k,v [B,Tk,H,64] (row strides ld_q / ld_kv); query i sees keys j <= i + (Tk-Tq).
+ * lse [B,H,Tq] fp32 saved for backward. */
+int emo_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                 void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk, int H, float scale,
+                 float drop_p, uint64_t seed, int dtype, void* stream);
+int emo_attn_bwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                 const void* out, const void* dout, int64_t ld_out, const float* lse, void* dq,
+                 void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, int B, int Tq, int Tk, int H,
+                 float scale, float drop_p, uint64_t seed, int dtype, void* stream);
+
+/* ---- A9: stage-1 relative-position attention ----------------------------------------------
+ * optimus_txl_decoder.py:305-387: score(i,j) = ((q_i+r_w_bias).k_j + (q_i+r_r_bias).r_{dist})/8,
+ * dist = i + mlen - j (>= 0 visible), softmax, (dropatt), renormalise /(sum+1e-8), . v.
+ * q [B,Tq,H,64]; k,v [B,Tk,H,64]; r [Tk,H,64] with row p holding distance Tk-1-p (as r_net of
+ * pos_emb for pos_seq = Tk-1..0, :792-796); biases [H,64] fp32. */
+int emo_relattn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                    const void* r, int64_t ld_r, const float* r_w_bias, const float* r_r_bias,
+                    void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk, int H,
+                    float scale, int dtype, void* stream);
+int emo_relattn_bwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                    const void* r, int64_t ld_r, const float* r_w_bias, const float* r_r_bias,
+                    const void* out, const void* dout, int64_t ld_out, const float* lse,
+                    void* dq, void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, float* dr,
+                    float* d_r_w_bias, float* d_r_r_bias, int B, int Tq, int Tk, int H,
+                    float scale, int dtype, void* stream);
+
+/* ---- A8: cross-entropy over the vocabulary -------------------------------------------------
+ * compute_loss (music_performer.py:72-81, music_gpt2.py:94-103, plain_transformer.py:82-93):
+ * mean NLL over targets != ignore_index.  logits fp32 [rows, ld]; tgt int64 with element r at
+ * tgt[(r / tgt_inner) * tgt_stride_outer + (r % tgt_inner) * tgt_stride_inner].
+ * emo_ce_count: count[0] += #(tgt != ignore).   emo_ce_fwd_bwd: loss_sum[0] += sum NLL;
+ * ncorrect[0] += #(argmax == tgt) over non-ignored rows; pred[r] = argmax (may be NULL);
+ * dlogits (may be NULL; dtype dl_dtype, ld_dl) = gscale * (softmax - onehot) / count[0], zero on
+ * ignored rows and on pad columns [V, ld_dl). */
+int emo_ce_count(const int64_t* tgt, int64_t rows, int64_t tgt_inner, int64_t tgt_stride_outer,
+                 int64_t tgt_stride_inner, int64_t ignore_index, float* count, void* stream);
+int emo_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* tgt, int64_t rows,
+                   int64_t tgt_inner, int64_t tgt_stride_outer, int64_t tgt_stride_inner, int V,
+                   int64_t ignore_index, const float* count, float gscale, float* loss_sum,
+                   float* ncorrect, int32_t* pred, void* dlogits, int64_t ld_dl, int dl_dtype,
+                   void* stream);
+
+/* ---- A10: clip_grad_norm_ + Adam on flat fp32 buffers --------------------------------------
+ * stage2_accompaniment/train.py:79-81,318-322; stage1_compose/train.py:63-65,287-293.
+ * emo_sumsq: out[0] += sum g^2.  emo_adam_step: coef = min(1, max_norm/(sqrt(gnorm_sq[0])+1e-6))
+ * (max_norm <= 0 disables clipping), torch.optim.Adam update (no weight decay, no amsgrad) with
+ * bias corrections for `step` (1-based); optionally emits the bf16 shadow copy of the params and
+ * zeroes the gradient buffer for the next step. */
+int emo_sumsq(const float* g, int64_t n, float* out, void* stream);
+int emo_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t step, const float* gnorm_sq,
+                  float max_norm, float grad_scale, int zero_grad, void* stream);
+int emo_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
+/* ---- A12: temperature + nucleus sampling ---------------------------------------------------
+ * stage2_accompaniment/inference.py:71-100, stage1_compose/inference_utils.py:14-41.
+ * logits fp32 [rows, ld] (V <= 1024).  greedy != 0 -> argmax (bit-exact decode mode; lowest
+ * index wins ties like numpy.argmax).  Otherwise softmax(l/t), descending sort, cut at the second
+ * index whose cumulative mass exceeds top_p (top-3 fallback), renormalise, inverse-CDF draw with
+ * the caller-provided uniform u[row] in [0,1).  out int64 [rows]; status[row] = 1 when exactly
+ * one index exceeded top_p (the reference raises IndexError there). */
+int emo_sample(const float* logits, int64_t ld, int rows, int V, float temperature, float top_p,
+               const float* u, int greedy, int64_t* out, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMO_B200_H */
