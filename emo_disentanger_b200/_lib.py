@@ -69,6 +69,11 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0     # C-ABI calls that returned EMO_OK (each launches one kernel of ours); read by bench.py
+
+
 def check(rc, what=""):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise EmoError("%s failed (status %d): %s" % (what, rc, lib().emo_last_error().decode()))

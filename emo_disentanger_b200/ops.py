@@ -24,6 +24,50 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-kernel-class CUDA-event timing on the launching (current) stream.  bench.py turns
+    it on for the classes it reports a roofline for; off (the default) it costs one dict lookup."""
+
+    def __init__(self):
+        self.classes = set()
+        self.events = {}
+
+    def enable(self, classes):
+        self.classes = set(classes)
+        self.events = {c: [] for c in self.classes}
+
+    def disable(self):
+        self.classes = set()
+
+    def start(self, cls):
+        if cls not in self.classes:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (cls, e0, e1)
+
+    def stop(self, tok, work=0.0):
+        if tok is not None:
+            tok[2].record()
+            self.events[tok[0]].append((tok[1], tok[2], work))
+
+    def summary(self):
+        """{class: (launches, total_ms, total_work)} -- call after a synchronize."""
+        return {c: (len(ev), sum(a.elapsed_time(b) for a, b, _ in ev), sum(w for _, _, w in ev))
+                for c, ev in self.events.items()}
+
+
+TIMER = KernelTimer()
+
+
+def _call(name, *args):
+    """one C-ABI call = one kernel launch; timed under its own name when bench.py asks for it"""
+    tk = TIMER.start(name)
+    L.check(getattr(L.lib(), name)(*args), name)
+    TIMER.stop(tk)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -43,8 +87,8 @@ def embed_fwd(tok, seg, e_tok, e_seg, pe, out, scale, drop_p=0.0, seed=0, batch_
         assert seg.stride() == tok.stride() and seg.dtype == torch.int64
     assert tok.dtype == torch.int64
     d = e_tok.shape[1]
-    L.check(L.lib().emo_embed_fwd(_p(tok), _p(seg), sb, st, _p(e_tok), _p(e_seg), _p(pe), _p(out), B, T, d,
-                                  float(scale), float(drop_p), int(seed), _dt(out), _stream()), "emo_embed_fwd")
+    _call("emo_embed_fwd", _p(tok), _p(seg), sb, st, _p(e_tok), _p(e_seg), _p(pe), _p(out), B, T, d,
+                                  float(scale), float(drop_p), int(seed), _dt(out), _stream())
     return out
 
 
@@ -56,28 +100,26 @@ def embed_bwd(tok, seg, dout, d_e_tok, d_e_seg, scale, drop_p=0.0, seed=0, pad_i
         T, B = tok.shape
         sb, st = tok.stride(1), tok.stride(0)
     d = d_e_tok.shape[1]
-    L.check(L.lib().emo_embed_bwd(_p(tok), _p(seg), sb, st, _p(dout), _p(d_e_tok), _p(d_e_seg), B, T, d,
-                                  float(scale), float(drop_p), int(seed), int(pad_idx), _dt(dout), _stream()),
-            "emo_embed_bwd")
+    _call("emo_embed_bwd", _p(tok), _p(seg), sb, st, _p(dout), _p(d_e_tok), _p(d_e_seg), B, T, d,
+                                  float(scale), float(drop_p), int(seed), int(pad_idx), _dt(dout), _stream())
 
 
 def ln_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     rows = x.numel() // x.shape[-1]
-    L.check(L.lib().emo_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, x.shape[-1], eps,
-                               _dt(x), _stream()), "emo_ln_fwd")
+    _call("emo_ln_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, x.shape[-1], eps,
+                               _dt(x), _stream())
     return y
 
 
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0):
     rows = x.numel() // x.shape[-1]
-    L.check(L.lib().emo_ln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(add_in), _p(dx), _p(dx_drop),
+    _call("emo_ln_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(add_in), _p(dx), _p(dx_drop),
                                float(drop_p), int(seed), _p(dgamma), _p(dbeta), rows, x.shape[-1], _dt(x),
-                               _stream()), "emo_ln_bwd")
+                               _stream())
 
 
 def dropout_apply(x, y, drop_p, seed):
-    L.check(L.lib().emo_dropout_apply(_p(x), _p(y), x.numel(), float(drop_p), int(seed), _dt(x), _stream()),
-            "emo_dropout_apply")
+    _call("emo_dropout_apply", _p(x), _p(y), x.numel(), float(drop_p), int(seed), _dt(x), _stream())
     return y
 
 
@@ -88,8 +130,10 @@ def gemm(op, M, N, K, A, lda, B, ldb, Cmat, ldc, bias=None, act=ACT_NONE, aux=No
     e = L.Epilogue(_p(bias), act, _p(aux), _p(aux_out), ld_aux, aux_scale, drop_p, int(seed), _p(residual), ld_res,
                    alpha, 1 if accumulate else 0, None)
     assert A.dtype == B.dtype
+    tk = TIMER.start("gemm")
     L.check(L.lib().emo_gemm(op, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, _dt(A), _dt(Cmat), C.byref(e),
                              _stream()), "emo_gemm")
+    TIMER.stop(tk, 2.0 * M * N * K)
     return Cmat
 
 
@@ -138,67 +182,71 @@ def linear_wgrad_t(dy, x, dw_t):
 def colsum(x, out, n=None):
     M = x.shape[0]
     N = x.shape[1] if n is None else n
-    L.check(L.lib().emo_colsum(_p(x), x.stride(0), M, N, _p(out), _dt(x), _stream()), "emo_colsum")
+    _call("emo_colsum", _p(x), x.stride(0), M, N, _p(out), _dt(x), _stream())
 
 
 def favor_fwd(q, k, v, omega, out, den=None, state_out=None):
     """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view."""
     B, T, H, E = q.shape
-    assert E == 64 and q.stride(3) == 1 and q.stride(2) == 64 and q.stride(0) == T * q.stride(1)
+    assert E == 64 and q.stride(3) == 1 and q.stride(2) == 64 and (B == 1 or q.stride(0) == T * q.stride(1))
     assert k.stride() == q.stride() and v.stride() == q.stride()
+    tk = TIMER.start("favor_fwd")
     L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), out.stride(-2), _p(den),
                                   _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
+    TIMER.stop(tk, float(B * T * H * 64 * 4 * q.element_size()))      # algorithmic bytes: read q,k,v + write out
     return out
 
 
 def favor_bwd(q, k, v, omega, out, dout, den, state, dq, dk, dv):
     B, T, H, E = q.shape
     assert dq.stride() == dk.stride() == dv.stride()
+    tk = TIMER.start("favor_bwd")
     L.check(L.lib().emo_favor_bwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), _p(dout), out.stride(-2),
                                   _p(den), _p(state), _p(dq), _p(dk), _p(dv), dq.stride(1), B, T, H, _dt(q),
                                   _stream()), "emo_favor_bwd")
+    TIMER.stop(tk, float(B * T * H * 64 * 8 * q.element_size()))      # read q,k,v,out,dout + write dq,dk,dv
 
 
 def favor_step(q, k, v, omega, state, out):
     """q,k,v: [B,H,64] views (sequence stride = stride(0)); state [B,H,128,80] fp32; out [B,H*64]."""
     B, H, E = q.shape
-    L.check(L.lib().emo_favor_step(_p(q), _p(k), _p(v), q.stride(0), _p(omega), _p(state), _p(out), out.stride(0),
-                                   B, H, _dt(q), _stream()), "emo_favor_step")
+    _call("emo_favor_step", _p(q), _p(k), _p(v), q.stride(0), _p(omega), _p(state), _p(out), out.stride(0),
+                                   B, H, _dt(q), _stream())
     return out
 
 
 def attn_fwd(q, k, v, out, lse, scale, drop_p=0.0, seed=0):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    L.check(L.lib().emo_attn_fwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), out.stride(-2), _p(lse),
-                                 B, Tq, Tk, H, scale, drop_p, int(seed), _dt(q), _stream()), "emo_attn_fwd")
+    _call("emo_attn_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), out.stride(-2), _p(lse),
+                                 B, Tq, Tk, H, scale, drop_p, int(seed), _dt(q), _stream())
     return out
 
 
 def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale, drop_p=0.0, seed=0):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    L.check(L.lib().emo_attn_bwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), _p(dout), out.stride(-2),
+    _call("emo_attn_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), _p(dout), out.stride(-2),
                                  _p(lse), _p(dq), _p(dk), _p(dv), dq.stride(1), dk.stride(1), B, Tq, Tk, H, scale,
-                                 drop_p, int(seed), _dt(q), _stream()), "emo_attn_bwd")
+                                 drop_p, int(seed), _dt(q), _stream())
 
 
 def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    L.check(L.lib().emo_relattn_fwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
+    _call("emo_relattn_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
                                     _p(r_r_bias), _p(out), out.stride(-2), _p(lse), B, Tq, Tk, H, scale, _dt(q),
-                                    _stream()), "emo_relattn_fwd")
+                                    _stream())
     return out
 
 
 def relattn_bwd(q, k, v, r, r_w_bias, r_r_bias, out, dout, lse, dq, dk, dv, dr, d_rw, d_rr, scale):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    L.check(L.lib().emo_relattn_bwd(_p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
+    _call("emo_relattn_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
                                     _p(r_r_bias), _p(out), _p(dout), out.stride(-2), _p(lse), _p(dq), _p(dk), _p(dv),
                                     dq.stride(1), dk.stride(1), _p(dr), _p(d_rw), _p(d_rr), B, Tq, Tk, H, scale,
-                                    _dt(q), _stream()), "emo_relattn_bwd")
+                                    _dt(q), _stream())
 
 
 def _tgt_layout(tgt, batch_first):
@@ -212,8 +260,7 @@ def _tgt_layout(tgt, batch_first):
 
 def ce_count(tgt, ignore_index, count, batch_first=True):
     rows, inner, so, si = _tgt_layout(tgt, batch_first)
-    L.check(L.lib().emo_ce_count(_p(tgt), rows, inner, so, si, int(ignore_index), _p(count), _stream()),
-            "emo_ce_count")
+    _call("emo_ce_count", _p(tgt), rows, inner, so, si, int(ignore_index), _p(count), _stream())
 
 
 def ce_fwd_bwd(logits, tgt, V, ignore_index, count, loss_sum, ncorrect=None, pred=None, dlogits=None, gscale=1.0,
@@ -221,30 +268,30 @@ def ce_fwd_bwd(logits, tgt, V, ignore_index, count, loss_sum, ncorrect=None, pre
     """logits fp32 [rows, ld] (rows batch-major); dlogits [rows, ld_dl] or None."""
     rows, inner, so, si = _tgt_layout(tgt, batch_first)
     assert logits.dtype == torch.float32 and logits.shape[0] == rows
-    L.check(L.lib().emo_ce_fwd_bwd(_p(logits), logits.stride(0), _p(tgt), rows, inner, so, si, V, int(ignore_index),
+    _call("emo_ce_fwd_bwd", _p(logits), logits.stride(0), _p(tgt), rows, inner, so, si, V, int(ignore_index),
                                    _p(count), float(gscale), _p(loss_sum), _p(ncorrect), _p(pred), _p(dlogits),
                                    0 if dlogits is None else dlogits.stride(0),
-                                   F32 if dlogits is None else _dt(dlogits), _stream()), "emo_ce_fwd_bwd")
+                                   F32 if dlogits is None else _dt(dlogits), _stream())
 
 
 def sumsq(g, out):
-    L.check(L.lib().emo_sumsq(_p(g), g.numel(), _p(out), _stream()), "emo_sumsq")
+    _call("emo_sumsq", _p(g), g.numel(), _p(out), _stream())
 
 
 def adam_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0,
               zero_grad=False):
-    L.check(L.lib().emo_adam_step(_p(p), _p(g), _p(m), _p(v), _p(p_bf16), p.numel(), lr, beta1, beta2, eps,
+    _call("emo_adam_step", _p(p), _p(g), _p(m), _p(v), _p(p_bf16), p.numel(), lr, beta1, beta2, eps,
                                   int(step), _p(gnorm_sq), float(max_norm), float(grad_scale), 1 if zero_grad else 0,
-                                  _stream()), "emo_adam_step")
+                                  _stream())
 
 
 def cast(src, dst):
-    L.check(L.lib().emo_cast(_p(src), _p(dst), src.numel(), _dt(src), _dt(dst), _stream()), "emo_cast")
+    _call("emo_cast", _p(src), _p(dst), src.numel(), _dt(src), _dt(dst), _stream())
     return dst
 
 
 def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False):
     rows = logits.shape[0]
-    L.check(L.lib().emo_sample(_p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
-                               1 if greedy else 0, _p(out), _p(status), _stream()), "emo_sample")
+    _call("emo_sample", _p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
+                               1 if greedy else 0, _p(out), _p(status), _stream())
     return out
