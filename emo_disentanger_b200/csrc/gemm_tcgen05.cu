@@ -4,7 +4,7 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> 4/6-stage smem ring
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16 (one elected lane), fp32
 //                              accumulators in TMEM, double-buffered (2 x BN columns)
-//   warps 2..5  epilogue       tcgen05.ld (32x32b.x32) -> bias / activation / dropout / residual
+//   warps 2..9  epilogue       tcgen05.ld (32x32b.x32) -> bias / activation / dropout / residual
 //                              -> 16-byte global stores, or fp32 atomic accumulate (split-K wgrad)
 // Tile 128 x BN (BN = 256 or 128) x 64.  Three contractions share the kernel through the operand
 // "major-ness" encoded in the TMA boxes, the smem descriptors and the instruction descriptor:
@@ -19,7 +19,7 @@ int emo_gemm_simt(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_
 namespace tc {
 
 constexpr int BM = 128, BK = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -105,6 +105,123 @@ struct Params {
   EpiParams ep;
 };
 
+
+// ---- epilogue of one 32-column chunk of one accumulator row (lane = row) -------------------------
+// Fast path: every branch below is warp-uniform and sits OUTSIDE the per-element loops; all global
+// accesses are 16-byte vectors.  Order of operations = include/emo_b200.h (emo_epilogue).
+template <typename TOut>
+__device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
+  const EpiParams& ep = p.ep;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (ep.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+  }
+  if (ep.rowscale) {
+    const float rs = ep.rowscale[m];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rs;
+  }
+  if (ep.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (ep.act == EMO_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (ep.act == EMO_ACT_GELU_NEW) {
+    if (ep.aux_out) {
+      TOut* arow = reinterpret_cast<TOut*>(ep.aux_out) + m * ep.ld_aux + nb;
+#pragma unroll
+      for (int j = 0; j < 32; j += Vec<TOut>::N) {
+        Vec<TOut> t;
+#pragma unroll
+        for (int i = 0; i < Vec<TOut>::N; ++i) t.v[i] = v[j + i];
+        t.store(arow + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+  } else if (ep.act == EMO_ACT_RELU_MASK_BWD || ep.act == EMO_ACT_GELU_NEW_BWD) {
+    const bf16* arow = reinterpret_cast<const bf16*>(ep.aux) + m * ep.ld_aux + nb;
+    float a[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      Vec<bf16> t;
+      t.load(arow + j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[j + i] = t.v[i];
+    }
+    if (ep.act == EMO_ACT_RELU_MASK_BWD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (a[j] != 0.f) ? v[j] * ep.aux_scale : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_f(a[j]);
+    }
+  }
+  if (ep.drop_thr) {
+    const uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
+    if ((e0 & 1) == 0 && ((e0 >> 33) == ((e0 + 31) >> 33))) {
+      // same value as emo_drop_hash(seed, e0 + j): the high half of the pair index is constant here
+      const uint32_t base = (uint32_t)ep.seed ^ emo_mix32((uint32_t)(e0 >> 33) + (uint32_t)(ep.seed >> 32) + 0x7f4a7c15u);
+      const uint32_t lo0 = (uint32_t)(e0 >> 1);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        uint32_t h = emo_mix32(((lo0 + (j >> 1)) * 0x9E3779B9u) ^ base);
+        v[j] = ((h & 0xffffu) >= ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
+        v[j + 1] = ((h >> 16) >= ep.drop_thr) ? v[j + 1] * ep.keep_scale : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = emo_drop_keep(ep.seed, e0 + j, ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
+    }
+  }
+  if (ep.accumulate) {
+    float* crow = reinterpret_cast<float*>(p.C) + m * p.ldc + nb;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    return;
+  }
+  if (ep.residual) {
+    const TOut* rrow = reinterpret_cast<const TOut*>(ep.residual) + m * ep.ld_res + nb;
+#pragma unroll
+    for (int j = 0; j < 32; j += Vec<TOut>::N) {
+      Vec<TOut> t;
+      t.load(rrow + j);
+#pragma unroll
+      for (int i = 0; i < Vec<TOut>::N; ++i) v[j + i] += t.v[i];
+    }
+  }
+  TOut* crow = reinterpret_cast<TOut*>(p.C) + m * p.ldc + nb;
+#pragma unroll
+  for (int j = 0; j < 32; j += Vec<TOut>::N) {
+    Vec<TOut> t;
+#pragma unroll
+    for (int i = 0; i < Vec<TOut>::N; ++i) t.v[i] = v[j + i];
+    t.store(crow + j);
+  }
+}
+
+// Slow path (ragged last columns, unaligned leading dims): per-element, fully guarded.
+template <typename TOut>
+__device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
+  const EpiParams& ep = p.ep;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    if (nb + j >= p.N) break;
+    float x = epi_full<bf16, TOut>(__uint_as_float(r[j]), m, nb + j, ep);
+    if (ep.accumulate) atomicAdd(reinterpret_cast<float*>(p.C) + m * p.ldc + nb + j, x);
+    else reinterpret_cast<TOut*>(p.C)[m * p.ldc + nb + j] = from_f<TOut>(x);
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, typename TOut>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -129,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -200,15 +317,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ---- epilogue warps: TMEM lane quadrant = warp % 4 ----
+    // ---- epilogue warps 2..9: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the
+    //      tile's columns (first / second half) ----
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     int as = 0;
     uint32_t aphase = 0;
     const EpiParams& ep = p.ep;
-    TOut* __restrict__ Cp = reinterpret_cast<TOut*>(p.C);
     constexpr int VEC = 16 / sizeof(TOut);
-    const bool vec_ok = ((p.ldc % VEC) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (ep.residual == nullptr || (((ep.ld_res % VEC) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)));
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec_ok = ((p.ldc % VEC) == 0) && al16(p.C) &&
+                        (ep.residual == nullptr || (((ep.ld_res % VEC) == 0) && al16(ep.residual))) &&
+                        (ep.bias == nullptr || al16(ep.bias)) &&
+                        (ep.aux == nullptr || (((ep.ld_aux % 8) == 0) && al16(ep.aux))) &&
+                        (ep.aux_out == nullptr || (((ep.ld_aux % VEC) == 0) && al16(ep.aux_out)));
+    constexpr int CH_PER_WARP = BN / 64;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       int rem = it % tiles;
       int64_t m0 = (int64_t)(rem / p.n_tiles) * BM, n0 = (int64_t)(rem % p.n_tiles) * BN;
@@ -217,70 +340,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m = m0 + quad * 32 + lane;
       const bool row_ok = m < p.M;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int c = 0; c < CH_PER_WARP; ++c) {
+        const int ch = half * CH_PER_WARP + c;
         const int64_t nb = n0 + ch * 32;
         if (nb >= p.N) break;   // warp-uniform
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + ch * 32, r);
-        if (row_ok) {
-        float v[32];
-        const bool full = (nb + 32 <= p.N);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (full || nb + j < p.N) ? epi_pre<bf16, TOut>(__uint_as_float(r[j]), m, nb + j, ep) : 0.f;
-        if (ep.drop_thr) {
-          uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
-          if ((e0 & 1) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              uint32_t h = emo_drop_hash(ep.seed, e0 + j);
-              v[j] = ((h & 0xffffu) >= ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
-              v[j + 1] = ((h >> 16) >= ep.drop_thr) ? v[j + 1] * ep.keep_scale : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = emo_drop_keep(ep.seed, e0 + j, ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
-          }
-        }
-        if (ep.accumulate) {
-          float* crow = reinterpret_cast<float*>(p.C) + m * p.ldc + nb;
-          if (full && vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) atomicAdd(crow + j, v[j]);
-          }
-        } else if (full && vec_ok) {
-          TOut* crow = Cp + m * p.ldc + nb;
-          if (ep.residual) {
-            const TOut* rrow = reinterpret_cast<const TOut*>(ep.residual) + m * ep.ld_res + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += Vec<TOut>::N) {
-              Vec<TOut> t;
-              t.load(rrow + j);
-#pragma unroll
-              for (int i = 0; i < Vec<TOut>::N; ++i) v[j + i] += t.v[i];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += Vec<TOut>::N) {
-            Vec<TOut> t;
-#pragma unroll
-            for (int i = 0; i < Vec<TOut>::N; ++i) t.v[i] = v[j + i];
-            t.store(crow + j);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j < p.N) {
-              float x = v[j];
-              if (ep.residual) x += to_f(reinterpret_cast<const TOut*>(ep.residual)[m * ep.ld_res + nb + j]);
-              Cp[m * p.ldc + nb + j] = from_f<TOut>(x);
-            }
-          }
-        }
-        }  // row_ok
+        if (!row_ok) continue;
+        if (vec_ok && nb + 32 <= p.N) epi_chunk_vec<TOut>(r, m, nb, p);
+        else epi_chunk_generic<TOut>(r, m, nb, p);
       }
       tc_fence_before();
       __syncwarp();
