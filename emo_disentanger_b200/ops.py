@@ -185,13 +185,29 @@ def colsum(x, out, n=None):
     _call("emo_colsum", _p(x), x.stride(0), M, N, _p(out), _dt(x), _stream())
 
 
+def _favor_ld(q, k, v):
+    """token stride of the [B,T,H,64] q/k/v views (size-1 dims carry arbitrary strides in torch)"""
+    B, T, H, E = q.shape
+    assert E == 64 and q.stride(3) == 1 and (H == 1 or q.stride(2) == 64)
+    ld = q.stride(1) if T > 1 else (q.stride(0) if B > 1 else H * 64)
+    assert B == 1 or T == 1 or q.stride(0) == T * ld, "q/k/v must be batch-contiguous views"
+    for t in (k, v):
+        assert t.shape == q.shape and t.stride(3) == 1
+        assert (T == 1 or t.stride(1) == ld) and (B == 1 or t.stride(0) == q.stride(0))
+    return ld
+
+
+def _row_ld(t):
+    """row stride of a [B,T,d] (or [rows,d]) view"""
+    return t.stride(-2) if t.shape[-2] > 1 else t.shape[-1]
+
+
 def favor_fwd(q, k, v, omega, out, den=None, state_out=None):
     """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view."""
     B, T, H, E = q.shape
-    assert E == 64 and q.stride(3) == 1 and q.stride(2) == 64 and (B == 1 or q.stride(0) == T * q.stride(1))
-    assert k.stride() == q.stride() and v.stride() == q.stride()
+    ld = _favor_ld(q, k, v)
     tk = TIMER.start("favor_fwd")
-    L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), out.stride(-2), _p(den),
+    L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), ld, _p(omega), _p(out), _row_ld(out), _p(den),
                                   _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
     TIMER.stop(tk, float(B * T * H * 64 * 4 * q.element_size()))      # algorithmic bytes: read q,k,v + write out
     return out
@@ -199,10 +215,11 @@ def favor_fwd(q, k, v, omega, out, den=None, state_out=None):
 
 def favor_bwd(q, k, v, omega, out, dout, den, state, dq, dk, dv):
     B, T, H, E = q.shape
-    assert dq.stride() == dk.stride() == dv.stride()
+    ld = _favor_ld(q, k, v)
+    ldd = _favor_ld(dq, dk, dv)
     tk = TIMER.start("favor_bwd")
-    L.check(L.lib().emo_favor_bwd(_p(q), _p(k), _p(v), q.stride(1), _p(omega), _p(out), _p(dout), out.stride(-2),
-                                  _p(den), _p(state), _p(dq), _p(dk), _p(dv), dq.stride(1), B, T, H, _dt(q),
+    L.check(L.lib().emo_favor_bwd(_p(q), _p(k), _p(v), ld, _p(omega), _p(out), _p(dout), _row_ld(out),
+                                  _p(den), _p(state), _p(dq), _p(dk), _p(dv), ldd, B, T, H, _dt(q),
                                   _stream()), "emo_favor_bwd")
     TIMER.stop(tk, float(B * T * H * 64 * 8 * q.element_size()))      # read q,k,v,out,dout + write dq,dk,dv
 
@@ -215,38 +232,49 @@ def favor_step(q, k, v, omega, state, out):
     return out
 
 
+def _qkv_ld(t):
+    """token stride of a [B,T,H,64] view, and check of the batch stride"""
+    B, T, H, E = t.shape
+    assert E == 64 and t.stride(3) == 1 and (H == 1 or t.stride(2) == 64)
+    ld = t.stride(1) if T > 1 else (t.stride(0) if B > 1 else H * 64)
+    assert B == 1 or T == 1 or t.stride(0) == T * ld, "attention operands must be batch-contiguous views"
+    return ld
+
+
 def attn_fwd(q, k, v, out, lse, scale, drop_p=0.0, seed=0):
+    """q [B,Tq,H,64], k,v [B,Tk,H,64] views; out [B,Tq,H*64]; lse [B,H,Tq] fp32."""
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    _call("emo_attn_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), out.stride(-2), _p(lse),
-                                 B, Tq, Tk, H, scale, drop_p, int(seed), _dt(q), _stream())
+    _call("emo_attn_fwd", _p(q), _p(k), _p(v), _qkv_ld(q), _qkv_ld(k), _p(out), _row_ld(out), _p(lse),
+          B, Tq, Tk, H, scale, drop_p, int(seed), _dt(q), _stream())
     return out
 
 
 def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale, drop_p=0.0, seed=0):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    _call("emo_attn_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(out), _p(dout), out.stride(-2),
-                                 _p(lse), _p(dq), _p(dk), _p(dv), dq.stride(1), dk.stride(1), B, Tq, Tk, H, scale,
-                                 drop_p, int(seed), _dt(q), _stream())
+    _call("emo_attn_bwd", _p(q), _p(k), _p(v), _qkv_ld(q), _qkv_ld(k), _p(out), _p(dout), _row_ld(out),
+          _p(lse), _p(dq), _p(dk), _p(dv), _qkv_ld(dq), _qkv_ld(dk), B, Tq, Tk, H, scale,
+          drop_p, int(seed), _dt(q), _stream())
 
 
-def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale):
+def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale, drop_p=0.0, seed=0):
+    """r [Tk,H,64] (row p = distance Tk-1-p); biases [H,64] fp32."""
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    _call("emo_relattn_fwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
-                                    _p(r_r_bias), _p(out), out.stride(-2), _p(lse), B, Tq, Tk, H, scale, _dt(q),
-                                    _stream())
+    _call("emo_relattn_fwd", _p(q), _p(k), _p(v), _qkv_ld(q), _qkv_ld(k), _p(r), r.stride(0) if Tk > 1 else H * 64,
+          _p(r_w_bias), _p(r_r_bias), _p(out), _row_ld(out), _p(lse), B, Tq, Tk, H, scale, drop_p, int(seed),
+          _dt(q), _stream())
     return out
 
 
-def relattn_bwd(q, k, v, r, r_w_bias, r_r_bias, out, dout, lse, dq, dk, dv, dr, d_rw, d_rr, scale):
+def relattn_bwd(q, k, v, r, r_w_bias, r_r_bias, out, dout, lse, dq, dk, dv, dr, d_rw, d_rr, scale, drop_p=0.0, seed=0):
     B, Tq, H, E = q.shape
     Tk = k.shape[1]
-    _call("emo_relattn_bwd", _p(q), _p(k), _p(v), q.stride(1), k.stride(1), _p(r), r.stride(0), _p(r_w_bias),
-                                    _p(r_r_bias), _p(out), _p(dout), out.stride(-2), _p(lse), _p(dq), _p(dk), _p(dv),
-                                    dq.stride(1), dk.stride(1), _p(dr), _p(d_rw), _p(d_rr), B, Tq, Tk, H, scale,
-                                    _dt(q), _stream())
+    _call("emo_relattn_bwd", _p(q), _p(k), _p(v), _qkv_ld(q), _qkv_ld(k), _p(r), r.stride(0) if Tk > 1 else H * 64,
+          _p(r_w_bias), _p(r_r_bias), _p(out), _p(dout), _row_ld(out), _p(lse), _p(dq), _p(dk), _p(dv),
+          _qkv_ld(dq), _qkv_ld(dk), _p(dr), _p(d_rw), _p(d_rr), B, Tq, Tk, H, scale, drop_p, int(seed),
+          _dt(q), _stream())
 
 
 def _tgt_layout(tgt, batch_first):

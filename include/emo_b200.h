@@ -139,19 +139,21 @@ int emo_attn_bwd(const void* q, const void* k, const void* v, int64_t ld_q, int6
 
 /* ---- A9: stage-1 relative-position attention ----------------------------------------------
  * optimus_txl_decoder.py:305-387: score(i,j) = ((q_i+r_w_bias).k_j + (q_i+r_r_bias).r_{dist})/8,
- * dist = i + mlen - j (>= 0 visible), softmax, (dropatt), renormalise /(sum+1e-8), . v.
+ * dist = i + mlen - j (>= 0 visible), softmax, dropatt(drop_p, seed), renormalise /(sum+1e-8), . v
+ * (drop + renormalise = softmax over the randomly kept keys; a row whose keys were all dropped gives 0).
+ * dr [Tk,H,64], d_r_w_bias, d_r_r_bias [H,64] are fp32 and ACCUMULATED (atomics).
  * q [B,Tq,H,64]; k,v [B,Tk,H,64]; r [Tk,H,64] with row p holding distance Tk-1-p (as r_net of
  * pos_emb for pos_seq = Tk-1..0, :792-796); biases [H,64] fp32. */
 int emo_relattn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
                     const void* r, int64_t ld_r, const float* r_w_bias, const float* r_r_bias,
                     void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk, int H,
-                    float scale, int dtype, void* stream);
+                    float scale, float drop_p, uint64_t seed, int dtype, void* stream);
 int emo_relattn_bwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
                     const void* r, int64_t ld_r, const float* r_w_bias, const float* r_r_bias,
                     const void* out, const void* dout, int64_t ld_out, const float* lse,
                     void* dq, void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, float* dr,
                     float* d_r_w_bias, float* d_r_r_bias, int B, int Tq, int Tk, int H,
-                    float scale, int dtype, void* stream);
+                    float scale, float drop_p, uint64_t seed, int dtype, void* stream);
 
 /* ---- A8: cross-entropy over the vocabulary -------------------------------------------------
  * compute_loss (music_performer.py:72-81, music_gpt2.py:94-103, plain_transformer.py:82-93):
