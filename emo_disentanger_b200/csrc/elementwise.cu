@@ -84,6 +84,36 @@ extern "C" int emo_embed_fwd(const int64_t* tok, const int64_t* seg, int64_t str
   return EMO_OK;
 }
 
+// decode-time embedding: one row per sequence, token / segment / POSITION read from device memory, so a
+// ragged batch of independent generations is one static-shaped (CUDA-graph capturable) launch.
+template <typename T>
+__global__ void embed_rows_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ seg,
+                                  const int64_t* __restrict__ pos, const float* __restrict__ e_tok,
+                                  const float* __restrict__ e_seg, const float* __restrict__ pe,
+                                  T* __restrict__ out, int rows, int d, float scale) {
+  int row = blockIdx.x;
+  if (row >= rows) return;
+  const float* e = e_tok + tok[row] * d;
+  const float* s = (seg && e_seg) ? e_seg + seg[row] * d : nullptr;
+  const float* p = (pos && pe) ? pe + pos[row] * d : nullptr;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v = e[c] * scale;
+    if (s) v += s[c] * scale;
+    if (p) v += p[c];
+    out[(int64_t)row * d + c] = from_f<T>(v);
+  }
+}
+extern "C" int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, const float* e_tok,
+                              const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
+                              int out_dtype, void* stream) {
+  if (rows == 0) return EMO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == EMO_BF16) embed_rows_kernel<bf16><<<rows, 128, 0, s>>>(tok, seg, pos, e_tok, e_seg, pe, (bf16*)out, rows, d, scale);
+  else embed_rows_kernel<float><<<rows, 128, 0, s>>>(tok, seg, pos, e_tok, e_seg, pe, (float*)out, rows, d, scale);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+
 // embedding backward: each block owns ROWS consecutive tokens; 128 threads x 4 columns (d = 512).
 // Segment-table gradient is reduced in registers per block (2 rows), token table via atomics.
 template <typename T>

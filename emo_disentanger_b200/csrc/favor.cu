@@ -127,7 +127,7 @@ template <typename T>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
                  const float* __restrict__ omega, T* __restrict__ out, int64_t ld_out, float* __restrict__ den_out,
-                 float* __restrict__ state_out, int Tlen, int H) {
+                 const float* __restrict__ state_in, float* __restrict__ state_out, int Tlen, int H) {
   constexpr int C = FavorCfg<T>::C;
   using S = FavorSmemFwd<T, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -137,9 +137,14 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
 
   load_omega<T>(omega, sm.om);
-  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
   BlockGemm<FM, FV, T> gs;   // running prefix state S' (fp32 master)
-  gs.clear();
+  if (state_in) {            // continue a sequence (decode: append a block of tokens to a running state)
+    const float* si = state_in + (int64_t)blockIdx.x * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; sm.s[row][col] = from_f<T>(x); });
+  } else {
+    for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
+    gs.clear();
+  }
   __syncthreads();
 
   for (int t0 = 0; t0 < Tlen; t0 += C) {
@@ -414,12 +419,13 @@ __global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
-                            int64_t ld_out, float* den, float* state_out, int B, int T_, int H, cudaStream_t s) {
+                            int64_t ld_out, float* den, const float* state_in, float* state_out, int B, int T_, int H,
+                            cudaStream_t s) {
   constexpr int C = FavorCfg<T>::C;
   size_t smem = sizeof(FavorSmemFwd<T, C>);
   EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   favor_fwd_kernel<T><<<B * H, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
-                                                      den, state_out, T_, H);
+                                                      den, state_in, state_out, T_, H);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
@@ -441,14 +447,14 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
-                             void* out, int64_t ld_out, float* den, float* state_out, int B, int T, int H, int dtype,
-                             void* stream) {
+                             void* out, int64_t ld_out, float* den, const float* state_in, float* state_out, int B,
+                             int T, int H, int dtype, void* stream) {
   int esz = dtype == EMO_BF16 ? 2 : 4;
   EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "emo_favor_fwd: pointers must be 16-byte aligned");
   EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0, "emo_favor_fwd: row strides must be 16-byte multiples");
   if (B * H == 0 || T == 0) return EMO_OK;
-  if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_out, B, T, H, (cudaStream_t)stream);
-  return favor_fwd_launch<float>(q, k, v, ld_qkv, omega, out, ld_out, den, state_out, B, T, H, (cudaStream_t)stream);
+  if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, B, T, H, (cudaStream_t)stream);
+  return favor_fwd_launch<float>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, B, T, H, (cudaStream_t)stream);
 }
 
 extern "C" int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,

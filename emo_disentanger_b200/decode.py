@@ -1,0 +1,216 @@
+"""Incremental autoregressive decode for the stage-2 models.
+
+The reference re-runs the model over the WHOLE prefix for every sampled token
+(stage2_accompaniment/inference.py:252-272: Performer O(t), GPT-2 O(t^2) per token) and copies the last
+logits row to the host.  Here the prefix is folded into per-layer state:
+
+  * Performer: the FAVOR+ prefix state  [sum phi(k) v^T | sum phi(k)]  (128 x 80 fp32 per head), advanced
+    by favor.cu's recurrent step (one token) or chunked forward with state_in/state_out (a block of tokens:
+    the primer, or a lead-sheet bar appended mid-generation, inference.py:293-307).  A step for a RAGGED
+    batch of independent sequences is one static-shaped launch sequence -> captured once in a CUDA graph.
+  * GPT-2: a K/V cache per layer; attention over the cache for the new rows only.
+
+The feature map Omega is drawn ONCE per decoder (the reference passes `omit_feature_map_draw: steps > 0`
+to keep it fixed during a generation, but fast_transformer_decoder.py:62,71 drops the kwarg and Omega is
+redrawn on every call; a recurrent state is only meaningful with the intended, fixed, Omega).
+Validity: absolute positions -> state is valid while len(prefix) <= max_len (inference.py:255-257 slides
+the window after that); `generate.py` falls back to full-prefix recompute past that point.
+"""
+import torch
+
+from . import ops
+from .stage2.music_performer import MusicPerformer
+from .stage2.music_gpt2 import MusicGPT2
+
+E = 64
+
+
+class Stage2Decoder:
+    def __init__(self, model, batch=1, max_len=2048, omegas=None, use_graph=True):
+        if model.training:
+            raise RuntimeError("decode needs model.eval() (dropout off)")
+        self.m = model
+        self.B = batch
+        self.max_len = max_len
+        self.dev = model._flat.device
+        self.dt = model.compute_dtype
+        self.is_performer = isinstance(model, MusicPerformer)
+        if not self.is_performer and not isinstance(model, MusicGPT2):
+            raise TypeError("Stage2Decoder drives MusicPerformer or MusicGPT2")
+        L, H, d = model.n_layer, model.n_head, model.d_model
+        dev = self.dev
+        self.pos = torch.zeros(batch, dtype=torch.int64, device=dev)          # next position of each sequence
+        self.pos_host = [0] * batch
+        if self.is_performer:
+            self.omegas = (model.draw_omegas(dev) if omegas is None else omegas.to(dev, torch.float32)).contiguous()
+            self.state = torch.zeros(L, batch, H, 128, 80, dtype=torch.float32, device=dev)
+        else:
+            self.kv = torch.zeros(L, batch, max_len, 2 * d, dtype=self.dt, device=dev)
+        # static step buffers (graph inputs / outputs)
+        self.tok_in = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.seg_in = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
+        self.use_graph = bool(use_graph) and self.is_performer
+        self.graph = None
+
+    def reset(self, b=None):
+        sl = slice(None) if b is None else slice(b, b + 1)
+        if self.is_performer:
+            self.state[:, sl].zero_()
+        self.pos[sl] = 0
+        for i in (range(self.B) if b is None else [b]):
+            self.pos_host[i] = 0
+
+    # ---- shared layer tails -------------------------------------------------------------------
+    def _performer_rows(self, h, B, T, favor):
+        """h [B*T, d] -> hidden after the 12 post-LN layers; `favor(l, q, k, v, att)` runs the attention."""
+        m = self.m
+        d, f, H = m.d_model, m.d_ff, m.n_head
+        Wc, Wf = m.weights(), m._flat
+        R = B * T
+        new = lambda *shape, dtype=self.dt: torch.empty(*shape, dtype=dtype, device=self.dev)
+        for l in range(m.n_layer):
+            nm = m._layer_names(l)
+            qkv = new(R, 3 * d)
+            ops.linear_fwd(h, m._qkv_w(Wc, l), qkv, bias=m._qkv_b(Wf, l))
+            att = new(R, d)
+            favor(l, qkv, att)
+            s1 = new(R, d)
+            ops.linear_fwd(att, m._wv(Wc, nm + "attention.out_projection.weight"), s1,
+                           bias=m._wv(Wf, nm + "attention.out_projection.bias"), residual=h, ld_res=d)
+            y1 = new(R, d)
+            ops.ln_fwd(s1, m._wv(Wf, nm + "norm1.weight"), m._wv(Wf, nm + "norm1.bias"), y1)
+            hh = new(R, f)
+            ops.linear_fwd(y1, m._wv(Wc, nm + "linear1.weight"), hh, bias=m._wv(Wf, nm + "linear1.bias"), act=ops.ACT_RELU)
+            s2 = new(R, d)
+            ops.linear_fwd(hh, m._wv(Wc, nm + "linear2.weight"), s2, bias=m._wv(Wf, nm + "linear2.bias"),
+                           residual=y1, ld_res=d)
+            h = new(R, d)
+            ops.ln_fwd(s2, m._wv(Wf, nm + "norm2.weight"), m._wv(Wf, nm + "norm2.bias"), h)
+        return h
+
+    def _gpt2_rows(self, h, b, T, pos0):
+        """one sequence b, T new rows at positions pos0.. -> hidden"""
+        m = self.m
+        d, f, H = m.d_model, m.d_ff, m.n_head
+        Wc, Wf = m.weights(), m._flat
+        new = lambda *shape, dtype=self.dt: torch.empty(*shape, dtype=dtype, device=self.dev)
+        for l in range(m.n_layer):
+            nm = "transformer_decoder.%d." % l
+            a = new(T, d)
+            ops.ln_fwd(h, m._wv(Wf, nm + "ln_1.weight"), m._wv(Wf, nm + "ln_1.bias"), a)
+            qkv = new(T, 3 * d)
+            ops.linear_fwd_t(a, m._wv(Wc, nm + "attn.c_attn.weight"), qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"))
+            cache = self.kv[l, b]
+            cache[pos0:pos0 + T].copy_(qkv[:, d:])                                   # append K|V rows (plumbing)
+            Tk = pos0 + T
+            q = qkv[:, :d].view(1, T, H, E)
+            k = cache[:Tk, :d].view(1, Tk, H, E)
+            v = cache[:Tk, d:].view(1, Tk, H, E)
+            att = new(T, d)
+            ops.attn_fwd(q, k, v, att.view(1, T, d), None, 1.0 / (E ** 0.5))
+            hx = new(T, d)
+            ops.linear_fwd_t(att, m._wv(Wc, nm + "attn.c_proj.weight"), hx, bias=m._wv(Wf, nm + "attn.c_proj.bias"),
+                             residual=h, ld_res=d)
+            c = new(T, d)
+            ops.ln_fwd(hx, m._wv(Wf, nm + "ln_2.weight"), m._wv(Wf, nm + "ln_2.bias"), c)
+            g = new(T, f)
+            ops.linear_fwd_t(c, m._wv(Wc, nm + "mlp.c_fc.weight"), g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"),
+                             act=ops.ACT_GELU_NEW)
+            h = new(T, d)
+            ops.linear_fwd_t(g, m._wv(Wc, nm + "mlp.c_proj.weight"), h, bias=m._wv(Wf, nm + "mlp.c_proj.bias"),
+                             residual=hx, ld_res=d)
+        return h
+
+    def _logits_into(self, hid_rows, out_rows):
+        m = self.m
+        ops.linear_fwd(hid_rows, m._wv(m.weights(), "dec_out_proj.weight"), out_rows[:, :m.n_token],
+                       bias=m._wv(m._flat, "dec_out_proj.bias"))
+
+    # ---- append a block of tokens to ONE sequence (primer / lead-sheet bar) -------------------------
+    @torch.no_grad()
+    def append(self, b, tokens, segs):
+        """tokens / segs: python lists (or 1-D int64 tensors).  Returns the fp32 logits [V] after the last one."""
+        m = self.m
+        tok = torch.as_tensor(tokens, dtype=torch.int64).view(1, -1).to(self.dev)
+        seg = torch.as_tensor(segs, dtype=torch.int64).view(1, -1).to(self.dev) if m.use_segment_emb else None
+        T = tok.shape[1]
+        pos0 = self.pos_host[b]
+        if pos0 + T > self.max_len:
+            raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
+        d, H = m.d_model, m.n_head
+        h = torch.empty(T, d, dtype=self.dt, device=self.dev)
+        ops.embed_fwd(tok, seg, m._wv(m._flat, "token_emb.emb_lookup.weight"),
+                      m._wv(m._flat, "segemb.emb_lookup.weight") if seg is not None else None,
+                      m.pe.pe[pos0:] if m.use_pe else None, h, d ** 0.5)
+        if self.is_performer:
+            def favor(l, qkv, att):
+                q3 = qkv.view(1, T, 3 * d)
+                q, k, v = (q3[:, :, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
+                st = self.state[l, b:b + 1]
+                ops.favor_fwd(q, k, v, self.omegas[l], att.view(1, T, d), None, state_out=st, state_in=st)
+            hid = self._performer_rows(h, 1, T, favor)
+        else:
+            hid = self._gpt2_rows(h, b, T, pos0)
+        self._logits_into(hid[T - 1:T], self.logits[b:b + 1])
+        self.pos_host[b] = pos0 + T
+        self.pos[b] = pos0 + T
+        return self.logits[b, :m.n_token]
+
+    # ---- one token for every sequence ------------------------------------------------------------
+    def _performer_step_body(self):
+        m = self.m
+        B, d, H = self.B, m.d_model, m.n_head
+        h = torch.empty(B, d, dtype=self.dt, device=self.dev)
+        ops.embed_rows(self.tok_in, self.seg_in if m.use_segment_emb else None, self.pos if m.use_pe else None,
+                       m._wv(m._flat, "token_emb.emb_lookup.weight"),
+                       m._wv(m._flat, "segemb.emb_lookup.weight") if m.use_segment_emb else None,
+                       m.pe.pe if m.use_pe else None, h, d ** 0.5)
+
+        def favor(l, qkv, att):
+            q, k, v = (qkv[:, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
+            ops.favor_step(q, k, v, self.omegas[l], self.state[l], att)
+        hid = self._performer_rows(h, B, 1, favor)
+        self._logits_into(hid, self.logits)
+        self.pos.add_(1)
+
+    @torch.no_grad()
+    def step(self, tokens, segs):
+        """tokens / segs: python lists of length B (one new token per sequence). Returns logits [B, V] (fp32,
+        a view of a static buffer: consume before the next call)."""
+        m = self.m
+        if max(self.pos_host) + 1 > self.max_len:
+            raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
+        if self.is_performer:
+            host = torch.tensor([list(tokens), list(segs)], dtype=torch.int64).pin_memory()
+            self.tok_in.copy_(host[0], non_blocking=True)
+            self.seg_in.copy_(host[1], non_blocking=True)
+            if self.use_graph:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+            else:
+                self._performer_step_body()
+            for b in range(self.B):
+                self.pos_host[b] += 1
+        else:
+            for b in range(self.B):
+                self.append(b, [tokens[b]], [segs[b]])
+        return self.logits[:, :m.n_token]
+
+    def _capture(self):
+        m = self.m
+        m.weights()                                   # make sure the bf16 shadow exists before capture
+        state0, pos0 = self.state.clone(), self.pos.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                        # warm-up outside capture (lazy module / attribute init)
+                self._performer_step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._performer_step_body()
+        self.state.copy_(state0)                      # undo the warm-up / capture-time state advance
+        self.pos.copy_(pos0)
+        self.graph = g

@@ -1,0 +1,257 @@
+"""Decode loops: drop-ins for `generate_conditional` (reference stage2_accompaniment/inference.py:231-327)
+and `generate_plain_xl` (stage1_compose/inference_utils.py:51-135).
+
+Same arguments, same grammar rules (monotone Beat positions with the 256-retry abort, bar counting,
+Track_LeadSheet interleave, PAD / EOS handling, first-token Key rule), same return values.  What changed
+is where the arithmetic runs: the model step is incremental (decode.py / PlainTransformer.generate) and
+`temperature` + `nucleus` run in the fused device sampler (sampler.cu) -- one int64 per token crosses to
+the host instead of the whole logits row.  The uniform that drives the draw still comes from numpy's
+global MT19937 stream (one `random_sample()` per draw, exactly what `np.random.choice(..., p=)` consumes),
+so a seeded run follows the reference's stream.  A rejected sample (Beat going backwards, PAD, early EOS)
+re-draws from the SAME logits: with a fixed feature map the model output for an unchanged prefix is
+unchanged, so the reference's re-run of the model is skipped (stage 1 keeps the reference's quirk of
+advancing the memory on a rejected step, SURVEY App. B.9, because it changes later logits).
+"""
+import time
+import numpy as np
+import torch
+
+from . import ops
+from .decode import Stage2Decoder
+
+MAX_DEC_INP_LEN = 2048          # stage2_accompaniment/inference.py:19
+
+
+class DeviceSampler:
+    """temperature + nucleus on the device (K11).  greedy=True -> argmax (bit-exact decode mode)."""
+
+    def __init__(self, device, rows=1):
+        self.u = torch.zeros(rows, dtype=torch.float32, device=device)
+        self.out = torch.zeros(rows, dtype=torch.int64, device=device)
+        self.status = torch.zeros(rows, dtype=torch.int32, device=device)
+
+    def draw(self, logits, V, temp, top_p, greedy=False, rng=None):
+        """logits fp32 [rows, >=V] (device).  Returns python ints (tokens); raises IndexError where the
+        reference would (exactly one index above top_p, inference.py:93)."""
+        rows = logits.shape[0]
+        if not greedy:
+            r = np.random if rng is None else rng
+            self.u[:rows].copy_(torch.tensor([r.random_sample() for _ in range(rows)], dtype=torch.float32))
+        ops.sample(logits, V, temp, top_p, self.u, self.out, self.status, greedy=greedy)
+        res = torch.stack([self.out[:rows], self.status[:rows].to(torch.int64)]).cpu()      # ONE small D2H
+        if int(res[1].max()) != 0:
+            raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+        return [int(x) for x in res[0]]
+
+
+def get_position_idx(event):
+    return int(event.split('_')[-1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------------------
+def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
+                         max_events=10000, skip_check=False, max_bars=None,
+                         temp=1.2, top_p=0.9, inadmissibles=None,
+                         model_type="performer", greedy=False, decoder=None, rng=None, verbose=True):
+    if inadmissibles is not None:
+        raise NotImplementedError("the reference always passes inadmissibles=None (inference.py:467)")
+    say = print if verbose else (lambda *a, **k: None)
+    generated = primer + [event2idx['Track_LeadSheet']] + lead_sheet_events[0] + [event2idx['Track_Full']]
+    seg_inp = [0 for _ in range(len(generated))]
+    seg_inp[-1] = 1
+
+    target_bars, generated_bars = len(lead_sheet_events), 0
+    if max_bars is not None:
+        target_bars = min(max_bars, target_bars)
+
+    dec = decoder if decoder is not None else Stage2Decoder(model, batch=1, max_len=MAX_DEC_INP_LEN)
+    dec.reset(0)
+    sampler = DeviceSampler(dec.dev)
+    V = model.n_token
+    fed = 0                       # tokens of `generated` already folded into the decode state
+    logits = None
+
+    steps = 0
+    time_st = time.time()
+    cur_pos = 0
+    failed_cnt = 0
+
+    while generated_bars < target_bars:
+        assert len(generated) == len(seg_inp)
+        if len(generated) < MAX_DEC_INP_LEN:
+            if fed < len(generated):          # fold the not-yet-seen suffix (primer, new token, lead-sheet bar)
+                n_new = len(generated) - fed
+                if n_new == 1 and fed > 0:
+                    logits = dec.step([generated[-1]], [seg_inp[-1]])[0:1]
+                else:
+                    logits = dec.append(0, generated[fed:], seg_inp[fed:])[None]
+                fed = len(generated)
+        else:                                 # window slides -> absolute positions shift -> full recompute
+            dev = dec.dev
+            dec_input = torch.tensor([generated[-MAX_DEC_INP_LEN:]]).long().to(dev)
+            dec_seg_inp = torch.tensor([seg_inp[-MAX_DEC_INP_LEN:]]).long().to(dev)
+            if dec.is_performer:
+                model.fixed_omegas = dec.omegas
+            with torch.no_grad():
+                logits = model(dec_input, seg_inp=dec_seg_inp, keep_last_only=True).float().contiguous()
+
+        word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
+        word_event = idx2event[word]
+
+        if not skip_check:
+            if 'Beat' in word_event:
+                event_pos = get_position_idx(word_event)
+                if not event_pos >= cur_pos:
+                    failed_cnt += 1
+                    say('[info] position not increasing, failed cnt:', failed_cnt)
+                    if failed_cnt >= 256 or greedy:
+                        say('[FATAL] model stuck, exiting with generated events ...')
+                        return generated
+                    continue
+                else:
+                    cur_pos = event_pos
+                    failed_cnt = 0
+
+        if word_event == 'Track_LeadSheet':
+            steps += 1
+            generated.append(word)
+            seg_inp.append(0)
+            generated_bars += 1
+            say('[info] generated {} bars, #events = {}'.format(generated_bars, len(generated)))
+
+            if generated_bars < target_bars:
+                generated.extend(lead_sheet_events[generated_bars])
+                seg_inp.extend([0 for _ in range(len(lead_sheet_events[generated_bars]))])
+
+                generated.append(event2idx['Track_Full'])
+                seg_inp.append(1)
+                cur_pos = 0
+            continue
+
+        if word_event == 'PAD_None' or (word_event == 'EOS_None' and generated_bars < target_bars - 1):
+            if greedy:
+                say('[FATAL] greedy decode stuck on an inadmissible token')
+                return generated
+            continue
+        elif word_event == 'EOS_None' and generated_bars == target_bars - 1:
+            say('[info] gotten eos')
+            generated.append(word)
+            break
+
+        generated.append(word)
+        seg_inp.append(1)
+        steps += 1
+
+        if len(generated) > max_events:
+            say('[info] max events reached')
+            break
+
+    say('-- generated events:', len(generated))
+    say('-- time elapsed  : {:.2f} secs'.format(time.time() - time_st))
+    say('-- time per event: {:.2f} secs'.format((time.time() - time_st) / len(generated)))
+    return generated[:-1]
+
+
+# ------------------------------------------------------------------------------------------------------
+# stage 1
+# ------------------------------------------------------------------------------------------------------
+MAJOR_KEY = np.array(['C', 'C#', 'D', 'D#', 'E', 'F', 'F#', 'G', 'G#', 'A', 'A#', 'B'])
+MINOR_KEY = np.array(['c', 'c#', 'd', 'd#', 'e', 'f', 'f#', 'g', 'g#', 'a', 'a#', 'b'])
+
+
+def match_emotion_key(emotion, key):
+    # stage1_compose/inference_utils.py:138-143
+    if emotion in ['Q1', 'Q4', 'Positive'] and key in MAJOR_KEY:
+        return True
+    if emotion in ['Q2', 'Q3', 'Negative'] and key in MINOR_KEY:
+        return True
+    return False
+
+
+def generate_plain_xl(model, event2idx, idx2event, max_bars=160,
+                      max_events=2048, primer=None, temp=1.2, top_p=0.9,
+                      prompt_bars=None, representation='functional', key_determine=None,
+                      greedy=False, rng=None, verbose=True):
+    say = print if verbose else (lambda *a, **k: None)
+    if primer is None:
+        generated = [event2idx['Bar_None']]
+        target_bars, generated_bars = max_bars, 0
+    else:
+        generated = [event2idx[e] for e in primer]
+        target_bars, generated_bars = max_bars, prompt_bars if prompt_bars is not None else 0
+
+    device = next(model.parameters()).device
+    sampler = DeviceSampler(device)
+    V = model.vocab_size
+    steps = 0
+    time_st = time.time()
+    cur_pos = 0
+    failed_cnt = 0
+    mems = tuple()
+    while generated_bars < target_bars:
+        if steps == 0:
+            dec_input = torch.LongTensor([generated]).to(device)
+            dec_input = dec_input.permute(1, 0) if len(generated) > 1 else dec_input
+        else:
+            dec_input = torch.LongTensor([[generated[-1]]]).to(device)
+
+        logits, mems = model.generate(dec_input, mems)         # memory advances even if the draw is rejected
+        logits = logits.float().view(1, -1)
+
+        if representation in ['functional', 'key'] and len(generated) == 1:
+            word = sampler.draw(logits, V, 1.1, 0.97, greedy=greedy, rng=rng)[0]
+            if key_determine == 'rule':
+                emotion_label = idx2event[generated[0]].split('_')[1]
+                key_event = idx2event[word]
+                if key_event.split('_')[0] != 'Key':
+                    raise ValueError('[info] key generation failed')
+                key_label = key_event.split('_')[1]
+                if not match_emotion_key(emotion_label, key_label):
+                    if greedy:
+                        raise ValueError('[info] greedy key does not match the emotion')
+                    continue
+            word_event = idx2event[word]
+        else:
+            word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
+            word_event = idx2event[word]
+
+        if 'Key' in word_event:
+            say('[info] generated {}, #events = {}'.format(word_event, len(generated)))
+
+        if 'Beat' in word_event:
+            event_pos = get_position_idx(word_event)
+            if not event_pos >= cur_pos:
+                failed_cnt += 1
+                say('[info] position not increasing, failed cnt:', failed_cnt)
+                if failed_cnt >= 256 or greedy:
+                    say('[FATAL] model stuck, exiting ...')
+                    return None, time.time() - time_st
+                continue
+            else:
+                cur_pos = event_pos
+                failed_cnt = 0
+
+        if 'Bar' in word_event:
+            generated_bars += 1
+            cur_pos = 0
+            say('[info] generated {} bars, #events = {}'.format(generated_bars, len(generated)))
+        if word_event == 'PAD_None':
+            if greedy:
+                return None, time.time() - time_st
+            continue
+
+        generated.append(word)
+        steps += 1
+
+        if len(generated) > max_events:
+            say('[info] max events reached')
+            break
+        if word_event == 'EOS_None':
+            say('[info] gotten eos')
+            break
+
+    say('-- generated events:', len(generated))
+    say('-- time elapsed: {:.2f} secs'.format(time.time() - time_st))
+    return generated[:-1], time.time() - time_st

@@ -92,6 +92,13 @@ def embed_fwd(tok, seg, e_tok, e_seg, pe, out, scale, drop_p=0.0, seed=0, batch_
     return out
 
 
+def embed_rows(tok, seg, pos, e_tok, e_seg, pe, out, scale):
+    """decode: tok/seg/pos int64 [rows] on the device; out [rows, d]."""
+    _call("emo_embed_rows", _p(tok), _p(seg), _p(pos), _p(e_tok), _p(e_seg), _p(pe), _p(out), tok.shape[0],
+          e_tok.shape[1], float(scale), _dt(out), _stream())
+    return out
+
+
 def embed_bwd(tok, seg, dout, d_e_tok, d_e_seg, scale, drop_p=0.0, seed=0, pad_idx=-1, batch_first=True):
     if batch_first:
         B, T = tok.shape
@@ -202,13 +209,13 @@ def _row_ld(t):
     return t.stride(-2) if t.shape[-2] > 1 else t.shape[-1]
 
 
-def favor_fwd(q, k, v, omega, out, den=None, state_out=None):
+def favor_fwd(q, k, v, omega, out, den=None, state_out=None, state_in=None):
     """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view."""
     B, T, H, E = q.shape
     ld = _favor_ld(q, k, v)
     tk = TIMER.start("favor_fwd")
     L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), ld, _p(omega), _p(out), _row_ld(out), _p(den),
-                                  _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
+                                  _p(state_in), _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
     TIMER.stop(tk, float(B * T * H * 64 * 4 * q.element_size()))      # algorithmic bytes: read q,k,v + write out
     return out
 

@@ -40,6 +40,12 @@ int emo_embed_fwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int6
                   const float* e_tok, const float* e_seg, const float* pe, void* out,
                   int B, int T, int d, float scale, float drop_p, uint64_t seed,
                   int out_dtype, void* stream);
+/* decode step of the same front-end (stage2_accompaniment/inference.py:252-272 feeds the model one new
+ * token per iteration): one row per sequence, out[b,:] = (E_tok[tok[b]] + E_seg[seg[b]]) * scale +
+ * pe[pos[b]], with tok / seg / pos read from DEVICE memory (ragged batch, CUDA-graph capturable). */
+int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, const float* e_tok,
+                   const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
+                   int out_dtype, void* stream);
 /* d_e_tok[tok] += dout*scale*mask (fp32 atomics); rows == pad_idx get no gradient (pass -1 for
  * none: nn.Embedding(padding_idx) in stage1 transformer_helpers.py:104-108). */
 int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
@@ -111,10 +117,12 @@ int emo_colsum(const void* x, int64_t ld, int64_t M, int64_t N, float* out, int 
  * q,k,v: [B,T,H,64] with token row stride ld_qkv (slices of one packed [B*T, 3*512] buffer);
  * omega [64,64] fp32 (row = input dim, col = feature); phi is recomputed in-kernel and never
  * written to HBM.  out [B,T,H*64] (ld_out); den [B,T,H] fp32 = phi(q).cumsum(phi(k)) + 1e-6;
- * state_out (may be NULL) [B,H,128,80] fp32: final prefix state [sum phi(k) v^T | sum phi(k) | 0]. */
+ * state_in (NULL = start of sequence) / state_out (may be NULL; may alias state_in) [B,H,128,80] fp32:
+ * prefix state [sum phi(k) v^T | sum phi(k) | 0] before / after these T tokens (decode appends blocks
+ * of tokens -- a lead-sheet bar -- to a running state, stage2_accompaniment/inference.py:293-307). */
 int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
-                  void* out, int64_t ld_out, float* den, float* state_out, int B, int T, int H,
-                  int dtype, void* stream);
+                  void* out, int64_t ld_out, float* den, const float* state_in, float* state_out, int B,
+                  int T, int H, int dtype, void* stream);
 /* reverse-scan backward; state_in = state_out of the forward call. */
 int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
                   const void* out, const void* dout, int64_t ld_out, const float* den,

@@ -97,3 +97,32 @@ def sampling_functions():
         exec(compile(mod, rel, "exec"), ns)
         out[stage] = (ns["temperature"], ns["nucleus"])
     return out
+
+
+def decode_functions():
+    """The reference decode loops, extracted verbatim (AST) from the unmodified scripts without
+    importing their heavy / missing dependencies (dataloader, convert2midi, miditoolkit, pickle5):
+      stage2: generate_conditional, temperature, nucleus, get_position_idx   (inference.py:71-100,206-327)
+      stage1: generate_plain_xl, temperature, nucleus, match_emotion_key       (inference_utils.py:14-143)
+    Returns {'stage1': namespace, 'stage2': namespace}; namespaces are plain dicts whose `nucleus` can be
+    swapped (e.g. for argmax) before calling the loop."""
+    import ast
+    import time
+    import numpy as np
+    import scipy, scipy.special
+    import torch
+    out = {}
+    wanted = {"stage2": ("stage2_accompaniment/inference.py",
+                         ("generate_conditional", "temperature", "nucleus", "get_position_idx")),
+              "stage1": ("stage1_compose/inference_utils.py",
+                         ("generate_plain_xl", "temperature", "nucleus", "get_position_idx", "match_emotion_key"))}
+    for stage, (rel, names) in wanted.items():
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+        ns = {"np": np, "scipy": scipy, "torch": torch, "time": time, "max_dec_inp_len": 2048,
+              "tensor_to_numpy": lambda t: t.cpu().detach().numpy(),
+              "MAJOR_KEY": np.array(['C', 'C#', 'D', 'D#', 'E', 'F', 'F#', 'G', 'G#', 'A', 'A#', 'B']),
+              "MINOR_KEY": np.array(['c', 'c#', 'd', 'd#', 'e', 'f', 'f#', 'g', 'g#', 'a', 'a#', 'b'])}
+        exec(compile(ast.Module(body=keep, type_ignores=[]), rel, "exec"), ns)
+        out[stage] = ns
+    return out
