@@ -8,8 +8,9 @@ from . import ops
 
 
 class FusedAdam:
-    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0):
+    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0, grad_sync=None):
         self.model = model
+        self.grad_sync = grad_sync        # dp.GradSync: one all-reduce of the flat gradient before the clip
         self.param_groups = [{"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False,
                               "initial_lr": lr, "params": list(range(len(list(model.parameters()))))}]
         self.max_grad_norm = float(max_grad_norm or 0.0)
@@ -27,6 +28,8 @@ class FusedAdam:
         m = self.model
         if self._m.device != m._flat.device:
             self._m, self._v, self._gn = self._m.to(m._flat.device), self._v.to(m._flat.device), self._gn.to(m._flat.device)
+        if self.grad_sync is not None:
+            self.grad_sync.allreduce_grads()
         g = self.param_groups[0]
         self._step += 1
         gn = None

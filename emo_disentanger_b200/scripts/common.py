@@ -1,0 +1,54 @@
+"""Shared plumbing of the four scripts: pickle5 shim, reference-tree imports for the OUT-OF-SCOPE host
+components (datasets, event->MIDI conversion; SURVEY 2: C8-C12), synthetic data, rank-0 logging."""
+import os
+import pickle
+import sys
+import torch
+
+from ..synth import synthetic_batch
+
+
+def install_pickle5_shim():
+    """the reference imports `pickle5` (utils.py:2), which is python<3.8 only"""
+    sys.modules.setdefault("pickle5", pickle)
+
+
+def reference_module(stage_dir, name):
+    """import `name` (dataloader / convert2midi / utils) from the reference tree the script is run in
+    (cwd = reference repo root, as the reference README does) or from $EMO_REFERENCE_ROOT"""
+    install_pickle5_shim()
+    roots = [os.environ.get("EMO_REFERENCE_ROOT", ""), os.getcwd()]
+    for r in roots:
+        p = os.path.join(r, stage_dir)
+        if r and os.path.isfile(os.path.join(p, name + ".py")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+            return __import__(name)
+    raise FileNotFoundError("%s/%s.py not found: run from the reference repo root (or set EMO_REFERENCE_ROOT), "
+                            "or use a config with a `synthetic` data section" % (stage_dir, name))
+
+
+class SyntheticStage2:
+    """iterable of reference-shaped stage-2 batches"""
+
+    def __init__(self, V, B, T, n, seed):
+        self.vocab_size, self.pad_token = V, V - 1
+        self.batches = []
+        for i in range(n):
+            tok, seg, tgt = synthetic_batch(V, B, T, seed + i)
+            z = torch.zeros_like(tok)
+            self.batches.append({"dec_input": tok, "dec_target": tgt, "track_mask": seg, "length": [T] * B,
+                                 "chord_idx": z, "melody_idx": z})
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __iter__(self):
+        return iter(self.batches)
+
+
+def rank_strided(loader, rank, world):
+    """data parallel: rank r takes batches r, r+world, ..."""
+    for i, b in enumerate(loader):
+        if i % world == rank:
+            yield b

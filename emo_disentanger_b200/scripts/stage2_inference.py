@@ -1,0 +1,126 @@
+"""Stage-2 generation -- the reference's `python3 stage2_accompaniment/inference.py -m MODEL -c CONFIG -r REPR
+[-i PARAMS] [-o OUT_DIR] [-p]` surface (inference.py:330-485) over the incremental B200 decode path.
+
+Reads every generated lead sheet (`*_roman.txt` / `*.txt`) in OUT_DIR, decodes one accompaniment per emotion
+quadrant (Positive -> Q1,Q4; Negative -> Q2,Q3) with the reference's sampling constants (performer: t=1.1,
+p=0.99; gpt2: t=1.2, p=0.97) and writes `<name>_<Q>_full.txt` token-event files; when the reference's
+`convert2midi` (+ miditoolkit) is importable the `.mid` is written too (post-processing is out of scope,
+SURVEY 2 C10).  `--synthetic V` runs on a synthetic vocabulary / random lead sheets / random weights."""
+import argparse
+import os
+import shutil
+import time
+from itertools import chain
+import numpy as np
+import torch
+import yaml
+
+from ..decode import Stage2Decoder
+from ..generate import generate_conditional
+from ..synth import synthetic_vocab, synthetic_lead_sheet
+from . import common
+from .stage2_train import build_model, load_params
+
+MAX_BARS = 128
+
+
+def read_generated_events(events_file, event2idx):
+    events = open(events_file).read().splitlines()
+    key = events[0] if 'Key' in events[0] else 'Key_C'
+    bar_pos = [i for i, e in enumerate(events) if e == 'Bar_None'] + [len(events)]
+    bars = [[event2idx[e] for e in events[bar_pos[b]:bar_pos[b + 1]]] for b in range(len(bar_pos) - 1)]
+    return key, bars
+
+
+def emotions_for(name):
+    for tag, quads in (('Positive', ['Q1', 'Q4']), ('Negative', ['Q2', 'Q3']), ('Q1', ['Q1']), ('Q2', ['Q2']),
+                       ('Q3', ['Q3']), ('Q4', ['Q4']), ('None', ['None'])):
+        if tag in name:
+            return quads
+    raise ValueError('wrong emotion label')
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description='')
+    req = ap.add_argument_group('required arguments')
+    req.add_argument('-m', '--model_type', choices=['performer', 'gpt2'], required=True, help='model backbone')
+    req.add_argument('-c', '--configuration', required=True, help='configurations of training')
+    req.add_argument('-r', '--representation', choices=['remi', 'functional'], required=True)
+    ap.add_argument('-i', '--inference_params', default=None, help='inference parameters')
+    ap.add_argument('-o', '--output_dir', default='generation/emopia_functional_two', help='output directory')
+    ap.add_argument('-p', '--play_midi', default=False, action='store_true')
+    ap.add_argument('--synthetic', type=int, default=0, help='vocabulary size of a synthetic run (no dataset needed)')
+    ap.add_argument('--max_bars', type=int, default=MAX_BARS)
+    args = ap.parse_args(argv)
+    conf = yaml.load(open(args.configuration), Loader=yaml.FullLoader)
+    tc, mc = conf['training'], conf['model']
+    gpuid = tc['gpuid']
+    torch.cuda.set_device(gpuid)
+    rep, out_dir = args.representation, args.output_dir
+    os.makedirs(out_dir, exist_ok=True)
+
+    if args.synthetic:
+        event2idx, idx2event = synthetic_vocab(args.synthetic, 2)
+        vocab_size = args.synthetic
+        for i, emo in enumerate(('Positive', 'Negative')):        # two synthetic lead sheets -> the 4Q run
+            path = os.path.join(out_dir, 'samp_%02d_%s%s.txt' % (i, emo, '_roman' if rep == 'functional' else ''))
+            if not os.path.exists(path):
+                bars = synthetic_lead_sheet(event2idx, 4, i)
+                with open(path, 'w') as f:
+                    print('Key_C', *[idx2event[t] for t in chain(*bars)], sep='\n', file=f)
+    else:
+        dl = common.reference_module('stage2_accompaniment', 'dataloader')
+        ut = common.reference_module('stage2_accompaniment', 'utils')
+        dset = dl.REMISkylineToMidiTransformerDataset(
+            conf['data_loader']['data_path'].format(rep), conf['data_loader']['vocab_path'].format(rep),
+            model_dec_seqlen=mc['max_len'], pieces=ut.pickle_load(conf['data_loader']['val_split']), pad_to_same=True)
+        event2idx, idx2event, vocab_size = dset.event2idx, dset.idx2event, dset.vocab_size
+
+    model = build_model(args.model_type, vocab_size, mc, gpuid)
+    temp, top_p = (1.1, 0.99) if args.model_type == "performer" else (1.2, 0.97)
+    print(f"[info] temp = {temp} | top_p = {top_p}")
+    if args.inference_params:
+        load_params(model, args.inference_params)
+    model.eval()
+    print('[info] model loaded')
+    shutil.copy(args.configuration, os.path.join(out_dir, 'config_full.yaml'))
+    try:
+        event_to_midi = common.reference_module('stage2_accompaniment', 'convert2midi').event_to_midi
+    except Exception as e:                                    # miditoolkit / reference tree absent
+        print('[info] event->MIDI conversion unavailable (%s); writing token-event text only' % type(e).__name__)
+        event_to_midi = None
+
+    tag = 'roman.txt' if rep == 'functional' else '.txt'
+    files = sorted(os.path.join(out_dir, f) for f in os.listdir(out_dir) if tag in f and '_full' not in f)
+    print('[# pieces]', len(files))
+    dec = Stage2Decoder(model, batch=1)
+    n_tok, t0 = 0, time.time()
+    for file in files:
+        out_name = '_'.join(os.path.basename(file).split('_')[:2])
+        for e in emotions_for(file):
+            out_txt = os.path.join(out_dir, out_name + '_' + e + '_full.txt')
+            if os.path.exists(out_txt):
+                print('[info] {} exists, skipping ...'.format(out_txt))
+                continue
+            key, lead = read_generated_events(file, event2idx)
+            primer = [event2idx['Emotion_{}'.format(e)]] + ([event2idx[key]] if rep == 'functional' else []) + \
+                     [event2idx['Tempo_{}'.format(110)]]
+            generated = generate_conditional(model, event2idx, idx2event, lead, primer=primer, max_bars=args.max_bars,
+                                             temp=temp, top_p=top_p, inadmissibles=None, model_type=args.model_type,
+                                             decoder=dec)
+            n_tok += len(generated)
+            events = [idx2event[w] for w in generated]
+            with open(out_txt, 'w') as f:
+                print(*events, sep='\n', file=f)
+            if event_to_midi is not None and not args.synthetic:
+                inf = common.reference_module('stage2_accompaniment', 'inference')
+                bars = inf.extract_midi_events_from_generation(key, events, relative_melody=(rep == 'functional'))
+                event_to_midi(key, list(chain(*bars[:args.max_bars])), mode='full',
+                              output_midi_path=os.path.join(out_dir, out_name + '_' + e + '_full.mid'))
+    dt = time.time() - t0
+    print('[info] %d events in %.2f s (%.1f events/s incl. grammar rejections and host loop)' % (n_tok, dt, n_tok / max(dt, 1e-9)))
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(main())
