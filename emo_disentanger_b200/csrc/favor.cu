@@ -23,7 +23,7 @@ constexpr float F_HALF_LOG_M = 2.4260151319598084f;   // 0.5 * ln(128)
 
 template <typename T> struct FavorCfg;
 template <> struct FavorCfg<bf16> { static constexpr int C = 64; };
-template <> struct FavorCfg<float> { static constexpr int C = 32; };
+template <> struct FavorCfg<float> { static constexpr int C = 16; };   // parity mode: smaller chunks keep the fp32 tiles within 227 KB
 
 template <typename T> __device__ __forceinline__ float f_exp(float x);
 template <> __device__ __forceinline__ float f_exp<bf16>(float x) { return __expf(x); }
@@ -41,13 +41,24 @@ template <typename T, int C> struct FavorSmemFwd {
   float oq[C], ok[C], den[C];
 };
 
-template <typename T, int C> struct FavorSmemBwd {
-  T xq[C][bg_ld<T>(FE)];
-  T xk[C][bg_ld<T>(FE)];
+// segment-sum kernels: x = k rows (fwd) or q rows (bwd), w = [v | 1 | 0] (fwd) or G (bwd)
+template <typename T, int C> struct FavorSmemSeg {
+  T x[2][C][bg_ld<T>(FE)];       // double-buffered (cp.async prefetch of the next chunk)
+  T w[2][C][bg_ld<T>(FV)];
+  T raw[2][2][C][bg_ld<T>(FE)];  // bwd only: raw out / dout tiles of the next chunk
   T om[FE][bg_ld<T>(FE)];
-  T du[C][bg_ld<T>(FE)];
-  T st[C][bg_ld<T>(FE)];
-  T v[C][bg_ld<T>(FV)];
+  T p[C][bg_ld<T>(FM)];
+  float den[2][C];
+  float off[C];
+};
+
+template <typename T, int C> struct FavorSmemBwd {
+  T xq[2][C][bg_ld<T>(FE)];      // q, k, v rows: double-buffered (cp.async prefetch of the next chunk)
+  T xk[2][C][bg_ld<T>(FE)];
+  T v[2][C][bg_ld<T>(FV)];
+  T raw[2][C][bg_ld<T>(FE)];     // out, dout rows of the chunk (dead once G is built -> refilled at once)
+  T om[FE][bg_ld<T>(FE)];
+  T du[C][bg_ld<T>(FE)];         // d(pre-exp) tile; doubles as the staging buffer of the dq/dk/dv stores
   T g[C][bg_ld<T>(FV)];
   T pq[C][bg_ld<T>(FM)];
   T pk[C][bg_ld<T>(FM)];
@@ -56,8 +67,60 @@ template <typename T, int C> struct FavorSmemBwd {
   T p[C][bg_ld<T>(C)];
   T s[FM][bg_ld<T>(FV)];
   T r[FM][bg_ld<T>(FV)];
+  float den[C];
   float oq[C], ok[C], dof[C];
 };
+
+static_assert(sizeof(FavorSmemBwd<bf16, FavorCfg<bf16>::C>) <= 227 * 1024, "bwd smem (bf16) exceeds the 227 KB CTA limit");
+static_assert(sizeof(FavorSmemBwd<float, FavorCfg<float>::C>) <= 227 * 1024, "bwd smem (fp32) exceeds the 227 KB CTA limit");
+static_assert(2 * (sizeof(FavorSmemFwd<bf16, FavorCfg<bf16>::C>) + 1024) <= 227 * 1024, "fwd smem: two CTAs per SM");
+
+// ---- asynchronous tile loads (cp.async / LDGSTS): the next chunk's rows stream into shared memory while the
+// current chunk is being computed; rows >= valid are zero-filled by the zero-size form of the copy ----
+template <typename T> struct CpA { static constexpr int BYTES = sizeof(T) == 2 ? 16 : 4; static constexpr int EL = BYTES / sizeof(T); };
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst, const void* src, bool pred) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  int n = pred ? BYTES : 0;
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// issue the copies of a [C x 64] tile of rows (token stride ld); `active` = false issues nothing (tail of the loop)
+template <typename T, int C, int LD>
+__device__ __forceinline__ void issue_rows(const T* __restrict__ src, int64_t ld, int valid, T (*dst)[LD], bool active) {
+  if (!active) return;
+  constexpr int EL = CpA<T>::EL, VPR = FE / EL;
+  for (int i = threadIdx.x; i < C * VPR; i += BG_THREADS) {
+    int row = i / VPR, part = i % VPR;
+    bool ok = row < valid;
+    cp_async<CpA<T>::BYTES>(&dst[row][part * EL], ok ? src + (int64_t)row * ld + part * EL : src, ok);
+  }
+}
+
+// off[row] = hs * |x_row|^2 + add  from a tile already in smem; TPR adjacent lanes share a row
+template <typename T, int C, int LD>
+__device__ __forceinline__ void row_offsets(T (*x)[LD], float* off, float hs, float add) {
+  constexpr int TPR = BG_THREADS / C, EPT = FE / TPR;
+  const int row = threadIdx.x / TPR, part = threadIdx.x % TPR;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) { float v = to_f(x[row][part * EPT + j]); ss += v * v; }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (part == 0) off[row] = ss * hs + add;
+}
+
+// constant part of V' = [v | 1 | 0..]: the ones column (harmless for rows >= valid: their phi(k) rows are zero)
+template <typename T, int C, int LD>
+__device__ __forceinline__ void init_ones(T (*v)[LD]) {
+  for (int i = threadIdx.x; i < C * (FV - FE); i += BG_THREADS) {
+    int row = i / (FV - FE), col = FE + i % (FV - FE);
+    v[row][col] = from_f<T>(col == FE ? 1.f : 0.f);
+  }
+}
 
 // load a [C x 64] tile of rows (token stride ld) into smem, returning per-row sum of squares
 // (rows >= valid are zero-filled).  VPR threads share a row.
@@ -124,48 +187,72 @@ __device__ __forceinline__ void phi_rows(T (*x)[LDX], T (*om)[LDO], const float*
 // forward
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(BG_THREADS, 1)
+__global__ void __launch_bounds__(BG_THREADS, 2)
 favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
                  const float* __restrict__ omega, T* __restrict__ out, int64_t ld_out, float* __restrict__ den_out,
-                 const float* __restrict__ state_in, float* __restrict__ state_out, int Tlen, int H) {
+                 const float* __restrict__ state_in, float* __restrict__ state_out,
+                 const float* __restrict__ seg_states, int nseg, int seg_chunks, int Tlen, int H) {
   constexpr int C = FavorCfg<T>::C;
   using S = FavorSmemFwd<T, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int bh = blockIdx.x / nseg, seg = blockIdx.x % nseg;
+  const int b = bh / H, h = bh % H;
   const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
   const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
 
   load_omega<T>(omega, sm.om);
   BlockGemm<FM, FV, T> gs;   // running prefix state S' (fp32 master)
+  gs.clear();
   if (state_in) {            // continue a sequence (decode: append a block of tokens to a running state)
-    const float* si = state_in + (int64_t)blockIdx.x * FM * FV;
-    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; sm.s[row][col] = from_f<T>(x); });
-  } else {
-    for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
-    gs.clear();
+    const float* si = state_in + (int64_t)bh * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
   }
+  for (int sp = 0; sp < seg; ++sp) {   // exclusive prefix over the earlier segments' local sums (favor_segsum_kernel)
+    const float* si = seg_states + ((int64_t)bh * nseg + sp) * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
+  }
+  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
+  __syncthreads();
+  gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
   __syncthreads();
 
-  for (int t0 = 0; t0 < Tlen; t0 += C) {
+  const int t_begin = seg * seg_chunks * C;
+  const int t_end = (t_begin + seg_chunks * C < Tlen) ? t_begin + seg_chunks * C : Tlen;
+  init_ones<T, C>(sm.v);
+  T (*stage)[bg_ld<T>(FE)] = reinterpret_cast<T (*)[bg_ld<T>(FE)]>(&sm.pq[0][0]);   // output staging (pq is dead by then)
+  // software pipeline over chunks: group 2c = (q,k) of chunk c, group 2c+1 = v of chunk c
+  {
+    const int valid0 = (Tlen - t_begin < C) ? (Tlen - t_begin) : C;
+    issue_rows<T, C>(q + base + (int64_t)t_begin * ld, ld, valid0, sm.xq, t_begin < t_end);
+    issue_rows<T, C>(k + base + (int64_t)t_begin * ld, ld, valid0, sm.xk, t_begin < t_end);
+    cp_commit();
+    issue_rows<T, C>(v + base + (int64_t)t_begin * ld, ld, valid0, sm.v, t_begin < t_end);
+    cp_commit();
+  }
+  for (int t0 = t_begin; t0 < t_end; t0 += C) {
     const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
-    load_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
-    load_rows<T, C>(k + base + (int64_t)t0 * ld, ld, valid, sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
-    load_rows<T, C>(v + base + (int64_t)t0 * ld, ld, valid, sm.v, (float*)nullptr, 0.f, 0.f);
-    for (int i = threadIdx.x; i < C * (FV - FE); i += BG_THREADS) {
-      int row = i / (FV - FE), col = FE + i % (FV - FE);
-      sm.v[row][col] = from_f<T>((col == FE && row < valid) ? 1.f : 0.f);
-    }
+    const int tn = t0 + C;
+    const bool more = tn < t_end;
+    const int validn = (Tlen - tn < C) ? (Tlen - tn) : C;
+    cp_wait<1>();            // (q,k) of this chunk have landed (v may still be in flight)
+    __syncthreads();
+    row_offsets<T, C>(sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
     __syncthreads();
     phi_rows<T, C>(sm.xq, sm.om, sm.oq, valid, sm.pq);
     phi_rows<T, C>(sm.xk, sm.om, sm.ok, valid, sm.pk);
     __syncthreads();
+    issue_rows<T, C>(q + base + (int64_t)tn * ld, ld, validn, sm.xq, more);     // prefetch the next chunk's q, k
+    issue_rows<T, C>(k + base + (int64_t)tn * ld, ld, validn, sm.xk, more);
+    cp_commit();
     {
       BlockGemm<C, C, T> ga;
       ga.clear();
       ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
       ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
     }
+    cp_wait<1>();            // v of this chunk has landed
     __syncthreads();
     {
       BlockGemm<C, FV, T> go;
@@ -174,20 +261,70 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       go.template mma<true, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.s[0][0], bg_ld<T>(FV), FM);
       go.foreach ([&](int row, int col, float& x) { if (col == FE) sm.den[row] = x + F_EPS; });
       __syncthreads();
-      go.foreach ([&](int row, int col, float& x) { if (col < FE) sm.xq[row][col] = from_f<T>(x / sm.den[row]); });
+      go.foreach ([&](int row, int col, float& x) { if (col < FE) stage[row][col] = from_f<T>(x / sm.den[row]); });
     }
     __syncthreads();
-    store_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.xq);
+    store_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, stage);
     if (den_out)
       for (int i = threadIdx.x; i < valid; i += BG_THREADS) den_out[((int64_t)b * Tlen + t0 + i) * H + h] = sm.den[i];
     gs.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
+    __syncthreads();         // every warp is done reading v and s
     gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
-    __syncthreads();
+    issue_rows<T, C>(v + base + (int64_t)tn * ld, ld, validn, sm.v, more);      // prefetch the next chunk's v
+    cp_commit();
   }
-  if (state_out) {
-    float* so = state_out + (int64_t)blockIdx.x * FM * FV;
+  cp_wait<0>();
+  if (state_out && seg == nseg - 1) {
+    float* so = state_out + (int64_t)bh * FM * FV;
     gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
   }
+}
+
+// segment-local sums of the prefix state: seg_states[bh][seg] = sum_{t in segment} phi(k_t)^T [v_t | 1 | 0]
+template <typename T>
+__global__ void __launch_bounds__(BG_THREADS, 2)
+favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld, const float* __restrict__ omega,
+                    float* __restrict__ seg_states, int nseg, int seg_chunks, int Tlen, int H) {
+  constexpr int C = FavorCfg<T>::C;
+  using S = FavorSmemSeg<T, C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int bh = blockIdx.x / nseg, seg = blockIdx.x % nseg;
+  const int b = bh / H, h = bh % H;
+  const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
+  load_omega<T>(omega, sm.om);
+  init_ones<T, C>(sm.w[0]);
+  init_ones<T, C>(sm.w[1]);
+  BlockGemm<FM, FV, T> gs;
+  gs.clear();
+  const int t_begin = seg * seg_chunks * C;
+  const int t_end = (t_begin + seg_chunks * C < Tlen) ? t_begin + seg_chunks * C : Tlen;
+  {
+    const int valid0 = (Tlen - t_begin < C) ? (Tlen - t_begin) : C;
+    issue_rows<T, C>(k + base + (int64_t)t_begin * ld, ld, valid0, sm.x[0], t_begin < t_end);
+    issue_rows<T, C>(v + base + (int64_t)t_begin * ld, ld, valid0, sm.w[0], t_begin < t_end);
+    cp_commit();
+  }
+  int buf = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += C, buf ^= 1) {
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    const int tn = t0 + C;
+    const int validn = (Tlen - tn < C) ? (Tlen - tn) : C;
+    __syncthreads();         // the other buffer is free (its mma of the previous iteration is done)
+    issue_rows<T, C>(k + base + (int64_t)tn * ld, ld, validn, sm.x[buf ^ 1], tn < t_end);
+    issue_rows<T, C>(v + base + (int64_t)tn * ld, ld, validn, sm.w[buf ^ 1], tn < t_end);
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2, F_HALF_LOG_M);
+    __syncthreads();
+    phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
+    __syncthreads();
+    gs.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[buf][0][0], bg_ld<T>(FV), C);
+  }
+  cp_wait<0>();
+  float* so = seg_states + (int64_t)blockIdx.x * FM * FV;
+  gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -212,77 +349,165 @@ __device__ __forceinline__ void phi_bwd_reduce(SM& sm) {
   if (part == 0) sm.dof[row] = -acc;
 }
 
+// G = [dout/den | -(dout.out)/den | 0] for one chunk, from the raw out / dout tiles in smem (rows >= valid -> 0)
+template <typename T, int C, int LD, int LDG>
+__device__ __forceinline__ void make_g(T (*o_)[LD], T (*d_)[LD], const float* den, int valid, T (*g)[LDG]) {
+  constexpr int TPR = BG_THREADS / C, EPT = FE / TPR;
+  const int row = threadIdx.x / TPR, part = threadIdx.x % TPR;
+  const float inv = row < valid ? 1.f / den[row] : 0.f;
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    float ov = to_f(o_[row][part * EPT + j]), dv = to_f(d_[row][part * EPT + j]);
+    dot += ov * dv;
+    g[row][part * EPT + j] = from_f<T>(dv * inv);
+  }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (part == 0) {
+    g[row][FE] = from_f<T>(-dot * inv);
+#pragma unroll
+    for (int j = FE + 1; j < FV; ++j) g[row][j] = from_f<T>(0.f);
+  }
+}
+
+// den of one chunk: C floats, one 4-byte async copy per row
+template <int C>
+__device__ __forceinline__ void issue_den(const float* __restrict__ den, int stride, int valid, float* dst, bool active) {
+  if (!active) return;
+  for (int i = threadIdx.x; i < C; i += BG_THREADS) cp_async<4>(&dst[i], i < valid ? den + (int64_t)i * stride : den, i < valid);
+}
+
+// segment-local sums of the reverse state: seg_rstates[bh][seg] = sum_{t in segment} phi(q_t)^T G_t
+template <typename T>
+__global__ void __launch_bounds__(BG_THREADS, 2)
+favor_bwd_segsum_kernel(const T* __restrict__ q, int64_t ld, const float* __restrict__ omega, const T* __restrict__ out,
+                        const T* __restrict__ dout, int64_t ld_out, const float* __restrict__ den_in,
+                        float* __restrict__ seg_rstates, int nseg, int seg_chunks, int Tlen, int H) {
+  constexpr int C = FavorCfg<T>::C;
+  using S = FavorSmemSeg<T, C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int bh = blockIdx.x / nseg, seg = blockIdx.x % nseg;
+  const int b = bh / H, h = bh % H;
+  const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
+  const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
+  load_omega<T>(omega, sm.om);
+  BlockGemm<FM, FV, T> gr;
+  gr.clear();
+  const int t_begin = seg * seg_chunks * C;
+  const int t_end = (t_begin + seg_chunks * C < Tlen) ? t_begin + seg_chunks * C : Tlen;
+  auto issue = [&](int t0, int buf) {
+    const bool act = t0 < t_end;
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    issue_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.x[buf], act);
+    issue_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.raw[buf][0], act);
+    issue_rows<T, C>(dout + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.raw[buf][1], act);
+    issue_den<C>(den_in + ((int64_t)b * Tlen + t0) * H + h, H, valid, sm.den[buf], act);
+    cp_commit();
+  };
+  issue(t_begin, 0);
+  int buf = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += C, buf ^= 1) {
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    __syncthreads();         // the other buffers are free
+    issue(t0 + C, buf ^ 1);
+    cp_wait<1>();
+    __syncthreads();
+    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2, F_HALF_LOG_M);
+    make_g<T, C>(sm.raw[buf][0], sm.raw[buf][1], sm.den[buf], valid, sm.w[0]);
+    __syncthreads();
+    phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
+    __syncthreads();
+    gr.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[0][0][0], bg_ld<T>(FV), C);
+  }
+  cp_wait<0>();
+  float* so = seg_rstates + (int64_t)blockIdx.x * FM * FV;
+  gr.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
                  const float* __restrict__ omega, const T* __restrict__ out, const T* __restrict__ dout,
-                 int64_t ld_out, const float* __restrict__ den_in, const float* __restrict__ state_in,
+                 int64_t ld_out, const float* __restrict__ den_in, const float* __restrict__ seg_states,
+                 const float* __restrict__ seg_rstates, int nseg, int seg_chunks,
                  T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t ld_d, int Tlen, int H) {
   constexpr int C = FavorCfg<T>::C;
   using S = FavorSmemBwd<T, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int bh = blockIdx.x / nseg, seg = blockIdx.x % nseg;
+  const int b = bh / H, h = bh % H;
   const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
   const int64_t obase = (int64_t)b * Tlen * ld_out + (int64_t)h * FE;
   const int64_t dbase = (int64_t)b * Tlen * ld_d + (int64_t)h * FE;
-
-  load_omega<T>(omega, sm.om);
-  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.r[0][0])[i] = from_f<T>(0.f);
-  BlockGemm<FM, FV, T> gs, gr;   // forward prefix state (rolled back) and reverse state
-  gr.clear();
-  {
-    const float* si = state_in + (int64_t)blockIdx.x * FM * FV;
-    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
-  }
-  __syncthreads();
-
   const int nchunk = (Tlen + C - 1) / C;
-  for (int c = nchunk - 1; c >= 0; --c) {
+  const int c_begin = seg * seg_chunks;
+  const int c_end = (c_begin + seg_chunks < nchunk) ? c_begin + seg_chunks : nchunk;
+
+  // chunk loads: one cp.async group per chunk; q/k/v into buffer `buf`, out/dout/den into the single raw set
+  auto issue_qkv = [&](int c, int buf) {
+    if (c < c_begin) return;
     const int t0 = c * C;
     const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
-    load_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
-    load_rows<T, C>(k + base + (int64_t)t0 * ld, ld, valid, sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
-    load_rows<T, C>(v + base + (int64_t)t0 * ld, ld, valid, sm.v, (float*)nullptr, 0.f, 0.f);
-    for (int i = threadIdx.x; i < C * (FV - FE); i += BG_THREADS) {
-      int row = i / (FV - FE), col = FE + i % (FV - FE);
-      sm.v[row][col] = from_f<T>((col == FE && row < valid) ? 1.f : 0.f);
-    }
-    {  // G = [dout/den | -(dout.out)/den | 0]
-      constexpr int N = Vec<T>::N;
-      constexpr int VPR = FE / N;
-      for (int i = threadIdx.x; i < C * VPR; i += BG_THREADS) {
-        int row = i / VPR, part = i % VPR;
-        Vec<T> o_, d_;
-        float inv = 0.f;
-        if (row < valid) {
-          o_.load(out + obase + (int64_t)(t0 + row) * ld_out + part * N);
-          d_.load(dout + obase + (int64_t)(t0 + row) * ld_out + part * N);
-          inv = 1.f / den_in[((int64_t)b * Tlen + t0 + row) * H + h];
-        } else {
-#pragma unroll
-          for (int j = 0; j < N; ++j) { o_.v[j] = 0.f; d_.v[j] = 0.f; }
-        }
-        float dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < N; ++j) { dot += o_.v[j] * d_.v[j]; sm.g[row][part * N + j] = from_f<T>(d_.v[j] * inv); }
-#pragma unroll
-        for (int o = VPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (part == 0) {
-          sm.g[row][FE] = from_f<T>(-dot * inv);
-#pragma unroll
-          for (int j = FE + 1; j < FV; ++j) sm.g[row][j] = from_f<T>(0.f);
-        }
-      }
-    }
+    issue_rows<T, C>(q + base + (int64_t)t0 * ld, ld, valid, sm.xq[buf], true);
+    issue_rows<T, C>(k + base + (int64_t)t0 * ld, ld, valid, sm.xk[buf], true);
+    issue_rows<T, C>(v + base + (int64_t)t0 * ld, ld, valid, sm.v[buf], true);
+  };
+  auto issue_raw = [&](int c) {
+    if (c < c_begin) return;
+    const int t0 = c * C;
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    issue_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.raw[0], true);
+    issue_rows<T, C>(dout + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.raw[1], true);
+    issue_den<C>(den_in + ((int64_t)b * Tlen + t0) * H + h, H, valid, sm.den, true);
+  };
+  issue_qkv(c_end - 1, 0);
+  issue_raw(c_end - 1);
+  cp_commit();
+
+  load_omega<T>(omega, sm.om);
+  init_ones<T, C>(sm.v[0]);
+  init_ones<T, C>(sm.v[1]);
+  for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.r[0][0])[i] = from_f<T>(0.f);
+  BlockGemm<FM, FV, T> gs, gr;   // forward prefix state (rolled back) and reverse state
+  gs.clear();
+  gr.clear();
+  for (int sp = 0; sp <= seg; ++sp) {          // prefix state at the END of this segment
+    const float* si = seg_states + ((int64_t)bh * nseg + sp) * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
+  }
+  for (int sp = seg + 1; sp < nseg; ++sp) {    // reverse state carried in from the later segments
+    const float* si = seg_rstates + ((int64_t)bh * nseg + sp) * FM * FV;
+    gr.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
+  }
+  __syncthreads();
+  gr.foreach ([&](int row, int col, float& x) { sm.r[row][col] = from_f<T>(x); });
+
+  int buf = 0;
+  for (int c = c_end - 1; c >= c_begin; --c, buf ^= 1) {
+    const int t0 = c * C;
+    const int valid = (Tlen - t0 < C) ? (Tlen - t0) : C;
+    T (*xq)[bg_ld<T>(FE)] = sm.xq[buf];
+    T (*xk)[bg_ld<T>(FE)] = sm.xk[buf];
+    T (*vv)[bg_ld<T>(FV)] = sm.v[buf];
+    cp_wait<0>();            // this chunk's q, k, v, out, dout, den have landed
     __syncthreads();
-    phi_rows<T, C>(sm.xq, sm.om, sm.oq, valid, sm.pq);
-    phi_rows<T, C>(sm.xk, sm.om, sm.ok, valid, sm.pk);
+    row_offsets<T, C>(xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
+    make_g<T, C>(sm.raw[0], sm.raw[1], sm.den, valid, sm.g);
+    __syncthreads();
+    issue_qkv(c - 1, buf ^ 1);     // prefetch the previous chunk (reverse order) while this one is computed
+    issue_raw(c - 1);
+    cp_commit();
+    phi_rows<T, C>(xq, sm.om, sm.oq, valid, sm.pq);
+    phi_rows<T, C>(xk, sm.om, sm.ok, valid, sm.pk);
     __syncthreads();
     {  // roll the prefix state back to the start of this chunk
       BlockGemm<FM, FV, T> tmp;
       tmp.clear();
-      tmp.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
+      tmp.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &vv[0][0], bg_ld<T>(FV), C);
       constexpr int NA = sizeof(gs.acc) / sizeof(float);
       float* a = reinterpret_cast<float*>(gs.acc);
       const float* t = reinterpret_cast<const float*>(tmp.acc);
@@ -296,7 +521,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
       ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
       ga.clear();
-      ga.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &sm.v[0][0], bg_ld<T>(FV), FV);
+      ga.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &vv[0][0], bg_ld<T>(FV), FV);
       ga.foreach ([&](int row, int col, float& x) { sm.p[row][col] = from_f<T>(col <= row ? x : 0.f); });
     }
     __syncthreads();
@@ -315,33 +540,35 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       BlockGemm<C, FE, T> gx;
       gx.clear();
       gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      __syncthreads();       // du is re-used as the store staging buffer
       gx.foreach ([&](int row, int col, float& x) {
-        sm.st[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(sm.xq[row][col]));
+        sm.du[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(xq[row][col]));
       });
     }
     __syncthreads();
-    store_rows<T, C>(dq + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    store_rows<T, C>(dq + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.du);
     // ---- dk ----
     {
       BlockGemm<C, FM, T> gd;
       gd.clear();
       gd.template mma<false, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pq[0][0], bg_ld<T>(FM), C);
-      gd.template mma<true, true>(&sm.v[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV), FV);
+      gd.template mma<true, true>(&vv[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV), FV);
       gd.foreach ([&](int row, int col, float& x) { sm.w[row][col] = from_f<T>(x * to_f(sm.pk[row][col])); });
     }
-    __syncthreads();
+    __syncthreads();         // also: the dq store has finished reading du
     phi_bwd_reduce<T, C>(sm);
     __syncthreads();
     {
       BlockGemm<C, FE, T> gx;
       gx.clear();
       gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      __syncthreads();
       gx.foreach ([&](int row, int col, float& x) {
-        sm.st[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(sm.xk[row][col]));
+        sm.du[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(xk[row][col]));
       });
     }
     __syncthreads();
-    store_rows<T, C>(dk + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    store_rows<T, C>(dk + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.du);
     __syncthreads();
     // ---- dv ----
     {
@@ -349,15 +576,16 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       gv.clear();
       gv.template mma<false, false>(&sm.a[0][0], bg_ld<T>(C), &sm.g[0][0], bg_ld<T>(FV), C);
       gv.template mma<true, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.r[0][0], bg_ld<T>(FV), FM);
-      gv.foreach ([&](int row, int col, float& x) { if (col < FE) sm.st[row][col] = from_f<T>(x); });
+      gv.foreach ([&](int row, int col, float& x) { if (col < FE) sm.du[row][col] = from_f<T>(x); });
     }
     __syncthreads();
-    store_rows<T, C>(dv + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.st);
+    store_rows<T, C>(dv + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.du);
     // ---- reverse state ----
     gr.template mma<false, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.g[0][0], bg_ld<T>(FV), C);
+    __syncthreads();         // every warp is done with r (dk, dv) and with du (dv store)
     gr.foreach ([&](int row, int col, float& x) { sm.r[row][col] = from_f<T>(x); });
-    __syncthreads();
   }
+  cp_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -417,29 +645,75 @@ __global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+// Segment plan: T is cut into `nseg` segments of `seg_chunks` chunks so that B*H*nseg CTAs fill the chip a few
+// times over (the sequential chunk loop is latency bound); the segments are stitched together by the
+// segment-local state sums written by the *_segsum kernels.
+template <typename T> static void favor_plan(int B, int T_, int H, int* nseg, int* seg_chunks) {
+  constexpr int C = FavorCfg<T>::C;
+  int nchunk = (T_ + C - 1) / C;
+  int want = (4 * emo_num_sms() + B * H - 1) / (B * H);
+  int maxseg = nchunk / 2 > 0 ? nchunk / 2 : 1;
+  int n = want < maxseg ? want : maxseg;
+  if (n < 1) n = 1;
+  int sc = (nchunk + n - 1) / n;
+  *seg_chunks = sc;
+  *nseg = (nchunk + sc - 1) / sc;
+}
+
+extern "C" int emo_favor_nseg(int B, int T, int H, int dtype) {
+  int nseg = 1, sc = 1;
+  if (B * H <= 0 || T <= 0) return 1;
+  if (dtype == EMO_BF16) favor_plan<bf16>(B, T, H, &nseg, &sc);
+  else favor_plan<float>(B, T, H, &nseg, &sc);
+  return nseg;
+}
+
 template <typename T>
 static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
-                            int64_t ld_out, float* den, const float* state_in, float* state_out, int B, int T_, int H,
-                            cudaStream_t s) {
+                            int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
+                            int B, int T_, int H, cudaStream_t s) {
   constexpr int C = FavorCfg<T>::C;
   size_t smem = sizeof(FavorSmemFwd<T, C>);
-  EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  favor_fwd_kernel<T><<<B * H, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
-                                                      den, state_in, state_out, T_, H);
+  int nseg = 1, sc = (T_ + C - 1) / C;
+  if (seg_states) favor_plan<T>(B, T_, H, &nseg, &sc);
+  static bool configured = false;
+  if (!configured) {
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_segsum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FavorSmemSeg<T, C>)));
+    configured = true;
+  }
+  if (seg_states) {
+    favor_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)k, (const T*)v, ld, omega, seg_states, nseg, sc, T_, H);
+    EMO_LAUNCH_CHECK();
+  }
+  favor_fwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
+                                                             den, state_in, state_out, seg_states, nseg, sc, T_, H);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
 template <typename T>
 static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega,
                             const void* out, const void* dout, int64_t ld_out, const float* den,
-                            const float* state_in, void* dq, void* dk, void* dv, int64_t ld_d, int B, int T_, int H,
-                            cudaStream_t s) {
+                            const float* seg_states, float* seg_rstates, void* dq, void* dk, void* dv, int64_t ld_d,
+                            int B, int T_, int H, cudaStream_t s) {
   constexpr int C = FavorCfg<T>::C;
   size_t smem = sizeof(FavorSmemBwd<T, C>);
-  EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  favor_bwd_kernel<T><<<B * H, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (const T*)out,
-                                                      (const T*)dout, ld_out, den, state_in, (T*)dq, (T*)dk, (T*)dv,
-                                                      ld_d, T_, H);
+  int nseg = 1, sc = 1;
+  favor_plan<T>(B, T_, H, &nseg, &sc);
+  static bool configured = false;
+  if (!configured) {
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_bwd_segsum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FavorSmemSeg<T, C>)));
+    configured = true;
+  }
+  if (nseg > 1) {
+    favor_bwd_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)q, ld, omega, (const T*)out, (const T*)dout,
+                                                                      ld_out, den, seg_rstates, nseg, sc, T_, H);
+    EMO_LAUNCH_CHECK();
+  }
+  favor_bwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (const T*)out,
+                                                             (const T*)dout, ld_out, den, seg_states, seg_rstates, nseg, sc,
+                                                             (T*)dq, (T*)dk, (T*)dv, ld_d, T_, H);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
@@ -447,30 +721,30 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
-                             void* out, int64_t ld_out, float* den, const float* state_in, float* state_out, int B,
-                             int T, int H, int dtype, void* stream) {
+                             void* out, int64_t ld_out, float* den, const float* state_in, float* state_out,
+                             float* seg_states, int B, int T, int H, int dtype, void* stream) {
   int esz = dtype == EMO_BF16 ? 2 : 4;
   EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "emo_favor_fwd: pointers must be 16-byte aligned");
   EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0, "emo_favor_fwd: row strides must be 16-byte multiples");
   if (B * H == 0 || T == 0) return EMO_OK;
-  if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, B, T, H, (cudaStream_t)stream);
-  return favor_fwd_launch<float>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, B, T, H, (cudaStream_t)stream);
+  if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, seg_states, B, T, H, (cudaStream_t)stream);
+  return favor_fwd_launch<float>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, seg_states, B, T, H, (cudaStream_t)stream);
 }
 
 extern "C" int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
                              const void* out, const void* dout, int64_t ld_out, const float* den,
-                             const float* state_in, void* dq, void* dk, void* dv, int64_t ld_dqkv, int B, int T,
-                             int H, int dtype, void* stream) {
+                             const float* seg_states, float* seg_rstates, void* dq, void* dk, void* dv,
+                             int64_t ld_dqkv, int B, int T, int H, int dtype, void* stream) {
   int esz = dtype == EMO_BF16 ? 2 : 4;
   EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out) && aligned16(dout) && aligned16(dq) &&
                   aligned16(dk) && aligned16(dv), "emo_favor_bwd: pointers must be 16-byte aligned");
   EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0 && (ld_dqkv * esz) % 16 == 0,
               "emo_favor_bwd: row strides must be 16-byte multiples");
-  EMO_REQUIRE(den != nullptr && state_in != nullptr, "emo_favor_bwd: den and state_in are required");
+  EMO_REQUIRE(den != nullptr && seg_states != nullptr && seg_rstates != nullptr, "emo_favor_bwd: den, seg_states and seg_rstates are required");
   if (B * H == 0 || T == 0) return EMO_OK;
   if (dtype == EMO_BF16)
-    return favor_bwd_launch<bf16>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, state_in, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
-  return favor_bwd_launch<float>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, state_in, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
+    return favor_bwd_launch<bf16>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, seg_states, seg_rstates, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
+  return favor_bwd_launch<float>(q, k, v, ld_qkv, omega, out, dout, ld_out, den, seg_states, seg_rstates, dq, dk, dv, ld_dqkv, B, T, H, (cudaStream_t)stream);
 }
 
 extern "C" int emo_favor_step(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,

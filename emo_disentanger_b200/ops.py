@@ -209,24 +209,37 @@ def _row_ld(t):
     return t.stride(-2) if t.shape[-2] > 1 else t.shape[-1]
 
 
-def favor_fwd(q, k, v, omega, out, den=None, state_out=None, state_in=None):
-    """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view."""
+def favor_nseg(B, T, H, dtype):
+    return int(L.lib().emo_favor_nseg(B, T, H, F32 if dtype == torch.float32 else BF16))
+
+
+def favor_workspace(B, T, H, dtype, device):
+    """[B,H,nseg,128,80] fp32 segment-state workspace for favor_fwd(seg_states=...) / favor_bwd"""
+    return torch.empty(B, H, favor_nseg(B, T, H, dtype), 128, 80, dtype=torch.float32, device=device)
+
+
+def favor_fwd(q, k, v, omega, out, den=None, state_out=None, state_in=None, seg_states=None):
+    """q,k,v: [B,T,H,64] views with a common token stride; out [B,T,H*64] view.  seg_states (from
+    favor_workspace) switches on the segment-parallel schedule and is what favor_bwd consumes."""
     B, T, H, E = q.shape
     ld = _favor_ld(q, k, v)
+    assert seg_states is None or state_in is None
     tk = TIMER.start("favor_fwd")
     L.check(L.lib().emo_favor_fwd(_p(q), _p(k), _p(v), ld, _p(omega), _p(out), _row_ld(out), _p(den),
-                                  _p(state_in), _p(state_out), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
+                                  _p(state_in), _p(state_out), _p(seg_states), B, T, H, _dt(q), _stream()), "emo_favor_fwd")
     TIMER.stop(tk, float(B * T * H * 64 * 4 * q.element_size()))      # algorithmic bytes: read q,k,v + write out
     return out
 
 
-def favor_bwd(q, k, v, omega, out, dout, den, state, dq, dk, dv):
+def favor_bwd(q, k, v, omega, out, dout, den, seg_states, dq, dk, dv, seg_rstates=None):
     B, T, H, E = q.shape
     ld = _favor_ld(q, k, v)
     ldd = _favor_ld(dq, dk, dv)
+    if seg_rstates is None:
+        seg_rstates = torch.empty_like(seg_states)
     tk = TIMER.start("favor_bwd")
     L.check(L.lib().emo_favor_bwd(_p(q), _p(k), _p(v), ld, _p(omega), _p(out), _p(dout), _row_ld(out),
-                                  _p(den), _p(state), _p(dq), _p(dk), _p(dv), ldd, B, T, H, _dt(q),
+                                  _p(den), _p(seg_states), _p(seg_rstates), _p(dq), _p(dk), _p(dv), ldd, B, T, H, _dt(q),
                                   _stream()), "emo_favor_bwd")
     TIMER.stop(tk, float(B * T * H * 64 * 8 * q.element_size()))      # read q,k,v,out,dout + write dq,dk,dv
 

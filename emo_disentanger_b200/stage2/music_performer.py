@@ -107,8 +107,8 @@ class MusicPerformer(Stage2Base):
             q, k, v = (q3[:, :, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
             att = new(R, d)
             den = new(B, T, H, dtype=torch.float32) if save else None
-            state = new(B, H, 128, 80, dtype=torch.float32) if save else None
-            ops.favor_fwd(q, k, v, omegas[l], att.view(B, T, d), den, state)
+            state = ops.favor_workspace(B, T, H, dt, dev)      # segment-state sums (kept for backward when save)
+            ops.favor_fwd(q, k, v, omegas[l], att.view(B, T, d), den, seg_states=state)
             s1 = new(R, d)
             ops.linear_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"), s1,
                            bias=self._wv(Wf, nm + "attention.out_projection.bias"),

@@ -119,15 +119,22 @@ int emo_colsum(const void* x, int64_t ld, int64_t M, int64_t N, float* out, int 
  * written to HBM.  out [B,T,H*64] (ld_out); den [B,T,H] fp32 = phi(q).cumsum(phi(k)) + 1e-6;
  * state_in (NULL = start of sequence) / state_out (may be NULL; may alias state_in) [B,H,128,80] fp32:
  * prefix state [sum phi(k) v^T | sum phi(k) | 0] before / after these T tokens (decode appends blocks
- * of tokens -- a lead-sheet bar -- to a running state, stage2_accompaniment/inference.py:293-307). */
+ * of tokens -- a lead-sheet bar -- to a running state, stage2_accompaniment/inference.py:293-307).
+ * seg_states (NULL = one sequential pass per (b,h)): workspace [B,H,nseg,128,80] fp32, nseg =
+ * emo_favor_nseg(B,T,H,dtype).  When given, the sequence is cut into nseg segments that run in parallel
+ * (B*H*nseg CTAs): a first kernel writes every segment's local state sum there, the main kernel starts each
+ * segment from the exclusive prefix of those sums.  The same buffer is what emo_favor_bwd needs. */
+int emo_favor_nseg(int B, int T, int H, int dtype);
 int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
-                  void* out, int64_t ld_out, float* den, const float* state_in, float* state_out, int B,
-                  int T, int H, int dtype, void* stream);
-/* reverse-scan backward; state_in = state_out of the forward call. */
+                  void* out, int64_t ld_out, float* den, const float* state_in, float* state_out,
+                  float* seg_states, int B, int T, int H, int dtype, void* stream);
+/* reverse-scan backward, segment-parallel like the forward: seg_states = the forward's workspace (required,
+ * from a forward call with state_in == NULL); seg_rstates = scratch of the same shape for the reverse state
+ * sum phi(q)^T G of every segment. */
 int emo_favor_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
                   const void* out, const void* dout, int64_t ld_out, const float* den,
-                  const float* state_in, void* dq, void* dk, void* dv, int64_t ld_dqkv, int B,
-                  int T, int H, int dtype, void* stream);
+                  const float* seg_states, float* seg_rstates, void* dq, void* dk, void* dv, int64_t ld_dqkv,
+                  int B, int T, int H, int dtype, void* stream);
 /* one decode step per sequence (recurrent form): state [B,H,128,80] fp32 updated in place;
  * q,k,v rows for the new token [B,H,64] (row stride ld_qkv per sequence). */
 int emo_favor_step(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,

@@ -11,7 +11,8 @@ q, k, v = (qkv[:, :, i * d:(i + 1) * d].unflatten(-1, (H, 64)) for i in range(3)
 om = torch.randn(64, 64, device=dev)
 out = torch.empty(B, T, d, device=dev, dtype=torch.bfloat16)
 den = torch.empty(B, T, H, device=dev)
-st = torch.empty(B, H, 128, 80, device=dev)
+st = ops.favor_workspace(B, T, H, torch.bfloat16, dev)
+print('nseg', st.shape[2])
 dout = torch.randn(B, T, d, device=dev).to(torch.bfloat16)
 dqkv = torch.empty_like(qkv)
 dq, dk, dv = (dqkv[:, :, i * d:(i + 1) * d].unflatten(-1, (H, 64)) for i in range(3))
@@ -30,7 +31,7 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-f = timeit(lambda: ops.favor_fwd(q, k, v, om, out, den, st))
+f = timeit(lambda: ops.favor_fwd(q, k, v, om, out, den, seg_states=st))
 b = timeit(lambda: ops.favor_bwd(q, k, v, om, out, dout, den, st, dq, dk, dv))
 tok = B * T
 print("favor fwd B=%d: %8.1f us  %7.1f GB/s algorithmic (4 KiB/token)" % (B, f, tok * 4096 / f / 1e3))
