@@ -16,7 +16,7 @@ vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("act", i32), ("aux", vp), ("aux_out", vp), ("ld_aux", i64),
                 ("aux_scale", f32), ("drop_p", f32), ("seed", u64), ("residual", vp), ("ld_res", i64),
-                ("alpha", f32), ("accumulate", i32), ("rowscale", vp)]
+                ("alpha", f32), ("accumulate", i32), ("rowscale", vp), ("colsum", vp)]
 
 
 SIGNATURES = {
@@ -26,7 +26,7 @@ SIGNATURES = {
     "emo_embed_rows": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, vp], i32),
     "emo_embed_bwd": ([vp, vp, i64, i64, vp, vp, vp, i32, i32, i32, f32, f32, u64, i64, i32, vp], i32),
     "emo_ln_fwd": ([vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp], i32),
-    "emo_ln_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, vp, vp, i64, i32, i32, vp], i32),
+    "emo_ln_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, vp, vp, vp, i64, i32, i32, vp], i32),
     "emo_dropout_apply": ([vp, vp, i64, f32, u64, i32, vp], i32),
     "emo_gemm": ([i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, i32, C.POINTER(Epilogue), vp], i32),
     "emo_colsum": ([vp, i64, i64, i64, vp, i32, vp], i32),

@@ -263,19 +263,20 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
                                                      const float* __restrict__ gamma, const T* __restrict__ add_in,
                                                      T* __restrict__ dx, T* __restrict__ dx_drop, uint32_t thr,
                                                      float keep_scale, uint64_t seed, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int64_t rows) {
+                                                     float* __restrict__ dbeta, float* __restrict__ dxsum,
+                                                     int64_t rows) {
   using R = RowRegs<T>;
   constexpr int E = R::NV * R::N;
-  __shared__ float s_dg[LN_D], s_db[LN_D];
-  for (int i = threadIdx.x; i < LN_D; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __shared__ float s_dg[LN_D], s_db[LN_D], s_dx[LN_D];
+  for (int i = threadIdx.x; i < LN_D; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; s_dx[i] = 0.f; }
   __syncthreads();
   int lane = threadIdx.x & 31;
   int wpb = blockDim.x >> 5;
-  float g_[E], dg[E], db[E];
+  float g_[E], dg[E], db[E], dxs[E];
 #pragma unroll
   for (int j = 0; j < R::NV; ++j)
 #pragma unroll
-    for (int i = 0; i < R::N; ++i) { g_[j * R::N + i] = gamma[R::col(j, lane) + i]; dg[j * R::N + i] = 0.f; db[j * R::N + i] = 0.f; }
+    for (int i = 0; i < R::N; ++i) { g_[j * R::N + i] = gamma[R::col(j, lane) + i]; dg[j * R::N + i] = 0.f; db[j * R::N + i] = 0.f; dxs[j * R::N + i] = 0.f; }
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
     R rdy, rx;
     rdy.load(dy + row * LN_D, lane);
@@ -321,6 +322,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
       }
       rdy.store(dx_drop + row * LN_D, lane);
     }
+    if (dxsum) {      // column sums of the tensor that feeds the projection below (dx_drop if written, else dx)
+#pragma unroll
+      for (int i = 0; i < E; ++i) dxs[i] += to_f(from_f<T>(rdy.v[i]));
+    }
   }
 #pragma unroll
   for (int j = 0; j < R::NV; ++j)
@@ -328,17 +333,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int i = 0; i < R::N; ++i) {
       atomicAdd(&s_dg[R::col(j, lane) + i], dg[j * R::N + i]);
       atomicAdd(&s_db[R::col(j, lane) + i], db[j * R::N + i]);
+      if (dxsum) atomicAdd(&s_dx[R::col(j, lane) + i], dxs[j * R::N + i]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < LN_D; i += blockDim.x) {
     atomicAdd(dgamma + i, s_dg[i]);
     atomicAdd(dbeta + i, s_db[i]);
+    if (dxsum) atomicAdd(dxsum + i, s_dx[i]);
   }
 }
 
 extern "C" int emo_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                           const float* gamma, const void* add_in, void* dx, void* dx_drop, float drop_p,
-                          uint64_t seed, float* dgamma, float* dbeta, int64_t rows, int d, int dtype,
+                          uint64_t seed, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int d, int dtype,
                           void* stream) {
   EMO_REQUIRE(d == LN_D, "emo_ln_bwd: d must be 512 (got %d)", d);
   if (rows == 0) return EMO_OK;
@@ -348,9 +355,9 @@ extern "C" int emo_ln_bwd(const void* dy, const void* x, const float* mean, cons
   float ks = 1.f / (1.f - drop_p);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == EMO_BF16)
-    ln_bwd_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)add_in, (bf16*)dx, (bf16*)dx_drop, thr, ks, seed, dgamma, dbeta, rows);
+    ln_bwd_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)add_in, (bf16*)dx, (bf16*)dx_drop, thr, ks, seed, dgamma, dbeta, dxsum, rows);
   else
-    ln_bwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, (const float*)x, mean, rstd, gamma, (const float*)add_in, (float*)dx, (float*)dx_drop, thr, ks, seed, dgamma, dbeta, rows);
+    ln_bwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, (const float*)x, mean, rstd, gamma, (const float*)add_in, (float*)dx, (float*)dx_drop, thr, ks, seed, dgamma, dbeta, dxsum, rows);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
@@ -391,8 +398,53 @@ extern "C" int emo_dropout_apply(const void* x, void* y, int64_t n, float drop_p
 }
 
 // ---------------------------------------------------------------------------------------------
-// column sums (bias gradients): block = 32 lanes x 8 row-groups; thread owns 2 adjacent columns
+// column sums (bias gradients).  Vector kernel: a warp covers 32 x 16 B of one row (256 bf16 / 128 fp32
+// columns, whole 128-byte lines), 8 warps x 4 rows in flight per CTA; fp32 partials meet in smem, one
+// atomic per column per CTA.  Scalar kernel: unaligned / odd shapes.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N,
+                                                         int64_t Npad, float* __restrict__ out, int rows_per_block) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int CW = 32 * VN;                 // columns per CTA
+  __shared__ float s[8][CW];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * CW + lane * VN;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  float acc[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+  if (c < Npad) {                             // Npad % VN == 0: a vector is all-in or all-out (pad columns are read, not summed out)
+    int64_t r = r0 + w;
+    for (; r + 24 < r1; r += 32) {            // 4 independent 16-byte loads in flight per thread
+      Vec<T> t0, t1, t2, t3;
+      t0.load(x + r * ld + c);
+      t1.load(x + (r + 8) * ld + c);
+      t2.load(x + (r + 16) * ld + c);
+      t3.load(x + (r + 24) * ld + c);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] += (t0.v[j] + t1.v[j]) + (t2.v[j] + t3.v[j]);
+    }
+    for (; r < r1; r += 8) {
+      Vec<T> t;
+      t.load(x + r * ld + c);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) acc[j] += t.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VN; ++j) s[w][lane * VN + j] = acc[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < CW; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][i];
+    int64_t cc = (int64_t)blockIdx.x * CW + i;
+    if (cc < N) atomicAdd(out + cc, t);
+  }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N, float* __restrict__ out,
                               int rows_per_block) {
@@ -422,9 +474,26 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t M, in
 }
 extern "C" int emo_colsum(const void* x, int64_t ld, int64_t M, int64_t N, float* out, int dtype, void* stream) {
   if (M == 0 || N == 0) return EMO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int vn = dtype == EMO_BF16 ? 8 : 4;
+  // ragged N is fine when the row is padded (ld >= N rounded up to a vector): the pad columns are read, not summed
+  const int64_t npad = (N + vn - 1) / vn * vn;
+  const bool vec = (ld % vn == 0) && (npad <= ld) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    const int cw = 32 * vn;
+    const unsigned gx = (unsigned)((npad + cw - 1) / cw);
+    int64_t want = (4 * (int64_t)emo_num_sms() + gx - 1) / gx;          // ~4 CTAs per SM
+    int64_t rpb = (M + want - 1) / want;
+    rpb = (rpb + 31) / 32 * 32;
+    if (rpb < 32) rpb = 32;
+    dim3 grid(gx, (unsigned)((M + rpb - 1) / rpb));
+    if (dtype == EMO_BF16) colsum_vec_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, ld, M, N, npad, out, (int)rpb);
+    else colsum_vec_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ld, M, N, npad, out, (int)rpb);
+    EMO_LAUNCH_CHECK();
+    return EMO_OK;
+  }
   int rpb = 256;
   dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + rpb - 1) / rpb));
-  cudaStream_t s = (cudaStream_t)stream;
   if (dtype == EMO_BF16) colsum_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, ld, M, N, out, rpb);
   else colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ld, M, N, out, rpb);
   EMO_LAUNCH_CHECK();

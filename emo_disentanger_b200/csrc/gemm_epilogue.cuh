@@ -17,6 +17,7 @@ struct EpiParams {
   float alpha;
   int accumulate;
   const float* rowscale;
+  float* colsum;     // optional fp32 [N]: += column sums of the stored values (fused bias gradient)
   int64_t n_total;   // logical N (dropout element index = m * n_total + n)
 };
 
@@ -30,7 +31,7 @@ static inline EpiParams make_epi(const emo_epilogue* e, int64_t N) {
     p.bias = e->bias; p.act = e->act; p.aux = e->aux; p.aux_out = e->aux_out; p.ld_aux = e->ld_aux;
     p.aux_scale = e->aux_scale; p.drop_thr = emo_drop_thr(e->drop_p);
     p.keep_scale = 1.f / (1.f - e->drop_p); p.seed = e->seed; p.residual = e->residual; p.ld_res = e->ld_res;
-    p.alpha = e->alpha; p.accumulate = e->accumulate; p.rowscale = (const float*)e->rowscale;
+    p.alpha = e->alpha; p.accumulate = e->accumulate; p.rowscale = (const float*)e->rowscale; p.colsum = e->colsum;
   }
   return p;
 }

@@ -4,8 +4,12 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> 4/6-stage smem ring
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16 (one elected lane), fp32
 //                              accumulators in TMEM, double-buffered (2 x BN columns)
-//   warps 2..9  epilogue       tcgen05.ld (32x32b.x32) -> bias / activation / dropout / residual
-//                              -> 16-byte global stores, or fp32 atomic accumulate (split-K wgrad)
+//   warps 2..9  epilogue       tcgen05.ld (32x32b.x32) -> bias / activation / dropout / residual.
+//                              bf16 outputs: residual / aux tiles arrive by TMA load into a per-warp
+//                              128B-swizzled staging buffer, results leave by TMA store (whole 128-byte
+//                              lines; a row-per-lane global store touches 32 lines per instruction and
+//                              made the K=512 shapes LSU-bound).  fp32 outputs: direct 16-byte stores, or
+//                              fp32 atomic accumulate (split-K wgrad)
 // Tile 128 x BN (BN = 256 or 128) x 64.  Three contractions share the kernel through the operand
 // "major-ness" encoded in the TMA boxes, the smem descriptors and the instruction descriptor:
 //   NT (forward)  A K-major,  B K-major          NN (dgrad)  A K-major,  B MN-major
@@ -21,6 +25,15 @@ namespace tc {
 constexpr int BM = 128, BK = 64;
 constexpr int NUM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 64 bf16 columns, 128B swizzle
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;   // double-buffered per warp: 64 KB
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+template <int BN> struct StageCfg {
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  static constexpr int RAW = (SMEM_BUDGET - EPI_STAGE_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = RAW > 6 ? 6 : RAW;
+};
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,6 +67,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -102,19 +126,20 @@ struct Params {
   void* C;
   int64_t ldc;
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int tma_epi;   // bf16 output leaves through the smem-staged TMA store path
+  int has_r;     // ... and the residual / aux tile arrives by TMA load (tmR)
+  int debug;     // perf triage only (emo_gemm_debug): 1 = skip the epilogue body, 2 = skip the MMAs, 4 = skip TMEM loads+math (stores only)
   EpiParams ep;
 };
 
 
 // ---- epilogue of one 32-column chunk of one accumulator row (lane = row) -------------------------
-// Fast path: every branch below is warp-uniform and sits OUTSIDE the per-element loops; all global
-// accesses are 16-byte vectors.  Order of operations = include/emo_b200.h (emo_epilogue).
-template <typename TOut>
-__device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
-  const EpiParams& ep = p.ep;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+// Every branch below is warp-uniform and sits OUTSIDE the per-element loops.  Order of operations =
+// include/emo_b200.h (emo_epilogue): alpha, rowscale, bias, activation (aux), dropout.
+// `a` = the 32 aux values of this row chunk (acts 3, 4), already in registers.
+template <int PART = 0>   // 0 = everything, 1 = linear part only (alpha, rowscale, bias), 2 = activation + dropout only
+__device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32], int64_t m, int64_t nb, const EpiParams& ep) {
+  if (PART != 2) {
   if (ep.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
@@ -132,39 +157,20 @@ __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m
       v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
+  }
+  if (PART == 1) return;
   if (ep.act == EMO_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (ep.act == EMO_ACT_GELU_NEW) {
-    if (ep.aux_out) {
-      TOut* arow = reinterpret_cast<TOut*>(ep.aux_out) + m * ep.ld_aux + nb;
-#pragma unroll
-      for (int j = 0; j < 32; j += Vec<TOut>::N) {
-        Vec<TOut> t;
-#pragma unroll
-        for (int i = 0; i < Vec<TOut>::N; ++i) t.v[i] = v[j + i];
-        t.store(arow + j);
-      }
-    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
-  } else if (ep.act == EMO_ACT_RELU_MASK_BWD || ep.act == EMO_ACT_GELU_NEW_BWD) {
-    const bf16* arow = reinterpret_cast<const bf16*>(ep.aux) + m * ep.ld_aux + nb;
-    float a[32];
+  } else if (ep.act == EMO_ACT_RELU_MASK_BWD) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      Vec<bf16> t;
-      t.load(arow + j);
+    for (int j = 0; j < 32; ++j) v[j] = (a[j] != 0.f) ? v[j] * ep.aux_scale : 0.f;
+  } else if (ep.act == EMO_ACT_GELU_NEW_BWD) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[j + i] = t.v[i];
-    }
-    if (ep.act == EMO_ACT_RELU_MASK_BWD) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (a[j] != 0.f) ? v[j] * ep.aux_scale : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_f(a[j]);
-    }
+    for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_f(a[j]);
   }
   if (ep.drop_thr) {
     const uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
@@ -182,6 +188,56 @@ __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = emo_drop_keep(ep.seed, e0 + j, ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
     }
+  }
+}
+
+// column sums of a 32(rows = lanes) x 32(columns = v[]) block: butterfly transpose-reduce, lane l ends
+// with the sum of column l; one coalesced fp32 red per warp (bias gradient fused into the dgrad GEMM)
+__device__ __forceinline__ void epi_colsum32(float (&v)[32], int lane, float* dst) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      float send = up ? v[j] : v[j + s];
+      float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  atomicAdd(dst + lane, v[0]);
+}
+
+// direct path (fp32 outputs, split-K accumulate, gelu aux_out): row-per-lane 16-byte global accesses
+template <typename TOut>
+__device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
+  const EpiParams& ep = p.ep;
+  float v[32], a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (ep.act == EMO_ACT_RELU_MASK_BWD || ep.act == EMO_ACT_GELU_NEW_BWD) {
+    const bf16* arow = reinterpret_cast<const bf16*>(ep.aux) + m * ep.ld_aux + nb;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      Vec<bf16> t;
+      t.load(arow + j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[j + i] = t.v[i];
+    }
+  }
+  if (ep.act == EMO_ACT_GELU_NEW && ep.aux_out) {
+    // pre-activation (alpha, rowscale, bias applied) goes to aux_out: run the linear part first
+    epi_math32<1>(v, a, m, nb, ep);
+    TOut* arow = reinterpret_cast<TOut*>(ep.aux_out) + m * ep.ld_aux + nb;
+#pragma unroll
+    for (int j = 0; j < 32; j += Vec<TOut>::N) {
+      Vec<TOut> t;
+#pragma unroll
+      for (int i = 0; i < Vec<TOut>::N; ++i) t.v[i] = v[j + i];
+      t.store(arow + j);
+    }
+    epi_math32<2>(v, a, m, nb, ep);
+  } else {
+    epi_math32(v, a, m, nb, ep);
   }
   if (ep.accumulate) {
     float* crow = reinterpret_cast<float*>(p.C) + m * p.ldc + nb;
@@ -209,6 +265,55 @@ __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], int64_t m
   }
 }
 
+// TMA path (bf16 outputs), one 32-column half of a 64-column staging buffer.  `buf` holds the residual or
+// aux tile of the same coordinates when p.has_r (TMA-loaded, 128B swizzle); the result overwrites it.
+// row = lane's row inside the 32-row box; chunk c (16 B) of row r sits at r*128 + ((c ^ (r & 7)) << 4).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 t;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr) : "memory");
+  return t;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& t) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+}
+__device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t buf, int row, int half,
+                                             int64_t m, int64_t nb, bool row_ok, const Params& p) {
+  const EpiParams& ep = p.ep;
+  float v[32], a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  const uint32_t rowp = buf + row * 128;
+  const int sw = row & 7;
+  if (p.has_r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 t = lds128(rowp + (((half * 4 + c) ^ sw) << 4));
+      unpack_bf16x2(t.x, a[8 * c], a[8 * c + 1]); unpack_bf16x2(t.y, a[8 * c + 2], a[8 * c + 3]);
+      unpack_bf16x2(t.z, a[8 * c + 4], a[8 * c + 5]); unpack_bf16x2(t.w, a[8 * c + 6], a[8 * c + 7]);
+    }
+  }
+  const int64_t ms = row_ok ? m : 0;       // rows past M are clipped by the TMA store; keep rowscale in bounds
+  epi_math32(v, a, ms, nb, ep);
+  if (ep.residual) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += a[j];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 t;
+    t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    if (!(p.debug & 64)) sts128(rowp + (((half * 4 + c) ^ sw) << 4), t);
+  }
+  if (ep.colsum) {
+    if (!row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    epi_colsum32(v, row, ep.colsum + nb);
+  }
+}
+
 // Slow path (ragged last columns, unaligned leading dims): per-element, fully guarded.
 template <typename TOut>
 __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
@@ -224,29 +329,36 @@ __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t 
 
 template <int BN, bool A_MN, bool B_MN, typename TOut>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ Params p) {
+  constexpr int STAGES = StageCfg<BN>::STAGES;
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  unsigned char* epi_smem = smem + STAGES * STAGE_BYTES;                 // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * EPI_WARPS);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto r_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 4 + 2 * w + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.tma_epi) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (p.has_r) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(r_bar(w, 0), 1); mbar_init(r_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -303,6 +415,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          if (p.debug & 2) {
+            mbar_arrive(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 0, 1024);
@@ -312,7 +429,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(as));
+        if (p.debug & 2) mbar_arrive(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -332,6 +450,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         (ep.aux == nullptr || (((ep.ld_aux % 8) == 0) && al16(ep.aux))) &&
                         (ep.aux_out == nullptr || (((ep.ld_aux % VEC) == 0) && al16(ep.aux_out)));
     constexpr int CH_PER_WARP = BN / 64;
+    if (p.tma_epi) {
+      // ---- smem-staged path: this warp owns rows quad*32.. of the tile and the 64-column groups
+      //      [half*BN/2, (half+1)*BN/2); group g of the warp's sequence uses staging buffer g & 1 ----
+      constexpr int GROUPS = BN / 128;           // 64-column groups per warp per tile
+      const int ew = warp - 2;
+      unsigned char* mybuf = epi_smem + ew * 2 * EPI_BUF_BYTES;
+      const uint32_t mybuf_u32 = smem_u32(mybuf);
+      uint32_t rphase = 0;   // bit b = parity of the next completion of r_bar(ew, b)
+      uint32_t g = 0;
+      auto coords = [&](int it_, int c_, int& col, int& rowc) {
+        int rem_ = it_ % tiles;
+        rowc = (rem_ / p.n_tiles) * BM + quad * 32;
+        col = (rem_ % p.n_tiles) * BN + (half * GROUPS + c_) * 64;
+      };
+      // advance (it_, c_) to this warp's next group whose columns lie inside N; false at the end of the work list
+      auto next_valid = [&](int& it_, int& c_) -> bool {
+        while (true) {
+          if (++c_ == GROUPS) { c_ = 0; it_ += gridDim.x; }
+          if (it_ >= items) return false;
+          int col_, row_;
+          coords(it_, c_, col_, row_);
+          if (col_ < p.N) return true;
+        }
+      };
+      if (p.has_r && lane == 0) {       // residual / aux tile of the first group
+        int it0 = blockIdx.x, c0 = -1;
+        if (it0 < items && next_valid(it0, c0)) {
+          int col, rowc;
+          coords(it0, c0, col, rowc);
+          mbar_expect_tx(r_bar(ew, 0), EPI_BUF_BYTES);
+          tma_load_2d(&tmR, r_bar(ew, 0), mybuf_u32, col, rowc);
+        }
+      }
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < ((p.debug & 1) ? 0 : GROUPS); ++c) {
+          int col, rowc;
+          coords(it, c, col, rowc);
+          if (col >= p.N) continue;   // warp-uniform; N % 64 == 0 on this path
+          const int b = g & 1;
+          const uint32_t buf = mybuf_u32 + b * EPI_BUF_BYTES;
+          uint32_t r0[32], r1[32];
+          __syncwarp();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + (half * GROUPS + c) * 64;
+          if (p.debug & 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { r0[j] = 0x3f800000u; r1[j] = 0x3f800000u; }
+          } else {
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+          }
+          if (p.has_r) {
+            if (lane == 0) {
+              tma_store_wait_read<0>();          // the store of group g-1 has drained buffer b^1
+              int itn = it, cn = c;
+              if (next_valid(itn, cn)) {
+                int coln, rown;
+                coords(itn, cn, coln, rown);
+                mbar_expect_tx(r_bar(ew, b ^ 1), EPI_BUF_BYTES);
+                tma_load_2d(&tmR, r_bar(ew, b ^ 1), mybuf_u32 + (b ^ 1) * EPI_BUF_BYTES, coln, rown);
+              }
+            }
+            mbar_wait(r_bar(ew, b), (rphase >> b) & 1u);
+            rphase ^= 1u << b;
+          } else {
+            if (lane == 0) tma_store_wait_read<1>();   // the store of group g-2 has drained buffer b
+            __syncwarp();
+          }
+          const int64_t m = (int64_t)rowc + lane;
+          const bool row_ok = m < p.M;
+          if (!(p.debug & 32)) {
+            epi_half_tma(r0, buf, lane, 0, m, col, row_ok, p);
+            epi_half_tma(r1, buf, lane, 1, m, col + 32, row_ok, p);
+          }
+          if (!(p.debug & 16)) fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 8)) tma_store_2d(&tmC, mybuf_u32 + b * EPI_BUF_BYTES, col, rowc);
+          ++g;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       int rem = it % tiles;
       int64_t m0 = (int64_t)(rem / p.n_tiles) * BM, n0 = (int64_t)(rem % p.n_tiles) * BN;
@@ -355,6 +561,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
     }
   }
   tc_fence_before();
@@ -395,10 +602,13 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t ou
   return EMO_OK;
 }
 
+struct Maps { CUtensorMap a, b, c, r; };
+
 template <int BN, bool A_MN, bool B_MN, typename TOut>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t s) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+static int launch(const Maps& mp, const Params& p, cudaStream_t s) {
+  constexpr int STAGES = StageCfg<BN>::STAGES;
+  constexpr int smem = STAGES * StageCfg<BN>::STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 512;
+  static_assert(smem <= 227 * 1024, "GEMM smem exceeds the CTA limit");
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut>;
   static bool configured = false;
   if (!configured) {
@@ -407,17 +617,17 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
   }
   int items = p.m_tiles * p.n_tiles * p.splits;
   int grid = items < emo_num_sms() ? items : emo_num_sms();
-  kern<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, smem, s>>>(mp.a, mp.b, mp.c, mp.r, p);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
 
 template <int BN, typename TOut>
-static int launch_op(int op, const CUtensorMap& a, const CUtensorMap& b, const Params& p, cudaStream_t s) {
+static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
   switch (op) {
-    case EMO_GEMM_NT: return launch<BN, false, false, TOut>(a, b, p, s);
-    case EMO_GEMM_NN: return launch<BN, false, true, TOut>(a, b, p, s);
-    case EMO_GEMM_TN: return launch<BN, true, true, TOut>(a, b, p, s);
+    case EMO_GEMM_NT: return launch<BN, false, false, TOut>(mp, p, s);
+    case EMO_GEMM_NN: return launch<BN, false, true, TOut>(mp, p, s);
+    case EMO_GEMM_TN: return launch<BN, true, true, TOut>(mp, p, s);
   }
   emo_set_error("emo_gemm: bad op %d", op);
   return EMO_ERR_ARG;
@@ -426,7 +636,11 @@ static int launch_op(int op, const CUtensorMap& a, const CUtensorMap& b, const P
 }  // namespace tc
 
 static int g_force_simt = 0;
+static int g_no_tma_epi = 0;
+static int g_debug = 0;
+extern "C" void emo_gemm_debug(int mode) { g_debug = mode; }   // perf triage only; results are wrong when != 0
 extern "C" void emo_gemm_force_simt(int on) { g_force_simt = on; }
+extern "C" void emo_gemm_direct_epilogue(int on) { g_no_tma_epi = on; }   // test / A-B hook: row-per-lane global stores
 
 extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                         int64_t ldb, void* C, int64_t ldc, int in_dtype, int out_dtype, const emo_epilogue* epi,
@@ -442,6 +656,7 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = (in_dtype == EMO_BF16) && !g_force_simt && (lda % 8 == 0) && (ldb % 8 == 0) &&
                ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  if (!tc_ok && ep.colsum) { emo_set_error("emo_gemm: fused column sum is a tensor-core (bf16) epilogue feature"); return EMO_ERR_UNSUPPORTED; }
   if (!tc_ok) return emo_gemm_simt(op, M, N, K, A, lda, B, ldb, C, ldc, in_dtype, out_dtype, ep, s);
 
   using namespace tc;
@@ -462,17 +677,42 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
 
-  CUtensorMap tmA, tmB;
+  Maps mp;
   int rc;
-  if (op == EMO_GEMM_TN) rc = make_map(&tmA, A, M, K, lda, 64);   // A stored [K][M]: inner = M
-  else rc = make_map(&tmA, A, K, M, lda, BM);                      // A stored [M][K]: inner = K
+  if (op == EMO_GEMM_TN) rc = make_map(&mp.a, A, M, K, lda, 64);   // A stored [K][M]: inner = M
+  else rc = make_map(&mp.a, A, K, M, lda, BM);                      // A stored [M][K]: inner = K
   if (rc) return rc;
-  if (op == EMO_GEMM_NT) rc = make_map(&tmB, B, K, N, ldb, BN);   // B stored [N][K]
-  else rc = make_map(&tmB, B, N, K, ldb, 64);                      // B stored [K][N]: inner = N
+  if (op == EMO_GEMM_NT) rc = make_map(&mp.b, B, K, N, ldb, BN);   // B stored [N][K]
+  else rc = make_map(&mp.b, B, N, K, ldb, 64);                      // B stored [K][N]: inner = N
   if (rc) return rc;
 
-  if (out_dtype == EMO_BF16) return BN == 256 ? launch_op<256, bf16>(op, tmA, tmB, p, s) : launch_op<128, bf16>(op, tmA, tmB, p, s);
-  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float>(op, tmA, tmB, p, s) : launch_op<128, float>(op, tmA, tmB, p, s);
+  // bf16 outputs leave through the smem-staged TMA store; a residual OR an aux operand rides in by TMA load
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool need_aux = (ep.act == EMO_ACT_RELU_MASK_BWD || ep.act == EMO_ACT_GELU_NEW_BWD);
+  const void* rptr = need_aux ? ep.aux : ep.residual;
+  const int64_t rld = need_aux ? ep.ld_aux : ep.ld_res;
+  p.tma_epi = (out_dtype == EMO_BF16) && !ep.accumulate && !g_no_tma_epi && (N % 64 == 0) && (ldc % 8 == 0) && al16(C) &&
+              !(need_aux && ep.residual) && !(ep.act == EMO_ACT_GELU_NEW && ep.aux_out) &&
+              (ep.bias == nullptr || al16(ep.bias)) && (rptr == nullptr || ((rld % 8 == 0) && al16(rptr)));
+  p.has_r = p.tma_epi && rptr != nullptr;
+  p.debug = g_debug;
+  mp.c = mp.a;
+  mp.r = mp.a;
+  if (p.tma_epi) {
+    rc = make_map(&mp.c, C, N, M, ldc, 32);
+    if (rc) return rc;
+    if (p.has_r) {
+      rc = make_map(&mp.r, rptr, N, M, rld, 32);
+      if (rc) return rc;
+    }
+  }
+  if (ep.colsum && !p.tma_epi) {
+    emo_set_error("emo_gemm: the fused column sum needs the bf16 TMA-store epilogue (N %% 64 == 0, aligned C)");
+    return EMO_ERR_UNSUPPORTED;
+  }
+
+  if (out_dtype == EMO_BF16) return BN == 256 ? launch_op<256, bf16>(op, mp, p, s) : launch_op<128, bf16>(op, mp, p, s);
+  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float>(op, mp, p, s) : launch_op<128, float>(op, mp, p, s);
   emo_set_error("emo_gemm: bad out dtype %d", out_dtype);
   return EMO_ERR_ARG;
 }

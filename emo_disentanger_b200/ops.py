@@ -118,10 +118,11 @@ def ln_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
-def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0):
+def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0, dxsum=None):
+    """dxsum (fp32 [d]) += column sums of dx_drop (or dx): the bias gradient of the projection below."""
     rows = x.numel() // x.shape[-1]
     _call("emo_ln_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(add_in), _p(dx), _p(dx_drop),
-                               float(drop_p), int(seed), _p(dgamma), _p(dbeta), rows, x.shape[-1], _dt(x),
+                               float(drop_p), int(seed), _p(dgamma), _p(dbeta), _p(dxsum), rows, x.shape[-1], _dt(x),
                                _stream())
 
 
@@ -131,16 +132,22 @@ def dropout_apply(x, y, drop_p, seed):
 
 
 def gemm(op, M, N, K, A, lda, B, ldb, Cmat, ldc, bias=None, act=ACT_NONE, aux=None, aux_out=None, ld_aux=0,
-         aux_scale=1.0, drop_p=0.0, seed=0, residual=None, ld_res=0, alpha=1.0, accumulate=False):
-    """Raw GEMM call; A/B/Cmat are tensors (or (tensor, element_offset) handled by the caller via views)."""
+         aux_scale=1.0, drop_p=0.0, seed=0, residual=None, ld_res=0, alpha=1.0, accumulate=False, colsum_out=None):
+    """Raw GEMM call; A/B/Cmat are tensors (or (tensor, element_offset) handled by the caller via views).
+    colsum_out (fp32 [N]) += column sums of the stored C (bias gradient): fused into the epilogue on the
+    bf16 tensor-core path, a separate emo_colsum launch otherwise."""
     _need_cuda(A, B, Cmat)
+    fuse_cs = (colsum_out is not None and A.dtype == torch.bfloat16 and Cmat.dtype == torch.bfloat16 and N % 64 == 0
+               and ldc % 8 == 0 and Cmat.data_ptr() % 16 == 0 and not accumulate)
     e = L.Epilogue(_p(bias), act, _p(aux), _p(aux_out), ld_aux, aux_scale, drop_p, int(seed), _p(residual), ld_res,
-                   alpha, 1 if accumulate else 0, None)
+                   alpha, 1 if accumulate else 0, None, _p(colsum_out) if fuse_cs else None)
     assert A.dtype == B.dtype
     tk = TIMER.start("gemm")
     L.check(L.lib().emo_gemm(op, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, _dt(A), _dt(Cmat), C.byref(e),
                              _stream()), "emo_gemm")
     TIMER.stop(tk, 2.0 * M * N * K)
+    if colsum_out is not None and not fuse_cs:
+        colsum(Cmat, colsum_out, n=N)
     return Cmat
 
 

@@ -147,14 +147,13 @@ class MusicPerformer(Stage2Base):
             ds2 = new(R, d)
             ds2d = new(R, d) if p > 0 else None
             ops.ln_bwd(dout, s2, m2, r2, self._wv(Wf, nm + "norm2.weight"), ds2, self._gv(nm + "norm2.weight"),
-                       self._gv(nm + "norm2.bias"), dx_drop=ds2d, drop_p=p, seed=site_seed(seed, 4 * l + 3))
+                       self._gv(nm + "norm2.bias"), dx_drop=ds2d, drop_p=p, seed=site_seed(seed, 4 * l + 3),
+                       dxsum=self._gv(nm + "linear2.bias"))                  # bias gradients ride along
             g2 = ds2d if p > 0 else ds2
-            ops.colsum(g2, self._gv(nm + "linear2.bias"))
             ops.linear_wgrad(g2, hh, self._gv(nm + "linear2.weight"))
             da = new(R, f)
             ops.linear_dgrad(g2, self._wv(Wc, nm + "linear2.weight"), da, act=ops.ACT_RELU_MASK_BWD, aux=hh,
-                             ld_aux=f, aux_scale=keep_scale)
-            ops.colsum(da, self._gv(nm + "linear1.bias"))
+                             ld_aux=f, aux_scale=keep_scale, colsum_out=self._gv(nm + "linear1.bias"))
             ops.linear_wgrad(da, y1, self._gv(nm + "linear1.weight"))
             dy1 = new(R, d)
             ops.linear_dgrad(da, self._wv(Wc, nm + "linear1.weight"), dy1, residual=ds2, ld_res=d)
@@ -162,9 +161,9 @@ class MusicPerformer(Stage2Base):
             ds1 = ds2      # reuse buffers
             ds1d = ds2d
             ops.ln_bwd(dy1, s1, m1, r1, self._wv(Wf, nm + "norm1.weight"), ds1, self._gv(nm + "norm1.weight"),
-                       self._gv(nm + "norm1.bias"), dx_drop=ds1d, drop_p=p, seed=site_seed(seed, 4 * l + 1))
+                       self._gv(nm + "norm1.bias"), dx_drop=ds1d, drop_p=p, seed=site_seed(seed, 4 * l + 1),
+                       dxsum=self._gv(nm + "attention.out_projection.bias"))
             g1 = ds1d if p > 0 else ds1
-            ops.colsum(g1, self._gv(nm + "attention.out_projection.bias"))
             ops.linear_wgrad(g1, att, self._gv(nm + "attention.out_projection.weight"))
             datt = dy1     # reuse
             ops.linear_dgrad(g1, self._wv(Wc, nm + "attention.out_projection.weight"), datt)

@@ -60,10 +60,12 @@ int emo_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, fl
                float* rstd, int64_t rows, int d, float eps, int dtype, void* stream);
 /* dx = LNgrad(dy) (+ add_in if non-NULL).  If dx_drop != NULL also writes
  * dx_drop = dx * dropmask(seed)/(1-p) (gradient entering a `x + dropout(proj)` branch).
- * dgamma/dbeta (fp32 [d]) are ACCUMULATED (atomics). */
+ * dgamma/dbeta (fp32 [d]) are ACCUMULATED (atomics).  dxsum (fp32 [d], may be NULL) += column sums of
+ * dx_drop (of dx when dx_drop is NULL): the bias gradient of the projection this gradient flows into
+ * (out_projection / linear2 / c_proj), so no separate pass over the tensor is needed. */
 int emo_ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                const float* gamma, const void* add_in, void* dx, void* dx_drop, float drop_p,
-               uint64_t seed, float* dgamma, float* dbeta, int64_t rows, int d, int dtype,
+               uint64_t seed, float* dgamma, float* dbeta, float* dxsum, int64_t rows, int d, int dtype,
                void* stream);
 /* y = dropmask(seed)/(1-p) * x  (elementwise helper for branches without an LN in between) */
 int emo_dropout_apply(const void* x, void* y, int64_t n, float drop_p, uint64_t seed, int dtype,
@@ -102,6 +104,9 @@ typedef struct {
   float alpha;
   int accumulate;       /* 1: C (fp32) += result                                             */
   const void* rowscale; /* optional fp32 [M]: v *= rowscale[m] before bias (unused = NULL)    */
+  float* colsum;        /* optional fp32 [N]: colsum[n] += sum_m C[m,n] of the values stored (the
+                           bias gradient of the producing layer, fused into its dgrad GEMM);
+                           bf16 tensor-core path with N % 64 == 0 only, else EMO_ERR_UNSUPPORTED */
 } emo_epilogue;
 int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
              int64_t ldb, void* C, int64_t ldc, int in_dtype, int out_dtype,

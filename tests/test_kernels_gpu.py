@@ -117,6 +117,45 @@ def test_gemm_dropout_epilogue_is_consistent_with_standalone_mask(ops):
     assert not torch.equal(ref == 0, dropped == 0)
 
 
+@pytest.mark.parametrize("M,N,K", [(32768 // 8 + 37, 512, 512), (1000, 1536, 512), (129, 2048, 512), (3, 320, 2048)])
+def test_gemm_tma_store_epilogue_equals_direct_epilogue(ops, M, N, K):
+    """bf16 outputs leave through the smem-staged TMA store (residual / aux tiles by TMA load): bit-identical to
+    the direct row-per-lane epilogue on ragged M, strided residual, dropout, relu-mask; fused column sums."""
+    from emo_disentanger_b200 import _lib
+    torch.manual_seed(M + N)
+    a, w = _bf(torch.randn(M, K, device=DEV)), _bf(torch.randn(N, K, device=DEV) * 0.05)
+    bias = torch.randn(N, device=DEV) * 0.1
+    resbuf = _bf(torch.randn(M, 2 * N, device=DEV))
+    res = resbuf[:, N:]                                   # strided residual view (ld = 2N)
+    h = _bf(torch.relu(torch.randn(M, N, device=DEV)))
+    cases = [dict(bias=bias), dict(bias=bias, act=ops.ACT_RELU, drop_p=0.1, seed=11),
+             dict(bias=bias, drop_p=0.1, seed=5, residual=res, ld_res=2 * N),
+             dict(act=ops.ACT_RELU_MASK_BWD, aux=h, ld_aux=N, aux_scale=1.0 / 0.9), dict(residual=res, ld_res=2 * N)]
+    for kw in cases:
+        o_tma = torch.full((M + 1, N), 7.0, device=DEV, dtype=torch.bfloat16)     # row M = canary (TMA clips rows >= M)
+        o_dir = torch.full((M + 1, N), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.linear_fwd(a, w, o_tma[:M], **kw)
+        _lib.lib().emo_gemm_direct_epilogue(1)
+        try:
+            ops.linear_fwd(a, w, o_dir[:M], **kw)
+        finally:
+            _lib.lib().emo_gemm_direct_epilogue(0)
+        assert torch.equal(o_tma, o_dir), sorted(kw)
+        assert float(o_tma[M].float().min()) == 7.0
+    # fused bias-gradient column sums (accumulating) == column sums of what was stored
+    cs = torch.ones(N, device=DEV)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear_fwd(a, w, out, act=ops.ACT_RELU_MASK_BWD, aux=h, ld_aux=N, aux_scale=1.25, colsum_out=cs)
+    ref = (a.float() @ w.float().T) * (h.float() != 0) * 1.25
+    assert rms_rel(out.float(), ref) < 6e-3
+    assert rel_err(cs, 1.0 + ref.sum(0)) < 2e-3
+    # same API on the fp32 path falls back to a separate column-sum launch
+    cs32 = torch.zeros(N, device=DEV)
+    o32 = torch.empty(M, N, device=DEV)
+    ops.linear_fwd(a.float(), w.float(), o32, colsum_out=cs32)
+    assert rel_err(cs32, o32.sum(0)) < 1e-4
+
+
 @pytest.mark.parametrize("op", ["nt", "nn", "tn"])
 def test_gemm_fp32_simt(ops, op):
     torch.manual_seed(5)
@@ -190,6 +229,24 @@ def test_layernorm_fwd_bwd(ops, dtype):
     # same mask (zero pattern) everywhere; values equal up to the extra bf16 rounding of the two-pass reference
     assert torch.equal(dxd == 0, ref == 0)
     assert rel_err(dxd.float(), ref.float()) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # fused bias gradient of the projection below: accumulating column sums of dx_drop (of dx without dropout)
+    cs = torch.full((512,), 2.0, device=DEV)
+    ops.ln_bwd(dy, x, mean, rstd, gamma, dx, dg, db, dx_drop=dxd, drop_p=0.1, seed=99, dxsum=cs)
+    assert rel_err(cs, 2.0 + dxd.float().sum(0)) < 1e-4
+    cs.zero_()
+    ops.ln_bwd(dy, x, mean, rstd, gamma, dx, dg, db, dxsum=cs)
+    assert rel_err(cs, dx.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,ld", [(5000, 512, 512), (777, 329, 336), (64, 1536, 4608), (100, 331, 331)])
+def test_colsum(ops, dtype, M, N, ld):
+    torch.manual_seed(M)
+    buf = torch.randn(M, ld, device=DEV).to(dtype)
+    out = torch.full((N + 3,), 1.5, device=DEV)
+    ops.colsum(buf[:, :N], out, n=N)
+    assert rel_err(out[:N], 1.5 + buf[:, :N].float().sum(0)) < 1e-4
+    assert float(out[N:].min()) == 1.5 and float(out[N:].max()) == 1.5       # nothing written past N
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
