@@ -141,6 +141,22 @@ template <int M, int N> struct BlockGemm<M, N, bf16> {
           f(row, col, acc[mt][nt][i]);
         }
   }
+  // pairs of adjacent columns (col even): lets callers emit one packed bf16x2 shared-memory store per pair
+  template <typename F> __device__ __forceinline__ void foreach2(F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m_base = (warp / WN) * (MT * 16);
+    const int n_base = (warp % WN) * (NT * 8);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+          int row = m_base + mt * 16 + (lane >> 2) + (i ? 8 : 0);
+          int col = n_base + nt * 8 + (lane & 3) * 2;
+          f(row, col, acc[mt][nt][i], acc[mt][nt][i + 1]);
+        }
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -184,3 +200,7 @@ template <int M, int N> struct BlockGemm<M, N, float> {
       for (int j = 0; j < NT; ++j) f(ty + 16 * i, tx + 16 * j, acc[i][j]);
   }
 };
+
+// store two adjacent elements (col even) of a shared-memory tile
+__device__ __forceinline__ void st_pair(bf16* p, float x0, float x1) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(x0, x1); }
+__device__ __forceinline__ void st_pair(float* p, float x0, float x1) { p[0] = x0; p[1] = x1; }

@@ -216,30 +216,48 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      int64_t rows, float eps) {
+  // persistent warps: gamma / beta stay in registers, each warp streams rows with the NEXT row's loads
+  // already in flight while the current one is reduced (memory-bound: 2 x 1 KiB per row at bf16)
   using R = RowRegs<T>;
-  int lane = threadIdx.x & 31;
+  constexpr int E = R::NV * R::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  R r;
+  float g_[E], b_[E];
+#pragma unroll
+  for (int j = 0; j < R::NV; ++j)
+#pragma unroll
+    for (int i = 0; i < R::N; i += 4) {
+      float4 g4 = *reinterpret_cast<const float4*>(gamma + R::col(j, lane) + i);
+      float4 b4 = *reinterpret_cast<const float4*>(beta + R::col(j, lane) + i);
+      g_[j * R::N + i] = g4.x; g_[j * R::N + i + 1] = g4.y; g_[j * R::N + i + 2] = g4.z; g_[j * R::N + i + 3] = g4.w;
+      b_[j * R::N + i] = b4.x; b_[j * R::N + i + 1] = b4.y; b_[j * R::N + i + 2] = b4.z; b_[j * R::N + i + 3] = b4.w;
+    }
+  R r, nxt;
   r.load(x + row * LN_D, lane);
-  float s = 0.f;
+  for (; row < rows; row += wstride) {
+    const bool more = row + wstride < rows;
+    if (more) nxt.load(x + (row + wstride) * LN_D, lane);
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < R::NV * R::N; ++i) s += r.v[i];
-  float mu = warp_sum(s) * (1.f / LN_D);
-  float q = 0.f;
+    for (int i = 0; i < E; ++i) s += r.v[i];
+    float mu = warp_sum(s) * (1.f / LN_D);
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < R::NV * R::N; ++i) { float dlt = r.v[i] - mu; q += dlt * dlt; }
-  float rs = rsqrtf(warp_sum(q) * (1.f / LN_D) + eps);
+    for (int i = 0; i < E; ++i) { float dlt = r.v[i] - mu; q += dlt * dlt; }
+    float rs = rsqrtf(warp_sum(q) * (1.f / LN_D) + eps);
 #pragma unroll
-  for (int j = 0; j < R::NV; ++j) {
-    int c = R::col(j, lane);
+    for (int i = 0; i < E; ++i) r.v[i] = (r.v[i] - mu) * rs * g_[i] + b_[i];
+    r.store(y + row * LN_D, lane);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+    if (more) {
 #pragma unroll
-    for (int i = 0; i < R::N; ++i) r.v[j * R::N + i] = (r.v[j * R::N + i] - mu) * rs * gamma[c + i] + beta[c + i];
-  }
-  r.store(y + row * LN_D, lane);
-  if (lane == 0) {
-    if (mean) mean[row] = mu;
-    if (rstd) rstd[row] = rs;
+      for (int i = 0; i < E; ++i) r.v[i] = nxt.v[i];
+    }
   }
 }
 
@@ -247,7 +265,8 @@ extern "C" int emo_ln_fwd(const void* x, const float* gamma, const float* beta, 
                           float* rstd, int64_t rows, int d, float eps, int dtype, void* stream) {
   EMO_REQUIRE(d == LN_D, "emo_ln_fwd: d must be 512 (got %d)", d);
   if (rows == 0) return EMO_OK;
-  int blocks = (int)((rows + 7) / 8);
+  int64_t want = (rows + 7) / 8;
+  int blocks = (int)(want < (int64_t)emo_num_sms() * 8 ? want : (int64_t)emo_num_sms() * 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == EMO_BF16)
     ln_fwd_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps);

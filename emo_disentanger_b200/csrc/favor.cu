@@ -13,6 +13,7 @@
 // chunk by chunk (S'_{c-1} = S'_c - Phi_k^T V'), and carries the reverse state R' = sum Phi_q^T G.
 // All small products run through BlockGemm (tensor-core mma for bf16, fp32 FMA for the parity mode).
 #include "block_gemm.cuh"
+#include <stdlib.h>
 
 constexpr int FE = 64;    // head dim
 constexpr int FM = 128;   // feature dim (n_dims)
@@ -25,9 +26,35 @@ template <typename T> struct FavorCfg;
 template <> struct FavorCfg<bf16> { static constexpr int C = 64; };
 template <> struct FavorCfg<float> { static constexpr int C = 16; };   // parity mode: smaller chunks keep the fp32 tiles within 227 KB
 
-template <typename T> __device__ __forceinline__ float f_exp(float x);
-template <> __device__ __forceinline__ float f_exp<bf16>(float x) { return __expf(x); }
-template <> __device__ __forceinline__ float f_exp<float>(float x) { return expf(x); }
+// exp of the feature map.  bf16 mode works in base 2: Omega and the row offsets are pre-multiplied by log2(e)
+// when they are staged, so phi = ex2.approx(u' - o') is ONE MUFU instruction per feature (the exp was a quarter
+// of the forward's instructions); in the backward du . Omega'^T carries the same factor and is multiplied by kInv = ln 2.
+// fp32 (parity) mode keeps expf on unscaled operands.
+template <typename T> struct FavorMath;
+template <> struct FavorMath<bf16> {
+  static constexpr float kScale = 1.4426950408889634f;
+  static constexpr float kInv = 0.6931471805599453f;     // 1 / kScale
+  static __device__ __forceinline__ float ex(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+};
+template <> struct FavorMath<float> {
+  static constexpr float kScale = 1.f;
+  static constexpr float kInv = 1.f;
+  static __device__ __forceinline__ float ex(float x) { return expf(x); }
+};
+
+// registers -> shared tile: one packed bf16x2 store per adjacent column pair (bf16), scalar stores (fp32)
+template <int M, int N, typename T, typename F>
+__device__ __forceinline__ void acc_to_smem(BlockGemm<M, N, T>& g, T* dst, int ld, F f) {
+  if constexpr (sizeof(T) == 2) {
+    g.foreach2([&](int r, int c, float& a, float& b) { st_pair(dst + r * ld + c, f(r, c, a), f(r, c + 1, b)); });
+  } else {
+    g.foreach ([&](int r, int c, float& a) { dst[r * ld + c] = f(r, c, a); });
+  }
+}
 
 template <typename T, int C> struct FavorSmemFwd {
   T xq[C][bg_ld<T>(FE)];
@@ -165,8 +192,17 @@ __device__ __forceinline__ void store_rows(T* __restrict__ dst, int64_t ld, int 
 
 template <typename T, int LD>
 __device__ __forceinline__ void load_omega(const float* __restrict__ omega, T (*om)[LD]) {
-  const float s = 0.35355339059327373f;   // 64^(-1/4) folded into omega
-  for (int i = threadIdx.x; i < FE * FE; i += BG_THREADS) om[i / FE][i % FE] = from_f<T>(omega[i] * s);
+  const float s = 0.35355339059327373f * FavorMath<T>::kScale;   // 64^(-1/4) (and log2 e in bf16 mode) folded into omega
+  static_assert(FE * FE == 4 * 4 * BG_THREADS, "omega tile: 4 float4 per thread");
+  float4 v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(omega) + threadIdx.x + u * BG_THREADS);   // all in flight
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int i = (threadIdx.x + u * BG_THREADS) * 4;
+    T* d = &om[i / FE][i % FE];
+    d[0] = from_f<T>(v[u].x * s); d[1] = from_f<T>(v[u].y * s); d[2] = from_f<T>(v[u].z * s); d[3] = from_f<T>(v[u].w * s);
+  }
 }
 
 // U = X . Om_s -> phi rows in smem (rows >= valid zeroed)
@@ -175,12 +211,8 @@ __device__ __forceinline__ void phi_rows(T (*x)[LDX], T (*om)[LDO], const float*
   BlockGemm<C, FE, T> g;
   g.clear();
   g.template mma<true, false>(&x[0][0], LDX, &om[0][0], LDO, FE);
-  g.foreach ([&](int row, int col, float& u) {
-    float o = off[row];
-    bool ok = row < valid;
-    phi[row][col] = from_f<T>(ok ? f_exp<T>(u - o) : 0.f);
-    phi[row][FE + col] = from_f<T>(ok ? f_exp<T>(-u - o) : 0.f);
-  });
+  acc_to_smem(g, &phi[0][0], LDP, [&](int row, int col, float u) { return row < valid ? FavorMath<T>::ex(u - off[row]) : 0.f; });
+  acc_to_smem(g, &phi[0][FE], LDP, [&](int row, int col, float u) { return row < valid ? FavorMath<T>::ex(-u - off[row]) : 0.f; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,8 +240,8 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     const float* si = state_in + (int64_t)bh * FM * FV;
     gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
   }
-  for (int sp = 0; sp < seg; ++sp) {   // exclusive prefix over the earlier segments' local sums (favor_segsum_kernel)
-    const float* si = seg_states + ((int64_t)bh * nseg + sp) * FM * FV;
+  if (seg_states) {          // exclusive prefix over the earlier segments (favor_segsum_kernel + favor_prefix_kernel)
+    const float* si = seg_states + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
     gs.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
   }
   for (int i = threadIdx.x; i < FM * bg_ld<T>(FV); i += BG_THREADS) (&sm.s[0][0])[i] = from_f<T>(0.f);
@@ -237,8 +269,8 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     const int validn = (Tlen - tn < C) ? (Tlen - tn) : C;
     cp_wait<1>();            // (q,k) of this chunk have landed (v may still be in flight)
     __syncthreads();
-    row_offsets<T, C>(sm.xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
-    row_offsets<T, C>(sm.xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(sm.xq, sm.oq, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
+    row_offsets<T, C>(sm.xk, sm.ok, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
     __syncthreads();
     phi_rows<T, C>(sm.xq, sm.om, sm.oq, valid, sm.pq);
     phi_rows<T, C>(sm.xk, sm.om, sm.ok, valid, sm.pk);
@@ -250,7 +282,7 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       BlockGemm<C, C, T> ga;
       ga.clear();
       ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
-      ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
+      acc_to_smem(ga, &sm.a[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
     }
     cp_wait<1>();            // v of this chunk has landed
     __syncthreads();
@@ -259,9 +291,13 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       go.clear();
       go.template mma<true, false>(&sm.a[0][0], bg_ld<T>(C), &sm.v[0][0], bg_ld<T>(FV), C);
       go.template mma<true, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.s[0][0], bg_ld<T>(FV), FM);
-      go.foreach ([&](int row, int col, float& x) { if (col == FE) sm.den[row] = x + F_EPS; });
-      __syncthreads();
-      go.foreach ([&](int row, int col, float& x) { if (col < FE) stage[row][col] = from_f<T>(x / sm.den[row]); });
+      go.foreach ([&](int row, int col, float& x) { if (col == FE) { sm.den[row] = x + F_EPS; sm.oq[row] = 1.f / (x + F_EPS); } });
+      __syncthreads();     // oq (the phi(q) offsets) is dead here: it carries 1/den to the output scaling
+      if constexpr (sizeof(T) == 2) {
+        go.foreach2([&](int row, int col, float& x0, float& x1) { if (col < FE) { float inv = sm.oq[row]; st_pair(&stage[row][col], x0 * inv, x1 * inv); } });
+      } else {
+        go.foreach ([&](int row, int col, float& x) { if (col < FE) stage[row][col] = x * sm.oq[row]; });
+      }
     }
     __syncthreads();
     store_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, stage);
@@ -269,7 +305,7 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       for (int i = threadIdx.x; i < valid; i += BG_THREADS) den_out[((int64_t)b * Tlen + t0 + i) * H + h] = sm.den[i];
     gs.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
     __syncthreads();         // every warp is done reading v and s
-    gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
+    acc_to_smem(gs, &sm.s[0][0], bg_ld<T>(FV), [](int, int, float x) { return x; });
     issue_rows<T, C>(v + base + (int64_t)tn * ld, ld, validn, sm.v, more);      // prefetch the next chunk's v
     cp_commit();
   }
@@ -316,15 +352,38 @@ favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld
     cp_commit();
     cp_wait<1>();
     __syncthreads();
-    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
     __syncthreads();
     phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
     __syncthreads();
     gs.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[buf][0][0], bg_ld<T>(FV), C);
   }
   cp_wait<0>();
-  float* so = seg_states + (int64_t)blockIdx.x * FM * FV;
+  float* so = seg_states + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
   gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+}
+
+// In-place scan over the nseg (+1) slots of every (b,h): forward -> slot s = sum of the local sums of segments < s
+// (slot nseg = total); reverse -> slot s = sum of the local sums of segments > s.  One thread per state element.
+__global__ void favor_prefix_kernel(float* __restrict__ states, int nseg, int reverse, int64_t n_bh) {
+  const int64_t per = (int64_t)FM * FV;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bh * per) return;
+  float* p = states + (i / per) * (nseg + 1) * per + (i % per);
+  float run = 0.f;
+  if (!reverse) {
+    for (int s = 0; s <= nseg; ++s) {
+      float t = (s < nseg) ? p[s * per] : 0.f;
+      p[s * per] = run;
+      run += t;
+    }
+  } else {
+    for (int s = nseg - 1; s >= 0; --s) {
+      float t = p[s * per];
+      p[s * per] = run;
+      run += t;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -414,7 +473,7 @@ favor_bwd_segsum_kernel(const T* __restrict__ q, int64_t ld, const float* __rest
     issue(t0 + C, buf ^ 1);
     cp_wait<1>();
     __syncthreads();
-    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(sm.x[buf], sm.off, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
     make_g<T, C>(sm.raw[buf][0], sm.raw[buf][1], sm.den[buf], valid, sm.w[0]);
     __syncthreads();
     phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
@@ -422,7 +481,7 @@ favor_bwd_segsum_kernel(const T* __restrict__ q, int64_t ld, const float* __rest
     gr.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[0][0][0], bg_ld<T>(FV), C);
   }
   cp_wait<0>();
-  float* so = seg_rstates + (int64_t)blockIdx.x * FM * FV;
+  float* so = seg_rstates + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
   gr.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
 }
 
@@ -431,7 +490,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1)
 favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
                  const float* __restrict__ omega, const T* __restrict__ out, const T* __restrict__ dout,
                  int64_t ld_out, const float* __restrict__ den_in, const float* __restrict__ seg_states,
-                 const float* __restrict__ seg_rstates, int nseg, int seg_chunks,
+                 const float* __restrict__ seg_rstates, int nseg, int seg_chunks, int fwd_nseg, int ratio,
                  T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t ld_d, int Tlen, int H) {
   constexpr int C = FavorCfg<T>::C;
   using S = FavorSmemBwd<T, C>;
@@ -474,13 +533,15 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   BlockGemm<FM, FV, T> gs, gr;   // forward prefix state (rolled back) and reverse state
   gs.clear();
   gr.clear();
-  for (int sp = 0; sp <= seg; ++sp) {          // prefix state at the END of this segment
-    const float* si = seg_states + ((int64_t)bh * nseg + sp) * FM * FV;
-    gs.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
+  {   // prefix state at the END of this segment = the forward's exclusive prefix at that boundary (last slot = total)
+    int slot = (seg + 1) * ratio;
+    if (slot > fwd_nseg) slot = fwd_nseg;
+    const float* si = seg_states + ((int64_t)bh * (fwd_nseg + 1) + slot) * FM * FV;
+    gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
   }
-  for (int sp = seg + 1; sp < nseg; ++sp) {    // reverse state carried in from the later segments
-    const float* si = seg_rstates + ((int64_t)bh * nseg + sp) * FM * FV;
-    gr.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
+  if (nseg > 1) {   // reverse state carried in from the later segments (suffix-exclusive, favor_prefix_kernel)
+    const float* si = seg_rstates + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
+    gr.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
   }
   __syncthreads();
   gr.foreach ([&](int row, int col, float& x) { sm.r[row][col] = from_f<T>(x); });
@@ -494,8 +555,8 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     T (*vv)[bg_ld<T>(FV)] = sm.v[buf];
     cp_wait<0>();            // this chunk's q, k, v, out, dout, den have landed
     __syncthreads();
-    row_offsets<T, C>(xq, sm.oq, 0.5f * F_S2, F_HALF_LOG_M);
-    row_offsets<T, C>(xk, sm.ok, 0.5f * F_S2, F_HALF_LOG_M);
+    row_offsets<T, C>(xq, sm.oq, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
+    row_offsets<T, C>(xk, sm.ok, 0.5f * F_S2 * FavorMath<T>::kScale, F_HALF_LOG_M * FavorMath<T>::kScale);
     make_g<T, C>(sm.raw[0], sm.raw[1], sm.den, valid, sm.g);
     __syncthreads();
     issue_qkv(c - 1, buf ^ 1);     // prefetch the previous chunk (reverse order) while this one is computed
@@ -513,16 +574,16 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       const float* t = reinterpret_cast<const float*>(tmp.acc);
 #pragma unroll
       for (int i = 0; i < NA; ++i) a[i] -= t[i];
-      gs.foreach ([&](int row, int col, float& x) { sm.s[row][col] = from_f<T>(x); });
+      acc_to_smem(gs, &sm.s[0][0], bg_ld<T>(FV), [](int, int, float x) { return x; });
     }
     {
       BlockGemm<C, C, T> ga;
       ga.clear();
       ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
-      ga.foreach ([&](int row, int col, float& x) { sm.a[row][col] = from_f<T>(col <= row ? x : 0.f); });
+      acc_to_smem(ga, &sm.a[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
       ga.clear();
       ga.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &vv[0][0], bg_ld<T>(FV), FV);
-      ga.foreach ([&](int row, int col, float& x) { sm.p[row][col] = from_f<T>(col <= row ? x : 0.f); });
+      acc_to_smem(ga, &sm.p[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
     }
     __syncthreads();
     // ---- dq ----
@@ -531,7 +592,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       gd.clear();
       gd.template mma<true, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pk[0][0], bg_ld<T>(FM), C);
       gd.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &sm.s[0][0], bg_ld<T>(FV), FV);
-      gd.foreach ([&](int row, int col, float& x) { sm.w[row][col] = from_f<T>(x * to_f(sm.pq[row][col])); });
+      acc_to_smem(gd, &sm.w[0][0], bg_ld<T>(FM), [&](int row, int col, float x) { return x * to_f(sm.pq[row][col]); });
     }
     __syncthreads();
     phi_bwd_reduce<T, C>(sm);
@@ -541,8 +602,8 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       gx.clear();
       gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
       __syncthreads();       // du is re-used as the store staging buffer
-      gx.foreach ([&](int row, int col, float& x) {
-        sm.du[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(xq[row][col]));
+      acc_to_smem(gx, &sm.du[0][0], bg_ld<T>(FE), [&](int row, int col, float x) {
+        return x * FavorMath<T>::kInv + sm.dof[row] * F_S2 * to_f(xq[row][col]);
       });
     }
     __syncthreads();
@@ -553,7 +614,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       gd.clear();
       gd.template mma<false, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pq[0][0], bg_ld<T>(FM), C);
       gd.template mma<true, true>(&vv[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV), FV);
-      gd.foreach ([&](int row, int col, float& x) { sm.w[row][col] = from_f<T>(x * to_f(sm.pk[row][col])); });
+      acc_to_smem(gd, &sm.w[0][0], bg_ld<T>(FM), [&](int row, int col, float x) { return x * to_f(sm.pk[row][col]); });
     }
     __syncthreads();         // also: the dq store has finished reading du
     phi_bwd_reduce<T, C>(sm);
@@ -563,8 +624,8 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       gx.clear();
       gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
       __syncthreads();
-      gx.foreach ([&](int row, int col, float& x) {
-        sm.du[row][col] = from_f<T>(x + sm.dof[row] * F_S2 * to_f(xk[row][col]));
+      acc_to_smem(gx, &sm.du[0][0], bg_ld<T>(FE), [&](int row, int col, float x) {
+        return x * FavorMath<T>::kInv + sm.dof[row] * F_S2 * to_f(xk[row][col]);
       });
     }
     __syncthreads();
@@ -583,7 +644,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     // ---- reverse state ----
     gr.template mma<false, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.g[0][0], bg_ld<T>(FV), C);
     __syncthreads();         // every warp is done with r (dk, dv) and with du (dv store)
-    gr.foreach ([&](int row, int col, float& x) { sm.r[row][col] = from_f<T>(x); });
+    acc_to_smem(gr, &sm.r[0][0], bg_ld<T>(FV), [](int, int, float x) { return x; });
   }
   cp_wait<0>();
 }
@@ -645,27 +706,48 @@ __global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-// Segment plan: T is cut into `nseg` segments of `seg_chunks` chunks so that B*H*nseg CTAs fill the chip a few
-// times over (the sequential chunk loop is latency bound); the segments are stitched together by the
-// segment-local state sums written by the *_segsum kernels.
-template <typename T> static void favor_plan(int B, int T_, int H, int* nseg, int* seg_chunks) {
+// Segment plan.  T is cut into segments of `sc` chunks; B*H*nseg CTAs run in parallel and are stitched together by
+// the per-segment state sums (*_segsum kernels) turned into prefixes (favor_prefix_kernel).  Measured on B200
+// (profiles/): every extra segment costs a fixed CTA prologue plus its share of the segsum pre-pass, so the best
+// plan is the COARSEST one that still gives every SM a CTA: the backward (1 CTA / SM, 213 KB smem) gets
+// nseg_b ~ SMs / (B*H) segments, the forward (2 CTAs / SM) twice as many while that still adds parallelism.
+// Backward segment boundaries are a subset of the forward's (sc_b = ratio * sc_f), so the forward's prefix slots
+// serve both.
+struct FavorPlan { int nseg_f, sc_f, nseg_b, sc_b, ratio; };
+template <typename T> static FavorPlan favor_plan(int B, int T_, int H) {
   constexpr int C = FavorCfg<T>::C;
-  int nchunk = (T_ + C - 1) / C;
-  int want = (4 * emo_num_sms() + B * H - 1) / (B * H);
-  int maxseg = nchunk / 2 > 0 ? nchunk / 2 : 1;
-  int n = want < maxseg ? want : maxseg;
-  if (n < 1) n = 1;
-  int sc = (nchunk + n - 1) / n;
-  *seg_chunks = sc;
-  *nseg = (nchunk + sc - 1) / sc;
+  const int nchunk = (T_ + C - 1) / C;
+  const int sms = emo_num_sms();
+  const int64_t bh = (int64_t)B * H;
+  int nb = (int)((sms + bh / 2) / bh);
+  if (nb < 1) nb = 1;
+  if (nb > nchunk) nb = nchunk;
+  int sc_b = (nchunk + nb - 1) / nb;
+  static int forced_f = -1, forced_b = -1;      // EMO_FAVOR_SEG_CHUNKS[_B]=<n>: tuning overrides
+  if (forced_f < 0) { const char* e = getenv("EMO_FAVOR_SEG_CHUNKS"); forced_f = e ? atoi(e) : 0; }
+  if (forced_b < 0) { const char* e = getenv("EMO_FAVOR_SEG_CHUNKS_B"); forced_b = e ? atoi(e) : 0; }
+  FavorPlan p;
+  const bool two = (bh * nb < 2 * (int64_t)sms) && sc_b >= 2;
+  if (two && (sc_b & 1)) ++sc_b;
+  p.sc_b = sc_b;
+  p.sc_f = two ? sc_b / 2 : sc_b;
+  if (forced_f > 0) {
+    p.sc_f = forced_f < nchunk ? forced_f : nchunk;
+    p.sc_b = p.sc_f;
+    if (forced_b > 0 && forced_b % p.sc_f == 0) p.sc_b = forced_b;
+  }
+  p.ratio = p.sc_b / p.sc_f;
+  p.nseg_f = (nchunk + p.sc_f - 1) / p.sc_f;
+  p.nseg_b = (nchunk + p.sc_b - 1) / p.sc_b;
+  return p;
 }
 
+// number of [128,80] fp32 slots per (b,h) of the seg_states / seg_rstates workspaces: the forward's segment
+// prefixes + the total
 extern "C" int emo_favor_nseg(int B, int T, int H, int dtype) {
-  int nseg = 1, sc = 1;
-  if (B * H <= 0 || T <= 0) return 1;
-  if (dtype == EMO_BF16) favor_plan<bf16>(B, T, H, &nseg, &sc);
-  else favor_plan<float>(B, T, H, &nseg, &sc);
-  return nseg;
+  if (B * H <= 0 || T <= 0) return 2;
+  FavorPlan p = dtype == EMO_BF16 ? favor_plan<bf16>(B, T, H) : favor_plan<float>(B, T, H);
+  return p.nseg_f + 1;
 }
 
 template <typename T>
@@ -675,7 +757,7 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
   constexpr int C = FavorCfg<T>::C;
   size_t smem = sizeof(FavorSmemFwd<T, C>);
   int nseg = 1, sc = (T_ + C - 1) / C;
-  if (seg_states) favor_plan<T>(B, T_, H, &nseg, &sc);
+  if (seg_states) { FavorPlan pl = favor_plan<T>(B, T_, H); nseg = pl.nseg_f; sc = pl.sc_f; }
   static bool configured = false;
   if (!configured) {
     EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -684,6 +766,9 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
   }
   if (seg_states) {
     favor_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)k, (const T*)v, ld, omega, seg_states, nseg, sc, T_, H);
+    EMO_LAUNCH_CHECK();
+    const int64_t n = (int64_t)B * H * FM * FV;
+    favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_states, nseg, 0, (int64_t)B * H);
     EMO_LAUNCH_CHECK();
   }
   favor_fwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
@@ -698,8 +783,8 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
                             int B, int T_, int H, cudaStream_t s) {
   constexpr int C = FavorCfg<T>::C;
   size_t smem = sizeof(FavorSmemBwd<T, C>);
-  int nseg = 1, sc = 1;
-  favor_plan<T>(B, T_, H, &nseg, &sc);
+  const FavorPlan pl = favor_plan<T>(B, T_, H);
+  const int nseg = pl.nseg_b, sc = pl.sc_b;
   static bool configured = false;
   if (!configured) {
     EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -710,10 +795,13 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
     favor_bwd_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)q, ld, omega, (const T*)out, (const T*)dout,
                                                                       ld_out, den, seg_rstates, nseg, sc, T_, H);
     EMO_LAUNCH_CHECK();
+    const int64_t n = (int64_t)B * H * FM * FV;
+    favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_rstates, nseg, 1, (int64_t)B * H);
+    EMO_LAUNCH_CHECK();
   }
   favor_bwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (const T*)out,
                                                              (const T*)dout, ld_out, den, seg_states, seg_rstates, nseg, sc,
-                                                             (T*)dq, (T*)dk, (T*)dv, ld_d, T_, H);
+                                                             pl.nseg_f, pl.ratio, (T*)dq, (T*)dk, (T*)dv, ld_d, T_, H);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
@@ -724,7 +812,7 @@ extern "C" int emo_favor_fwd(const void* q, const void* k, const void* v, int64_
                              void* out, int64_t ld_out, float* den, const float* state_in, float* state_out,
                              float* seg_states, int B, int T, int H, int dtype, void* stream) {
   int esz = dtype == EMO_BF16 ? 2 : 4;
-  EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "emo_favor_fwd: pointers must be 16-byte aligned");
+  EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out) && aligned16(omega), "emo_favor_fwd: pointers must be 16-byte aligned");
   EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0, "emo_favor_fwd: row strides must be 16-byte multiples");
   if (B * H == 0 || T == 0) return EMO_OK;
   if (dtype == EMO_BF16) return favor_fwd_launch<bf16>(q, k, v, ld_qkv, omega, out, ld_out, den, state_in, state_out, seg_states, B, T, H, (cudaStream_t)stream);
@@ -737,7 +825,7 @@ extern "C" int emo_favor_bwd(const void* q, const void* k, const void* v, int64_
                              int64_t ld_dqkv, int B, int T, int H, int dtype, void* stream) {
   int esz = dtype == EMO_BF16 ? 2 : 4;
   EMO_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out) && aligned16(dout) && aligned16(dq) &&
-                  aligned16(dk) && aligned16(dv), "emo_favor_bwd: pointers must be 16-byte aligned");
+                  aligned16(dk) && aligned16(dv) && aligned16(omega), "emo_favor_bwd: pointers must be 16-byte aligned");
   EMO_REQUIRE((ld_qkv * esz) % 16 == 0 && (ld_out * esz) % 16 == 0 && (ld_dqkv * esz) % 16 == 0,
               "emo_favor_bwd: row strides must be 16-byte multiples");
   EMO_REQUIRE(den != nullptr && seg_states != nullptr && seg_rstates != nullptr, "emo_favor_bwd: den, seg_states and seg_rstates are required");

@@ -108,3 +108,82 @@ int emo_gemm_simt(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_
   emo_set_error("emo_gemm: unsupported dtype combination in=%d out=%d", in_dtype, out_dtype);
   return EMO_ERR_UNSUPPORTED;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Skinny NT GEMM for the decode step (M <= 8 rows = sequences in flight): C[M,N] = A[M,K] . B[N,K]^T.
+// Weight-streaming bound (every weight byte is read once per token: 2*N*K bytes), so the kernel is a
+// GEMV: one warp per output column n streams the K-contiguous weight row with 16-byte loads (all of a
+// lane's chunks in flight at once), the M activation rows sit in shared memory, fp32 accumulate,
+// butterfly reduce, full epilogue on lane 0..M-1.  N/4 CTAs of 4 warps spread the rows over all SMs.
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_MAXM = 8;
+constexpr int SK_WARPS = 4;
+
+template <typename TOut>
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, int64_t N, int K, const bf16* __restrict__ A,
+                                                                       int64_t lda, const bf16* __restrict__ B, int64_t ldb,
+                                                                       TOut* __restrict__ C, int64_t ldc, EpiParams ep) {
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  bf16* As = reinterpret_cast<bf16*>(sk_smem);           // [M][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kv = K >> 3;                                  // 16-byte vectors per row
+  for (int i = threadIdx.x; i < M * kv; i += SK_WARPS * 32) {
+    int m = i / kv, c = i % kv;
+    reinterpret_cast<uint4*>(As)[i] = *reinterpret_cast<const uint4*>(A + (int64_t)m * lda + c * 8);
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)blockIdx.x * SK_WARPS + warp;
+  if (n >= N) return;
+  const bf16* brow = B + n * ldb;
+  float acc[SK_MAXM];
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+  for (int c0 = lane; c0 < kv; c0 += 32 * 4) {            // 4 weight vectors in flight per lane per trip
+    uint4 bw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int c = c0 + 32 * u;
+      bw[u] = (c < kv) ? __ldg(reinterpret_cast<const uint4*>(brow) + c) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int c = c0 + 32 * u;
+      if (c >= kv) break;
+      float b[8];
+      unpack_bf16x2(bw[u].x, b[0], b[1]); unpack_bf16x2(bw[u].y, b[2], b[3]);
+      unpack_bf16x2(bw[u].z, b[4], b[5]); unpack_bf16x2(bw[u].w, b[6], b[7]);
+#pragma unroll
+      for (int m = 0; m < SK_MAXM; ++m) {
+        if (m < M) {
+          uint4 aw = reinterpret_cast<const uint4*>(As)[m * kv + c];
+          float a[8];
+          unpack_bf16x2(aw.x, a[0], a[1]); unpack_bf16x2(aw.y, a[2], a[3]);
+          unpack_bf16x2(aw.z, a[4], a[5]); unpack_bf16x2(aw.w, a[6], a[7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[m] = fmaf(a[j], b[j], acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+    if (m < M) acc[m] = warp_sum(acc[m]);
+  }
+  // lane m finishes row m (epilogue reads bias / residual / aux for one element)
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+    if (m < M && lane == m) C[(int64_t)m * ldc + n] = from_f<TOut>(epi_full<bf16, TOut>(acc[m], m, n, ep));
+  }
+}
+
+int emo_gemm_skinny_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                       int64_t ldc, int out_dtype, const EpiParams& ep, cudaStream_t s) {
+  const size_t smem = (size_t)M * K * sizeof(bf16);
+  const unsigned grid = (unsigned)((N + SK_WARPS - 1) / SK_WARPS);
+  if (out_dtype == EMO_BF16)
+    gemm_skinny_nt_kernel<bf16><<<grid, SK_WARPS * 32, smem, s>>>((int)M, N, (int)K, (const bf16*)A, lda, (const bf16*)B, ldb, (bf16*)C, ldc, ep);
+  else
+    gemm_skinny_nt_kernel<float><<<grid, SK_WARPS * 32, smem, s>>>((int)M, N, (int)K, (const bf16*)A, lda, (const bf16*)B, ldb, (float*)C, ldc, ep);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}

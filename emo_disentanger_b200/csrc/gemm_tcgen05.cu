@@ -20,6 +20,9 @@
 int emo_gemm_simt(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
                   void* C, int64_t ldc, int in_dtype, int out_dtype, const EpiParams& ep, cudaStream_t s);
 
+int emo_gemm_skinny_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                       int64_t ldc, int out_dtype, const EpiParams& ep, cudaStream_t s);
+
 namespace tc {
 
 constexpr int BM = 128, BK = 64;
@@ -638,6 +641,8 @@ static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
 static int g_force_simt = 0;
 static int g_no_tma_epi = 0;
 static int g_debug = 0;
+static int g_no_skinny = 0;
+extern "C" void emo_gemm_no_skinny(int on) { g_no_skinny = on; }   // test hook: small-M shapes through the tensor-core kernel
 extern "C" void emo_gemm_debug(int mode) { g_debug = mode; }   // perf triage only; results are wrong when != 0
 extern "C" void emo_gemm_force_simt(int on) { g_force_simt = on; }
 extern "C" void emo_gemm_direct_epilogue(int on) { g_no_tma_epi = on; }   // test / A-B hook: row-per-lane global stores
@@ -656,6 +661,10 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = (in_dtype == EMO_BF16) && !g_force_simt && (lda % 8 == 0) && (ldb % 8 == 0) &&
                ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  // decode step (a handful of rows): weight-streaming GEMV instead of a 128-row tensor-core tile
+  if (tc_ok && op == EMO_GEMM_NT && M <= 8 && K % 8 == 0 && M * K * 2 <= 40 * 1024 && !ep.accumulate && !ep.colsum &&
+      !(ep.act == EMO_ACT_GELU_NEW && ep.aux_out) && !g_no_skinny)
+    return emo_gemm_skinny_nt(M, N, K, A, lda, B, ldb, C, ldc, out_dtype, ep, s);
   if (!tc_ok && ep.colsum) { emo_set_error("emo_gemm: fused column sum is a tensor-core (bf16) epilogue feature"); return EMO_ERR_UNSUPPORTED; }
   if (!tc_ok) return emo_gemm_simt(op, M, N, K, A, lda, B, ldb, C, ldc, in_dtype, out_dtype, ep, s);
 

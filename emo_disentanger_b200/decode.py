@@ -46,12 +46,25 @@ class Stage2Decoder:
             self.state = torch.zeros(L, batch, H, 128, 80, dtype=torch.float32, device=dev)
         else:
             self.kv = torch.zeros(L, batch, max_len, 2 * d, dtype=self.dt, device=dev)
+            # HF Conv1D stores weights [in, out]; decode keeps [out, in] copies (weights are frozen while
+            # generating) so that the one-row-per-sequence step runs the weight-streaming NT kernel
+            Wc = model.weights()
+            self.wT = {}
+            for l in range(L):
+                for nm in ("attn.c_attn", "attn.c_proj", "mlp.c_fc", "mlp.c_proj"):
+                    key = "transformer_decoder.%d.%s.weight" % (l, nm)
+                    self.wT[key] = model._wv(Wc, key).t().contiguous()
         # static step buffers (graph inputs / outputs)
-        self.tok_in = torch.zeros(batch, dtype=torch.int64, device=dev)
-        self.seg_in = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and self.is_performer
         self.graph = None
+        # pinned staging ring for the step inputs (tokens | segments): a slot is rewritten only after the
+        # async H2D copy that read it has completed
+        self._ring = [torch.zeros(2, batch, dtype=torch.int64).pin_memory() for _ in range(8)]
+        self._ring_ev = [None] * 8
+        self._ring_i = 0
+        self._dev_in = torch.zeros(2, batch, dtype=torch.int64, device=dev)
+        self.tok_in, self.seg_in = self._dev_in[0], self._dev_in[1]
 
     def reset(self, b=None):
         sl = slice(None) if b is None else slice(b, b + 1)
@@ -100,7 +113,7 @@ class Stage2Decoder:
             a = new(T, d)
             ops.ln_fwd(h, m._wv(Wf, nm + "ln_1.weight"), m._wv(Wf, nm + "ln_1.bias"), a)
             qkv = new(T, 3 * d)
-            ops.linear_fwd_t(a, m._wv(Wc, nm + "attn.c_attn.weight"), qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"))
+            ops.linear_fwd(a, self.wT[nm + "attn.c_attn.weight"], qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"))
             cache = self.kv[l, b]
             cache[pos0:pos0 + T].copy_(qkv[:, d:])                                   # append K|V rows (plumbing)
             Tk = pos0 + T
@@ -110,16 +123,16 @@ class Stage2Decoder:
             att = new(T, d)
             ops.attn_fwd(q, k, v, att.view(1, T, d), None, 1.0 / (E ** 0.5))
             hx = new(T, d)
-            ops.linear_fwd_t(att, m._wv(Wc, nm + "attn.c_proj.weight"), hx, bias=m._wv(Wf, nm + "attn.c_proj.bias"),
-                             residual=h, ld_res=d)
+            ops.linear_fwd(att, self.wT[nm + "attn.c_proj.weight"], hx, bias=m._wv(Wf, nm + "attn.c_proj.bias"),
+                           residual=h, ld_res=d)
             c = new(T, d)
             ops.ln_fwd(hx, m._wv(Wf, nm + "ln_2.weight"), m._wv(Wf, nm + "ln_2.bias"), c)
             g = new(T, f)
-            ops.linear_fwd_t(c, m._wv(Wc, nm + "mlp.c_fc.weight"), g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"),
-                             act=ops.ACT_GELU_NEW)
+            ops.linear_fwd(c, self.wT[nm + "mlp.c_fc.weight"], g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"),
+                           act=ops.ACT_GELU_NEW)
             h = new(T, d)
-            ops.linear_fwd_t(g, m._wv(Wc, nm + "mlp.c_proj.weight"), h, bias=m._wv(Wf, nm + "mlp.c_proj.bias"),
-                             residual=hx, ld_res=d)
+            ops.linear_fwd(g, self.wT[nm + "mlp.c_proj.weight"], h, bias=m._wv(Wf, nm + "mlp.c_proj.bias"),
+                           residual=hx, ld_res=d)
         return h
 
     def _logits_into(self, hid_rows, out_rows):
@@ -182,9 +195,18 @@ class Stage2Decoder:
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
         if self.is_performer:
-            host = torch.tensor([list(tokens), list(segs)], dtype=torch.int64).pin_memory()
-            self.tok_in.copy_(host[0], non_blocking=True)
-            self.seg_in.copy_(host[1], non_blocking=True)
+            i = self._ring_i
+            self._ring_i = (i + 1) % len(self._ring)
+            if self._ring_ev[i] is not None:
+                self._ring_ev[i].synchronize()
+            host = self._ring[i]
+            for b in range(self.B):
+                host[0, b] = int(tokens[b])
+                host[1, b] = int(segs[b])
+            self._dev_in.copy_(host, non_blocking=True)               # ONE small H2D per step (stream-ordered)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._ring_ev[i] = ev
             if self.use_graph:
                 if self.graph is None:
                     self._capture()

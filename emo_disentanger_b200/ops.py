@@ -221,7 +221,8 @@ def favor_nseg(B, T, H, dtype):
 
 
 def favor_workspace(B, T, H, dtype, device):
-    """[B,H,nseg,128,80] fp32 segment-state workspace for favor_fwd(seg_states=...) / favor_bwd"""
+    """[B,H,nseg+1,128,80] fp32 segment-state workspace for favor_fwd(seg_states=...) / favor_bwd
+    (emo_favor_nseg returns the slot count: nseg local sums, turned into prefixes in place, + the total)"""
     return torch.empty(B, H, favor_nseg(B, T, H, dtype), 128, 80, dtype=torch.float32, device=device)
 
 

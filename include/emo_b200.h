@@ -125,10 +125,11 @@ int emo_colsum(const void* x, int64_t ld, int64_t M, int64_t N, float* out, int 
  * state_in (NULL = start of sequence) / state_out (may be NULL; may alias state_in) [B,H,128,80] fp32:
  * prefix state [sum phi(k) v^T | sum phi(k) | 0] before / after these T tokens (decode appends blocks
  * of tokens -- a lead-sheet bar -- to a running state, stage2_accompaniment/inference.py:293-307).
- * seg_states (NULL = one sequential pass per (b,h)): workspace [B,H,nseg,128,80] fp32, nseg =
- * emo_favor_nseg(B,T,H,dtype).  When given, the sequence is cut into nseg segments that run in parallel
- * (B*H*nseg CTAs): a first kernel writes every segment's local state sum there, the main kernel starts each
- * segment from the exclusive prefix of those sums.  The same buffer is what emo_favor_bwd needs. */
+ * seg_states (NULL = one sequential pass per (b,h)): workspace [B,H,S,128,80] fp32, S = emo_favor_nseg(B,T,H,dtype)
+ * slots (S-1 segments + the total).  When given, the sequence is cut into S-1 segments that run in parallel
+ * (B*H*(S-1) CTAs): a first kernel writes every segment's local state sum there, a tiny scan turns them into
+ * exclusive prefixes in place, the main kernel starts each segment from its prefix.  The same buffer is what
+ * emo_favor_bwd needs. */
 int emo_favor_nseg(int B, int T, int H, int dtype);
 int emo_favor_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const float* omega,
                   void* out, int64_t ld_out, float* den, const float* state_in, float* state_out,

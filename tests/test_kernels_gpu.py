@@ -156,6 +156,35 @@ def test_gemm_tma_store_epilogue_equals_direct_epilogue(ops, M, N, K):
     assert rel_err(cs32, o32.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 512, 512), (4, 2048, 512), (8, 512, 2048), (3, 329, 512), (2, 1536, 512)])
+def test_gemm_skinny_decode_rows(ops, M, N, K):
+    """M <= 8 rows (decode step) run the weight-streaming GEMV: same numbers as the tensor-core kernel and as torch."""
+    from emo_disentanger_b200 import _lib
+    torch.manual_seed(M * N)
+    a, w = _bf(torch.randn(M, K, device=DEV)), _bf(torch.randn(N, K, device=DEV) * 0.05)
+    bias = torch.randn(N, device=DEV) * 0.1
+    ldc = (N + 7) // 8 * 8
+    res = _bf(torch.randn(M, ldc, device=DEV))
+    ref = a.float() @ w.float().T + bias
+    for kw0, r in ((dict(bias=bias), ref), (dict(bias=bias, act=ops.ACT_RELU), torch.relu(ref)),
+                   (dict(bias=bias, residual=res[:, :N], ld_res=ldc), ref + res[:, :N].float())):
+        for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 6e-3)):
+            kw = dict(kw0)
+            if "residual" in kw:                      # the residual operand is in the OUTPUT dtype (emo_b200.h)
+                kw["residual"] = res.to(dt)[:, :N]
+            o1 = torch.full((M, ldc), 3.0, device=DEV, dtype=dt)
+            ops.linear_fwd(a, w, o1[:, :N], **kw)
+            assert (rel_err(o1[:, :N].float(), r) if dt == torch.float32 else rms_rel(o1[:, :N].float(), r)) < tol
+            assert float(o1[:, N:].float().min()) == 3.0 if ldc > N else True
+            o2 = torch.empty_like(o1)
+            _lib.lib().emo_gemm_no_skinny(1)
+            try:
+                ops.linear_fwd(a, w, o2[:, :N], **kw)
+            finally:
+                _lib.lib().emo_gemm_no_skinny(0)
+            assert rel_err(o1[:, :N].float(), o2[:, :N].float()) < (2e-5 if dt == torch.float32 else 1e-2)
+
+
 @pytest.mark.parametrize("op", ["nt", "nn", "tn"])
 def test_gemm_fp32_simt(ops, op):
     torch.manual_seed(5)
@@ -375,14 +404,19 @@ def test_favor_forward_vs_oracle(ops, dtype, T):
     qo, ko, vo = _split(qkv_d.float().cpu().double(), H)
     ref, rden = PO.causal_linear_attention(qo, ko, vo, omega.double())
     tol = 1e-4 if dtype == torch.float32 else 1.5e-2
+    # the normaliser is dominated by its largest features, where the bf16 rounding of (log2e-scaled) Omega shows most;
+    # the north-star bound (1e-2 on bf16 hidden states) is held at the model level in test_performer_gpu.py
+    dtol = 1e-4 if dtype == torch.float32 else 2e-2
     assert rel_err(out.float().view(B, T, H, 64), ref.float()) < tol
-    assert rel_err(den, rden.float()) < tol
-    # segment-parallel schedule (what training uses): same result, and the segment sums add up to the final state
+    assert rel_err(den, rden.float()) < dtol
+    # segment-parallel schedule (what training uses): same result; the workspace holds the exclusive prefixes of the
+    # segment sums (slot 0 = empty prefix, last slot = the final state)
     ws = ops.favor_workspace(B, T, H, dtype, DEV)
     out2, den2, state2 = torch.empty_like(out), torch.empty_like(den), torch.empty_like(state)
     ops.favor_fwd(q, k, v, omega.to(DEV), out2, den2, state2, seg_states=ws)
-    assert rel_err(out2.float().view(B, T, H, 64), ref.float()) < tol and rel_err(den2, rden.float()) < tol
-    assert rel_err(ws.sum(2), state) < 1e-5 and rel_err(state2, state) < 1e-5
+    assert rel_err(out2.float().view(B, T, H, 64), ref.float()) < tol and rel_err(den2, rden.float()) < dtol
+    assert rel_err(ws[:, :, -1], state) < 1e-5 and rel_err(state2, state) < 1e-5
+    assert float(ws[:, :, 0].abs().max()) == 0.0
     # final prefix state == sum_j phi(k_j) [v_j | 1]
     K = PO.favor_features(ko, omega.double())
     S = torch.einsum("nlhi,nlhd->nhid", K, vo)
