@@ -135,6 +135,64 @@ def run_reference(args):
     return 0
 
 
+def bench_decode(model, V, n_tokens=384, prompt=64, cpu=True):
+    """BASELINE.json's second metric: 1-GPU autoregressive decode tokens/s of the stage-2 Performer (bf16), through
+    the decode engine the inference script uses: incremental FAVOR+ state (CUDA-graph step), fused temperature +
+    nucleus sampler on the device, ONE int64 per sequence per step back to the host.  batch 1 = one quadrant,
+    batch 4 = the four emotion quadrants of a lead-sheet pair decoded together."""
+    import numpy as np
+    import torch
+    from emo_disentanger_b200.decode import Stage2Decoder
+    from emo_disentanger_b200.generate import DeviceSampler
+    model.eval()
+    out = {"metric": "stage2_performer_decode_tokens_per_sec", "unit": "tokens/s", "temperature": 1.2, "top_p": 0.9,
+           "prompt_tokens": prompt, "generated_tokens_per_sequence": n_tokens, "dtype": "bf16",
+           "api": "Stage2Decoder.step + DeviceSampler.draw (host loop, D2H of the sampled ids every step)"}
+    np.random.seed(0)
+    for B in (1, 4):
+        dec = Stage2Decoder(model, batch=B, max_len=2048)
+        smp = DeviceSampler(dec.dev, rows=B)
+        rng = np.random.RandomState(B)
+        for b in range(B):
+            dec.append(b, rng.randint(0, V - 1, size=prompt).tolist(), [0] * prompt)
+        toks = [5] * B
+        for phase, n in (("warm", 16), ("timed", n_tokens)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                lg = dec.step(toks, [1] * B)
+                toks = smp.draw(lg, V, 1.2, 0.9)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out["batch%d" % B] = {"value": B * n_tokens / dt, "us_per_step": 1e6 * dt / n_tokens}
+        del dec
+    if cpu:
+        # the reference loop (inference.py:252-272) re-runs the model over the WHOLE prefix for every token; timed on
+        # the oracle port at one representative prefix length (cost grows linearly with the prefix)
+        from oracle import performer_oracle as PO
+        import os
+        torch.set_num_threads(os.cpu_count() or 1)
+        shapes = PO.performer_state_shapes(V, CFG["n_layer"])
+        sd = PO.seeded_state(shapes, 0)
+        sd["pe.pe"] = PO.sinusoid_pe(12000, 512)
+        plen, reps = 512, 3
+        tok = torch.randint(0, V - 1, (1, plen))
+        seg = torch.ones(1, plen, dtype=torch.long)
+        with torch.no_grad():
+            om = [PO.draw_omega(64, 64) for _ in range(CFG["n_layer"])]
+            PO.performer_forward(sd, tok, seg, om, CFG["n_layer"], 8, 512)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                om = [PO.draw_omega(64, 64) for _ in range(CFG["n_layer"])]
+                PO.performer_forward(sd, tok, seg, om, CFG["n_layer"], 8, 512)
+            dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d full-prefix forwards at prefix length %d (one per generated token, as the "
+                                         "reference loop does), fp32 oracle port" % (reps, plen)}
+    model.train()
+    return out
+
+
 def workload_config(B, world, l2note):
     return {"workload": "stage2 Performer train step: 12L d512 8h ff2048 FAVOR+ M=128, functional repr V=%d, "
                         "seq=%d, per-GPU batch %d, dropout 0.1, clip 0.5 + Adam, Omega redrawn per forward"
@@ -151,6 +209,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (sequences of 2048 tokens)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the 1-GPU autoregressive decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps or 3
@@ -297,6 +356,11 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "roofline": roof, "kernel_time_shares": shares,
             "clocks": ck, "loss_last_step": loss_last, "impl": "b200"}
 
+    if rank == 0 and world == 1 and not args.no_decode:
+        del devb, opt, sync
+        model.zero_grad()
+        torch.cuda.empty_cache()
+        line["decode"] = bench_decode(model, V, cpu=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_train import time_cpu_train
         r = time_cpu_train(V=V, B=1, T=T, steps=3, warmup=1)

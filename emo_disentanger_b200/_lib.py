@@ -16,7 +16,8 @@ vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 class Epilogue(C.Structure):
     _fields_ = [("bias", vp), ("act", i32), ("aux", vp), ("aux_out", vp), ("ld_aux", i64),
                 ("aux_scale", f32), ("drop_p", f32), ("seed", u64), ("residual", vp), ("ld_res", i64),
-                ("alpha", f32), ("accumulate", i32), ("rowscale", vp), ("colsum", vp)]
+                ("alpha", f32), ("accumulate", i32), ("rowscale", vp), ("colsum", vp),
+                ("ln_gamma", vp), ("ln_beta", vp), ("ln_out", vp), ("ld_ln", i64)]
 
 
 SIGNATURES = {

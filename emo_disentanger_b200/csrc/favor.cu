@@ -650,24 +650,31 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// decode step (recurrent form): one CTA of 128 threads per (sequence, head)
+// decode step (recurrent form): one CTA of 256 threads per (sequence, head).  The [128 x 80] fp32 state is
+// streamed once (read + write, 16-byte vectors, consecutive threads on consecutive columns of a row);
+// out = phi(q) . S' normalised by its ones-column.
 // ---------------------------------------------------------------------------------------------
+constexpr int FS_CG = 17;                    // float4 column groups that carry data: 64 values + the ones column
+constexpr int FS_RL = 15;                    // row lanes: 17 x 15 = 255 threads stream the state
 template <typename T>
-__global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q, const T* __restrict__ k,
+__global__ void __launch_bounds__(256) favor_step_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                          const T* __restrict__ v, int64_t ld,
                                                          const float* __restrict__ omega, float* __restrict__ state,
                                                          T* __restrict__ out, int64_t ld_out, int H) {
-  __shared__ float xq[FE], xk[FE], vv[FE + 1], pq[FM], pk[FM], red[4][FE + 1];
+  __shared__ float xq[FE], xk[FE], pq[FM], pk[FM];
+  __shared__ __align__(16) float vv[FS_CG * 4];
+  __shared__ float red[FS_RL][FS_CG * 4];
   const int b = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x;
   const float s = 0.35355339059327373f;
   if (tid < FE) {
     xq[tid] = to_f(q[(int64_t)b * ld + h * FE + tid]) * s;
     xk[tid] = to_f(k[(int64_t)b * ld + h * FE + tid]) * s;
     vv[tid] = to_f(v[(int64_t)b * ld + h * FE + tid]);
+  } else if (tid < FS_CG * 4) {
+    vv[tid] = (tid == FE) ? 1.f : 0.f;
   }
-  if (tid == 0) vv[FE] = 1.f;
   __syncthreads();
-  {  // thread f<64 -> q feature f ; thread 64+f -> k feature f
+  if (tid < 2 * FE) {  // thread f<64 -> q feature f ; thread 64+f -> k feature f
     const float* x = (tid < FE) ? xq : xk;
     int f = tid & (FE - 1);
     float u = 0.f, n2 = 0.f;
@@ -679,28 +686,31 @@ __global__ void __launch_bounds__(128) favor_step_kernel(const T* __restrict__ q
     p[FE + f] = expf(-u - o);
   }
   __syncthreads();
-  // thread i owns state row i (feature i): update, then contribute to the output reduction
-  float* srow = state + ((int64_t)blockIdx.x * FM + tid) * FV;
-  float pki = pk[tid], pqi = pq[tid];
-  float part[FE + 1];
-#pragma unroll
-  for (int c = 0; c <= FE; ++c) {
-    float sv = srow[c] + pki * vv[c];
-    srow[c] = sv;
-    part[c] = pqi * sv;
-  }
-  // reduce over the 128 features: warp shuffle then across 4 warps
-#pragma unroll
-  for (int c = 0; c <= FE; ++c) {
-    float x = warp_sum(part[c]);
-    if ((tid & 31) == 0) red[tid >> 5][c] = x;
+  if (tid < FS_CG * FS_RL) {
+    const int cg = tid % FS_CG, rl = tid / FS_CG;
+    const float4 v4 = *reinterpret_cast<const float4*>(&vv[cg * 4]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* sbase = state + (int64_t)blockIdx.x * FM * FV + cg * 4;
+#pragma unroll 3
+    for (int f = rl; f < FM; f += FS_RL) {
+      float4* sp = reinterpret_cast<float4*>(sbase + f * FV);
+      float4 sv = *sp;
+      const float a = pk[f], c = pq[f];
+      sv.x = fmaf(a, v4.x, sv.x); sv.y = fmaf(a, v4.y, sv.y); sv.z = fmaf(a, v4.z, sv.z); sv.w = fmaf(a, v4.w, sv.w);
+      *sp = sv;
+      acc.x = fmaf(c, sv.x, acc.x); acc.y = fmaf(c, sv.y, acc.y); acc.z = fmaf(c, sv.z, acc.z); acc.w = fmaf(c, sv.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(&red[rl][cg * 4]) = acc;
   }
   __syncthreads();
-  if (tid < FE) {
-    float num = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-    float den = red[0][FE] + red[1][FE] + red[2][FE] + red[3][FE] + F_EPS;
-    out[(int64_t)b * ld_out + h * FE + tid] = from_f<T>(num / den);
+  if (tid <= FE) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < FS_RL; ++r) t += red[r][tid];
+    red[0][tid] = t;
   }
+  __syncthreads();
+  if (tid < FE) out[(int64_t)b * ld_out + h * FE + tid] = from_f<T>(red[0][tid] / (red[0][FE] + F_EPS));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -840,9 +850,9 @@ extern "C" int emo_favor_step(const void* q, const void* k, const void* v, int64
   if (B * H == 0) return EMO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == EMO_BF16)
-    favor_step_kernel<bf16><<<B * H, 128, 0, s>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, ld_qkv, omega, state, (bf16*)out, ld_out, H);
+    favor_step_kernel<bf16><<<B * H, 256, 0, s>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, ld_qkv, omega, state, (bf16*)out, ld_out, H);
   else
-    favor_step_kernel<float><<<B * H, 128, 0, s>>>((const float*)q, (const float*)k, (const float*)v, ld_qkv, omega, state, (float*)out, ld_out, H);
+    favor_step_kernel<float><<<B * H, 256, 0, s>>>((const float*)q, (const float*)k, (const float*)v, ld_qkv, omega, state, (float*)out, ld_out, H);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -18,6 +18,10 @@ struct EpiParams {
   int accumulate;
   const float* rowscale;
   float* colsum;     // optional fp32 [N]: += column sums of the stored values (fused bias gradient)
+  const float* ln_gamma;   // A-operand LayerNorm prologue (decode rows): A := LN(A) * gamma + beta, also stored to ln_out
+  const float* ln_beta;
+  void* ln_out;
+  int64_t ld_ln;
   int64_t n_total;   // logical N (dropout element index = m * n_total + n)
 };
 
@@ -32,6 +36,7 @@ static inline EpiParams make_epi(const emo_epilogue* e, int64_t N) {
     p.aux_scale = e->aux_scale; p.drop_thr = emo_drop_thr(e->drop_p);
     p.keep_scale = 1.f / (1.f - e->drop_p); p.seed = e->seed; p.residual = e->residual; p.ld_res = e->ld_res;
     p.alpha = e->alpha; p.accumulate = e->accumulate; p.rowscale = (const float*)e->rowscale; p.colsum = e->colsum;
+    p.ln_gamma = e->ln_gamma; p.ln_beta = e->ln_beta; p.ln_out = e->ln_out; p.ld_ln = e->ld_ln;
   }
   return p;
 }

@@ -127,14 +127,66 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, in
   bf16* As = reinterpret_cast<bf16*>(sk_smem);           // [M][K]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kv = K >> 3;                                  // 16-byte vectors per row
-  for (int i = threadIdx.x; i < M * kv; i += SK_WARPS * 32) {
-    int m = i / kv, c = i % kv;
-    reinterpret_cast<uint4*>(As)[i] = *reinterpret_cast<const uint4*>(A + (int64_t)m * lda + c * 8);
+  // the weight row does not depend on the previous kernel's output: get its first vectors in flight before
+  // anything else (the step is a chain of small dependent launches; every exposed latency counts)
+  const int64_t n = (int64_t)blockIdx.x * SK_WARPS + warp;
+  const bf16* brow = B + (n < N ? n : 0) * ldb;
+  uint4 bw0[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int c = lane + 32 * u;
+    bw0[u] = (c < kv) ? __ldg(reinterpret_cast<const uint4*>(brow) + c) : make_uint4(0, 0, 0, 0);
+  }
+  for (int i0 = threadIdx.x; i0 < M * kv; i0 += SK_WARPS * 32 * 4) {      // 4 activation vectors in flight per thread
+    uint4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i = i0 + u * SK_WARPS * 32;
+      if (i < M * kv) t[u] = *reinterpret_cast<const uint4*>(A + (int64_t)(i / kv) * lda + (i % kv) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i = i0 + u * SK_WARPS * 32;
+      if (i < M * kv) reinterpret_cast<uint4*>(As)[i] = t[u];
+    }
   }
   __syncthreads();
-  const int64_t n = (int64_t)blockIdx.x * SK_WARPS + warp;
+  if (ep.ln_gamma) {
+    // LayerNorm prologue (K == 512): the rows are tiny, so every CTA normalises its own copy in shared memory
+    // (fp32 statistics, bf16 result -- the numbers emo_ln_fwd writes); CTA 0 also stores them for the residual
+    // branch of the next projection.  Saves a launch per LayerNorm in the launch-latency-bound decode step.
+    for (int m = warp; m < M; m += SK_WARPS) {
+      uint4* row = reinterpret_cast<uint4*>(As + m * K);
+      float x[16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 t = row[lane + 32 * h];
+        unpack_bf16x2(t.x, x[8 * h], x[8 * h + 1]); unpack_bf16x2(t.y, x[8 * h + 2], x[8 * h + 3]);
+        unpack_bf16x2(t.z, x[8 * h + 4], x[8 * h + 5]); unpack_bf16x2(t.w, x[8 * h + 6], x[8 * h + 7]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum += x[j];
+      const float mu = warp_sum(sum) * (1.f / 512.f);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { float d = x[j] - mu; q += d * d; }
+      const float rs = rsqrtf(warp_sum(q) * (1.f / 512.f) + 1e-5f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = (lane + 32 * h) * 8;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (x[8 * h + j] - mu) * rs * ep.ln_gamma[c0 + j] + ep.ln_beta[c0 + j];
+        uint4 t;
+        t.x = pack_bf16x2(y[0], y[1]); t.y = pack_bf16x2(y[2], y[3]); t.z = pack_bf16x2(y[4], y[5]); t.w = pack_bf16x2(y[6], y[7]);
+        row[lane + 32 * h] = t;
+        if (blockIdx.x == 0 && ep.ln_out) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.ln_out) + (int64_t)m * ep.ld_ln + c0) = t;
+      }
+    }
+    __syncthreads();
+  }
   if (n >= N) return;
-  const bf16* brow = B + n * ldb;
   float acc[SK_MAXM];
 #pragma unroll
   for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
@@ -143,7 +195,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, in
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int c = c0 + 32 * u;
-      bw[u] = (c < kv) ? __ldg(reinterpret_cast<const uint4*>(brow) + c) : make_uint4(0, 0, 0, 0);
+      if (c0 == lane) bw[u] = bw0[u];                      // first trip: prefetched above
+      else bw[u] = (c < kv) ? __ldg(reinterpret_cast<const uint4*>(brow) + c) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {

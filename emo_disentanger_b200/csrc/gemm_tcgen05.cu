@@ -661,8 +661,22 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = (in_dtype == EMO_BF16) && !g_force_simt && (lda % 8 == 0) && (ldb % 8 == 0) &&
                ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  if (ep.ln_gamma) {
+    EMO_REQUIRE(in_dtype == EMO_BF16 && K == 512 && ep.ln_beta && ep.ln_out && op != EMO_GEMM_TN,
+                "emo_gemm: the LayerNorm prologue needs bf16 operands, K == 512, ln_beta and ln_out");
+  }
+  const bool skinny = tc_ok && op == EMO_GEMM_NT && M <= 8 && K % 8 == 0 && M * K * 2 <= 40 * 1024 && !ep.accumulate &&
+                      !ep.colsum && !(ep.act == EMO_ACT_GELU_NEW && ep.aux_out) && !g_no_skinny;
+  if (ep.ln_gamma && !skinny) {   // general shapes: a separate LayerNorm launch, then the product on its output
+    EMO_REQUIRE(lda == 512 && ep.ld_ln == 512, "emo_gemm: LayerNorm prologue on the general path needs contiguous rows");
+    int rc = emo_ln_fwd(A, ep.ln_gamma, ep.ln_beta, ep.ln_out, nullptr, nullptr, M, 512, 1e-5f, EMO_BF16, stream);
+    if (rc) return rc;
+    A = ep.ln_out;
+    lda = ep.ld_ln;
+    ep.ln_gamma = nullptr;
+  }
   // decode step (a handful of rows): weight-streaming GEMV instead of a 128-row tensor-core tile
-  if (tc_ok && op == EMO_GEMM_NT && M <= 8 && K % 8 == 0 && M * K * 2 <= 40 * 1024 && !ep.accumulate && !ep.colsum &&
+  if (skinny && op == EMO_GEMM_NT && M <= 8 && K % 8 == 0 && M * K * 2 <= 40 * 1024 && !ep.accumulate && !ep.colsum &&
       !(ep.act == EMO_ACT_GELU_NEW && ep.aux_out) && !g_no_skinny)
     return emo_gemm_skinny_nt(M, N, K, A, lda, B, ldb, C, ldc, out_dtype, ep, s);
   if (!tc_ok && ep.colsum) { emo_set_error("emo_gemm: fused column sum is a tensor-core (bf16) epilogue feature"); return EMO_ERR_UNSUPPORTED; }

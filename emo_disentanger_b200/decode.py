@@ -76,31 +76,39 @@ class Stage2Decoder:
 
     # ---- shared layer tails -------------------------------------------------------------------
     def _performer_rows(self, h, B, T, favor):
-        """h [B*T, d] -> hidden after the 12 post-LN layers; `favor(l, q, k, v, att)` runs the attention."""
+        """h [B*T, d] (embedding rows) -> (s2, norm) of the LAST layer: the hidden state is LN(s2) with `norm`, which
+        the caller folds into the logits projection.  `favor(l, qkv, att)` runs the attention.
+        Post-LN layers: each LayerNorm is fused into the projection that consumes it (ops.gemm ln=...: in-kernel for
+        the <= 8 rows of a decode step, a separate launch for a longer block), so a layer is 5 launches."""
         m = self.m
         d, f, H = m.d_model, m.d_ff, m.n_head
         Wc, Wf = m.weights(), m._flat
         R = B * T
         new = lambda *shape, dtype=self.dt: torch.empty(*shape, dtype=dtype, device=self.dev)
+        pre, norm = h, None                 # layer input = LN(pre) with `norm` (None: `pre` is the input itself)
         for l in range(m.n_layer):
             nm = m._layer_names(l)
             qkv = new(R, 3 * d)
-            ops.linear_fwd(h, m._qkv_w(Wc, l), qkv, bias=m._qkv_b(Wf, l))
+            if norm is None:
+                h_in = pre
+                ops.linear_fwd(h_in, m._qkv_w(Wc, l), qkv, bias=m._qkv_b(Wf, l))
+            else:
+                h_in = new(R, d)
+                ops.linear_fwd(pre, m._qkv_w(Wc, l), qkv, bias=m._qkv_b(Wf, l), ln=(norm[0], norm[1], h_in))
             att = new(R, d)
             favor(l, qkv, att)
             s1 = new(R, d)
             ops.linear_fwd(att, m._wv(Wc, nm + "attention.out_projection.weight"), s1,
-                           bias=m._wv(Wf, nm + "attention.out_projection.bias"), residual=h, ld_res=d)
+                           bias=m._wv(Wf, nm + "attention.out_projection.bias"), residual=h_in, ld_res=d)
             y1 = new(R, d)
-            ops.ln_fwd(s1, m._wv(Wf, nm + "norm1.weight"), m._wv(Wf, nm + "norm1.bias"), y1)
             hh = new(R, f)
-            ops.linear_fwd(y1, m._wv(Wc, nm + "linear1.weight"), hh, bias=m._wv(Wf, nm + "linear1.bias"), act=ops.ACT_RELU)
+            ops.linear_fwd(s1, m._wv(Wc, nm + "linear1.weight"), hh, bias=m._wv(Wf, nm + "linear1.bias"), act=ops.ACT_RELU,
+                           ln=(m._wv(Wf, nm + "norm1.weight"), m._wv(Wf, nm + "norm1.bias"), y1))
             s2 = new(R, d)
             ops.linear_fwd(hh, m._wv(Wc, nm + "linear2.weight"), s2, bias=m._wv(Wf, nm + "linear2.bias"),
                            residual=y1, ld_res=d)
-            h = new(R, d)
-            ops.ln_fwd(s2, m._wv(Wf, nm + "norm2.weight"), m._wv(Wf, nm + "norm2.bias"), h)
-        return h
+            pre, norm = s2, (m._wv(Wf, nm + "norm2.weight"), m._wv(Wf, nm + "norm2.bias"))
+        return pre, norm
 
     def _gpt2_rows(self, h, b, T, pos0):
         """one sequence b, T new rows at positions pos0.. -> hidden"""
@@ -135,10 +143,14 @@ class Stage2Decoder:
                            residual=hx, ld_res=d)
         return h
 
-    def _logits_into(self, hid_rows, out_rows):
+    def _logits_into(self, hid_rows, out_rows, norm=None):
+        """norm = (gamma, beta): hid_rows are pre-LayerNorm sums of the last layer (Performer, post-LN)"""
         m = self.m
+        ln = None
+        if norm is not None:
+            ln = (norm[0], norm[1], torch.empty(hid_rows.shape[0], m.d_model, dtype=self.dt, device=self.dev))
         ops.linear_fwd(hid_rows, m._wv(m.weights(), "dec_out_proj.weight"), out_rows[:, :m.n_token],
-                       bias=m._wv(m._flat, "dec_out_proj.bias"))
+                       bias=m._wv(m._flat, "dec_out_proj.bias"), ln=ln)
 
     # ---- append a block of tokens to ONE sequence (primer / lead-sheet bar) -------------------------
     @torch.no_grad()
@@ -162,10 +174,10 @@ class Stage2Decoder:
                 q, k, v = (q3[:, :, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
                 st = self.state[l, b:b + 1]
                 ops.favor_fwd(q, k, v, self.omegas[l], att.view(1, T, d), None, state_out=st, state_in=st)
-            hid = self._performer_rows(h, 1, T, favor)
+            hid, norm = self._performer_rows(h, 1, T, favor)
         else:
-            hid = self._gpt2_rows(h, b, T, pos0)
-        self._logits_into(hid[T - 1:T], self.logits[b:b + 1])
+            hid, norm = self._gpt2_rows(h, b, T, pos0), None
+        self._logits_into(hid[T - 1:T], self.logits[b:b + 1], norm)
         self.pos_host[b] = pos0 + T
         self.pos[b] = pos0 + T
         return self.logits[b, :m.n_token]
@@ -183,8 +195,8 @@ class Stage2Decoder:
         def favor(l, qkv, att):
             q, k, v = (qkv[:, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
             ops.favor_step(q, k, v, self.omegas[l], self.state[l], att)
-        hid = self._performer_rows(h, B, 1, favor)
-        self._logits_into(hid, self.logits)
+        hid, norm = self._performer_rows(h, B, 1, favor)
+        self._logits_into(hid, self.logits, norm)
         self.pos.add_(1)
 
     @torch.no_grad()

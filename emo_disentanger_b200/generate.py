@@ -26,9 +26,13 @@ class DeviceSampler:
     """temperature + nucleus on the device (K11).  greedy=True -> argmax (bit-exact decode mode)."""
 
     def __init__(self, device, rows=1):
+        self.rows = rows
         self.u = torch.zeros(rows, dtype=torch.float32, device=device)
-        self.out = torch.zeros(rows, dtype=torch.int64, device=device)
-        self.status = torch.zeros(rows, dtype=torch.int32, device=device)
+        self._buf = torch.zeros(2 * rows, dtype=torch.int64, device=device)     # sampled ids | status words
+        self.out = self._buf[:rows]
+        self.status = self._buf[rows:].view(torch.int32)[:rows]
+        self._u_host = torch.zeros(rows, dtype=torch.float32).pin_memory()
+        self._host = torch.zeros(2 * rows, dtype=torch.int64).pin_memory()
 
     def draw(self, logits, V, temp, top_p, greedy=False, rng=None):
         """logits fp32 [rows, >=V] (device).  Returns python ints (tokens); raises IndexError where the
@@ -36,12 +40,16 @@ class DeviceSampler:
         rows = logits.shape[0]
         if not greedy:
             r = np.random if rng is None else rng
-            self.u[:rows].copy_(torch.tensor([r.random_sample() for _ in range(rows)], dtype=torch.float32))
+            for i in range(rows):
+                self._u_host[i] = r.random_sample()
+            self.u.copy_(self._u_host, non_blocking=True)
         ops.sample(logits, V, temp, top_p, self.u, self.out, self.status, greedy=greedy)
-        res = torch.stack([self.out[:rows], self.status[:rows].to(torch.int64)]).cpu()      # ONE small D2H
-        if int(res[1].max()) != 0:
+        self._host.copy_(self._buf, non_blocking=True)                          # ONE small D2H into pinned memory
+        torch.cuda.current_stream().synchronize()
+        st = self._host[self.rows:].view(torch.int32)[:rows]
+        if int(st.max()) != 0:
             raise IndexError("index 1 is out of bounds for axis 0 with size 1")
-        return [int(x) for x in res[0]]
+        return self._host[:rows].tolist()
 
 
 def get_position_idx(event):

@@ -132,15 +132,23 @@ def dropout_apply(x, y, drop_p, seed):
 
 
 def gemm(op, M, N, K, A, lda, B, ldb, Cmat, ldc, bias=None, act=ACT_NONE, aux=None, aux_out=None, ld_aux=0,
-         aux_scale=1.0, drop_p=0.0, seed=0, residual=None, ld_res=0, alpha=1.0, accumulate=False, colsum_out=None):
+         aux_scale=1.0, drop_p=0.0, seed=0, residual=None, ld_res=0, alpha=1.0, accumulate=False, colsum_out=None,
+         ln=None):
     """Raw GEMM call; A/B/Cmat are tensors (or (tensor, element_offset) handled by the caller via views).
     colsum_out (fp32 [N]) += column sums of the stored C (bias gradient): fused into the epilogue on the
-    bf16 tensor-core path, a separate emo_colsum launch otherwise."""
+    bf16 tensor-core path, a separate emo_colsum launch otherwise.
+    ln = (gamma, beta, out): A := LayerNorm(A) before the product (K == 512, bf16), normalised rows also written to
+    `out` -- fused into the decode-rows kernel, a separate LN launch for larger M."""
     _need_cuda(A, B, Cmat)
+    if ln is not None and (A.dtype != torch.bfloat16 or K != 512 or op == GEMM_TN):
+        ln_fwd(A, ln[0], ln[1], ln[2])          # fp32 parity mode: LayerNorm as its own launch
+        A, lda, ln = ln[2], ln[2].stride(0), None
     fuse_cs = (colsum_out is not None and A.dtype == torch.bfloat16 and Cmat.dtype == torch.bfloat16 and N % 64 == 0
                and ldc % 8 == 0 and Cmat.data_ptr() % 16 == 0 and not accumulate)
     e = L.Epilogue(_p(bias), act, _p(aux), _p(aux_out), ld_aux, aux_scale, drop_p, int(seed), _p(residual), ld_res,
-                   alpha, 1 if accumulate else 0, None, _p(colsum_out) if fuse_cs else None)
+                   alpha, 1 if accumulate else 0, None, _p(colsum_out) if fuse_cs else None,
+                   _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, _p(ln[2]) if ln else None,
+                   ln[2].stride(0) if ln else 0)
     assert A.dtype == B.dtype
     tk = TIMER.start("gemm")
     L.check(L.lib().emo_gemm(op, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, _dt(A), _dt(Cmat), C.byref(e),

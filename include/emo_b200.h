@@ -107,6 +107,10 @@ typedef struct {
   float* colsum;        /* optional fp32 [N]: colsum[n] += sum_m C[m,n] of the values stored (the
                            bias gradient of the producing layer, fused into its dgrad GEMM);
                            bf16 tensor-core path with N % 64 == 0 only, else EMO_ERR_UNSUPPORTED */
+  const float* ln_gamma; /* optional A-operand prologue (bf16, K == 512): A := LayerNorm(A)*gamma+beta   */
+  const float* ln_beta;  /* (eps 1e-5) before the product; the normalised rows are also written to       */
+  void* ln_out;          /* ln_out [M, ld_ln] (input dtype; required).  Fused into the decode-rows GEMV   */
+  int64_t ld_ln;         /* (M <= 8); otherwise emo_gemm runs emo_ln_fwd into ln_out first.               */
 } emo_epilogue;
 int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
              int64_t ldb, void* C, int64_t ldc, int in_dtype, int out_dtype,
