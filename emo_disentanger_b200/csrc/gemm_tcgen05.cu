@@ -32,8 +32,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 64 bf16 columns, 128B swizzle
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;   // double-buffered per warp: 64 KB
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
-template <int BN> struct StageCfg {
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+template <int BN, int CG> struct StageCfg {
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / CG) * BK * 2;     // per CTA: its A rows + its share of B
   static constexpr int RAW = (SMEM_BUDGET - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW > 6 ? 6 : RAW;
 };
@@ -68,6 +68,45 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the EVEN CTA of a pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// CTA-pair load: data lands in THIS CTA's smem, the bytes are counted on the leader (even) CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the even CTA's barrier (from either CTA)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {         // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -330,15 +369,21 @@ __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TOut>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, tcgen05 cta_group::2) per 256 x BN tile:
+// each CTA stages its own 128 A rows and HALF of the B tile, the leader's single MMA drives both tensor cores and
+// reads B from both CTAs' shared memory -- a third less L2->smem traffic and smem fill per flop than CG = 1, which
+// is what bounds the K = 512 shapes (profiles/).  Each CTA runs its own epilogue on its 128 accumulator rows.
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ Params p) {
-  constexpr int STAGES = StageCfg<BN>::STAGES;
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGES = StageCfg<BN, CG>::STAGES;
+  constexpr int BNL = BN / CG;                     // B rows (output columns) staged by this CTA
+  constexpr int STAGE_BYTES = StageCfg<BN, CG>::STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, nunits = gridDim.x / CG;   // scheduling unit = CTA (CG 1) or CTA pair (CG 2)
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -360,13 +405,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.tma_epi) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     if (p.has_r) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(r_bar(w, 0), 1); mbar_init(r_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -377,37 +426,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      auto load = [&](const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+        if (CG == 2) tma_load_2d_pair(map, bar, dst, c0, c1);
+        else tma_load_2d(map, bar, dst, c0, c1);
+      };
+      for (int it = unit; it < items; it += nunits) {
         int split = it / tiles, rem = it % tiles;
-        int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+        int m0 = (rem / p.n_tiles) * (BM * CG) + rank * BM, n0 = (rem % p.n_tiles) * BN + rank * BNL;
         int kb0 = split * p.kb_per_split;
         int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), STAGE_BYTES * CG);   // the pair's bytes are counted on the leader
           int k0 = kb * BK;
-          if (!A_MN) tma_load_2d(&tmA, full_bar(stage), sa, k0, m0);
+          if (!A_MN) load(&tmA, full_bar(stage), sa, k0, m0);
           else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(&tmA, full_bar(stage), sa + i * 8192, m0 + 64 * i, k0);
+            for (int i = 0; i < BM / 64; ++i) load(&tmA, full_bar(stage), sa + i * 8192, m0 + 64 * i, k0);
           }
-          if (!B_MN) tma_load_2d(&tmB, full_bar(stage), sb, k0, n0);
+          if (!B_MN) load(&tmB, full_bar(stage), sb, k0, n0);
           else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, full_bar(stage), sb + i * 8192, n0 + 64 * i, k0);
+            for (int i = 0; i < BNL / 64; ++i) load(&tmB, full_bar(stage), sb + i * 8192, n0 + 64 * i, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {      // the leader CTA issues the MMAs of the pair
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      for (int it = unit; it < items; it += nunits) {
         int split = it / tiles;
         int kb0 = split * p.kb_per_split;
         int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -427,12 +480,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 0, 1024);
             uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_2(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if (CG == 2) umma_commit2(empty_bar(stage));
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (p.debug & 2) mbar_arrive(tfull_bar(as));
+        else if (CG == 2) umma_commit2(tfull_bar(as));
         else umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
@@ -464,13 +520,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t g = 0;
       auto coords = [&](int it_, int c_, int& col, int& rowc) {
         int rem_ = it_ % tiles;
-        rowc = (rem_ / p.n_tiles) * BM + quad * 32;
+        rowc = (rem_ / p.n_tiles) * (BM * CG) + rank * BM + quad * 32;
         col = (rem_ % p.n_tiles) * BN + (half * GROUPS + c_) * 64;
       };
       // advance (it_, c_) to this warp's next group whose columns lie inside N; false at the end of the work list
       auto next_valid = [&](int& it_, int& c_) -> bool {
         while (true) {
-          if (++c_ == GROUPS) { c_ = 0; it_ += gridDim.x; }
+          if (++c_ == GROUPS) { c_ = 0; it_ += nunits; }
           if (it_ >= items) return false;
           int col_, row_;
           coords(it_, c_, col_, row_);
@@ -478,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       if (p.has_r && lane == 0) {       // residual / aux tile of the first group
-        int it0 = blockIdx.x, c0 = -1;
+        int it0 = unit, c0 = -1;
         if (it0 < items && next_valid(it0, c0)) {
           int col, rowc;
           coords(it0, c0, col, rowc);
@@ -486,7 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(&tmR, r_bar(ew, 0), mybuf_u32, col, rowc);
         }
       }
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      for (int it = unit; it < items; it += nunits) {
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -536,14 +592,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
       if (lane == 0) tma_store_wait_all();
     } else {
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    for (int it = unit; it < items; it += nunits) {
       int rem = it % tiles;
-      int64_t m0 = (int64_t)(rem / p.n_tiles) * BM, n0 = (int64_t)(rem % p.n_tiles) * BN;
+      int64_t m0 = (int64_t)(rem / p.n_tiles) * (BM * CG) + rank * BM, n0 = (int64_t)(rem % p.n_tiles) * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int64_t m = m0 + quad * 32 + lane;
@@ -562,16 +618,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as)); }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // nobody leaves (or frees TMEM) while the peer may still read its smem / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -607,32 +665,68 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t ou
 
 struct Maps { CUtensorMap a, b, c, r; };
 
-template <int BN, bool A_MN, bool B_MN, typename TOut>
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG>
 static int launch(const Maps& mp, const Params& p, cudaStream_t s) {
-  constexpr int STAGES = StageCfg<BN>::STAGES;
-  constexpr int smem = STAGES * StageCfg<BN>::STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 512;
+  constexpr int STAGES = StageCfg<BN, CG>::STAGES;
+  constexpr int smem = STAGES * StageCfg<BN, CG>::STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 512;
   static_assert(smem <= 227 * 1024, "GEMM smem exceeds the CTA limit");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, CG>;
   static bool configured = false;
+  static int max_units = 0;           // co-resident CTAs (CG 1) or CTA pairs (CG 2)
   if (!configured) {
     EMO_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_units = emo_num_sms() / CG;
+    if (CG == 2) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(emo_num_sms() / 2 * 2);
+      q.blockDim = dim3(NUM_THREADS);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) == cudaSuccess && nc > 0 && nc < max_units) max_units = nc;
+      (void)cudaGetLastError();
+    }
     configured = true;
   }
-  int items = p.m_tiles * p.n_tiles * p.splits;
-  int grid = items < emo_num_sms() ? items : emo_num_sms();
-  kern<<<grid, NUM_THREADS, smem, s>>>(mp.a, mp.b, mp.c, mp.r, p);
+  const int items = p.m_tiles * p.n_tiles * p.splits;
+  const int units = items < max_units ? items : max_units;
+  if (CG == 1) {
+    kern<<<units, NUM_THREADS, smem, s>>>(mp.a, mp.b, mp.c, mp.r, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(units * 2);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EMO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.c, mp.r, p));
+  }
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
 
-template <int BN, typename TOut>
+template <int BN, typename TOut, int CG>
 static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
   switch (op) {
-    case EMO_GEMM_NT: return launch<BN, false, false, TOut>(mp, p, s);
-    case EMO_GEMM_NN: return launch<BN, false, true, TOut>(mp, p, s);
-    case EMO_GEMM_TN: return launch<BN, true, true, TOut>(mp, p, s);
+    case EMO_GEMM_NT: return launch<BN, false, false, TOut, CG>(mp, p, s);
+    case EMO_GEMM_NN: return launch<BN, false, true, TOut, CG>(mp, p, s);
+    case EMO_GEMM_TN: return launch<BN, true, true, TOut, CG>(mp, p, s);
   }
   emo_set_error("emo_gemm: bad op %d", op);
+  return EMO_ERR_ARG;
+}
+
+template <int CG>
+static int launch_any(int op, int BN, int out_dtype, const Maps& mp, const Params& p, cudaStream_t s) {
+  if (out_dtype == EMO_BF16) return BN == 256 ? launch_op<256, bf16, CG>(op, mp, p, s) : launch_op<128, bf16, CG>(op, mp, p, s);
+  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float, CG>(op, mp, p, s) : launch_op<128, float, CG>(op, mp, p, s);
+  emo_set_error("emo_gemm: bad out dtype %d", out_dtype);
   return EMO_ERR_ARG;
 }
 
@@ -642,6 +736,8 @@ static int g_force_simt = 0;
 static int g_no_tma_epi = 0;
 static int g_debug = 0;
 static int g_no_skinny = 0;
+static int g_no_pair = 0;
+extern "C" void emo_gemm_single_cta(int on) { g_no_pair = on; }   // test / A-B hook: never use the CTA-pair (cta_group::2) kernel
 extern "C" void emo_gemm_no_skinny(int on) { g_no_skinny = on; }   // test hook: small-M shapes through the tensor-core kernel
 extern "C" void emo_gemm_debug(int mode) { g_debug = mode; }   // perf triage only; results are wrong when != 0
 extern "C" void emo_gemm_force_simt(int on) { g_force_simt = on; }
@@ -686,13 +782,14 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   const int BN = (N % 256 == 0 || N >= 1024) ? 256 : 128;
   Params p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.ep = ep;
-  p.m_tiles = (int)((M + BM - 1) / BM);
+  const int CG = (M > BM && !g_no_pair && !g_debug) ? 2 : 1;       // CTA pairs (256-row tiles) unless the problem is a single row block
+  p.m_tiles = (int)((M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((N + BN - 1) / BN);
   p.kb_total = (int)((K + BK - 1) / BK);
   p.splits = 1;
   if (ep.accumulate) {
     int tiles = p.m_tiles * p.n_tiles;
-    int want = (2 * emo_num_sms() + tiles - 1) / tiles;
+    int want = (2 * (emo_num_sms() / CG) + tiles - 1) / tiles;
     int maxs = p.kb_total / 8 > 0 ? p.kb_total / 8 : 1;
     p.splits = want < maxs ? want : maxs;
     if (p.splits < 1) p.splits = 1;
@@ -705,7 +802,7 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   if (op == EMO_GEMM_TN) rc = make_map(&mp.a, A, M, K, lda, 64);   // A stored [K][M]: inner = M
   else rc = make_map(&mp.a, A, K, M, lda, BM);                      // A stored [M][K]: inner = K
   if (rc) return rc;
-  if (op == EMO_GEMM_NT) rc = make_map(&mp.b, B, K, N, ldb, BN);   // B stored [N][K]
+  if (op == EMO_GEMM_NT) rc = make_map(&mp.b, B, K, N, ldb, BN / CG);   // B stored [N][K]; a pair member stages half the rows
   else rc = make_map(&mp.b, B, N, K, ldb, 64);                      // B stored [K][N]: inner = N
   if (rc) return rc;
 
@@ -734,8 +831,5 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
     return EMO_ERR_UNSUPPORTED;
   }
 
-  if (out_dtype == EMO_BF16) return BN == 256 ? launch_op<256, bf16>(op, mp, p, s) : launch_op<128, bf16>(op, mp, p, s);
-  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float>(op, mp, p, s) : launch_op<128, float>(op, mp, p, s);
-  emo_set_error("emo_gemm: bad out dtype %d", out_dtype);
-  return EMO_ERR_ARG;
+  return CG == 2 ? launch_any<2>(op, BN, out_dtype, mp, p, s) : launch_any<1>(op, BN, out_dtype, mp, p, s);
 }

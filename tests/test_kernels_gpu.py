@@ -185,6 +185,40 @@ def test_gemm_skinny_decode_rows(ops, M, N, K):
             assert rel_err(o1[:, :N].float(), o2[:, :N].float()) < (2e-5 if dt == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 2048, 512), (1000, 512, 2048), (257, 1536, 512), (129, 320, 512), (8192, 512, 512)])
+def test_gemm_cta_pair_equals_single_cta(ops, M, N, K):
+    """M > 128 runs the CTA-pair kernel (2-CTA cluster, tcgen05 cta_group::2, 256-row tiles); it must reproduce the
+    single-CTA kernel bit for bit (same K order per output) on all three contractions, ragged M / N included."""
+    from emo_disentanger_b200 import _lib
+    torch.manual_seed(M + K)
+    a, w = _bf(torch.randn(M, K, device=DEV)), _bf(torch.randn(N, K, device=DEV) * 0.05)
+    bias = torch.randn(N, device=DEV) * 0.1
+    res = _bf(torch.randn(M, N, device=DEV))
+    dy = _bf(torch.randn(M, N, device=DEV) * 0.1)
+
+    def run():
+        o = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.linear_fwd(a, w, o, bias=bias, act=ops.ACT_RELU, drop_p=0.1, seed=9, residual=res, ld_res=N)   # NT
+        of = torch.empty(M, N, device=DEV)
+        ops.linear_fwd(a, w, of, bias=bias)                                                                # NT, fp32 out
+        dx = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+        ops.linear_dgrad(dy, w, dx)                                                                        # NN
+        dw = torch.zeros(N, K, device=DEV)
+        ops.linear_wgrad(dy, a, dw)                                                                        # TN, split-K atomics
+        return o, of, dx, dw
+
+    o2, of2, dx2, dw2 = run()
+    _lib.lib().emo_gemm_single_cta(1)
+    try:
+        o1, of1, dx1, dw1 = run()
+    finally:
+        _lib.lib().emo_gemm_single_cta(0)
+    assert torch.equal(o1, o2) and torch.equal(of1, of2) and torch.equal(dx1, dx2)
+    assert rel_err(dw2, dw1) < 1e-5                      # fp32 atomics: summation order over the splits differs
+    assert rel_err(of2, a.float() @ w.float().T + bias) < 2e-5
+    assert rel_err(dw2, dy.float().T @ a.float()) < 5e-5
+
+
 @pytest.mark.parametrize("op", ["nt", "nn", "tn"])
 def test_gemm_fp32_simt(ops, op):
     torch.manual_seed(5)
