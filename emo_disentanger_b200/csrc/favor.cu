@@ -366,22 +366,23 @@ favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld
 // In-place scan over the nseg (+1) slots of every (b,h): forward -> slot s = sum of the local sums of segments < s
 // (slot nseg = total); reverse -> slot s = sum of the local sums of segments > s.  One thread per state element.
 __global__ void favor_prefix_kernel(float* __restrict__ states, int nseg, int reverse, int64_t n_bh) {
-  const int64_t per = (int64_t)FM * FV;
+  constexpr int64_t per4 = (int64_t)FM * FV / 4;          // float4 per slot
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_bh * per) return;
-  float* p = states + (i / per) * (nseg + 1) * per + (i % per);
-  float run = 0.f;
+  if (i >= n_bh * per4) return;
+  float4* p = reinterpret_cast<float4*>(states) + (i / per4) * (nseg + 1) * per4 + (i % per4);
+  float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
   if (!reverse) {
     for (int s = 0; s <= nseg; ++s) {
-      float t = (s < nseg) ? p[s * per] : 0.f;
-      p[s * per] = run;
-      run += t;
+      float4 t = (s < nseg) ? p[s * per4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      p[s * per4] = run;
+      add(run, t);
     }
   } else {
     for (int s = nseg - 1; s >= 0; --s) {
-      float t = p[s * per];
-      p[s * per] = run;
-      run += t;
+      float4 t = p[s * per4];
+      p[s * per4] = run;
+      add(run, t);
     }
   }
 }
@@ -777,7 +778,7 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
   if (seg_states) {
     favor_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)k, (const T*)v, ld, omega, seg_states, nseg, sc, T_, H);
     EMO_LAUNCH_CHECK();
-    const int64_t n = (int64_t)B * H * FM * FV;
+    const int64_t n = (int64_t)B * H * FM * FV / 4;
     favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_states, nseg, 0, (int64_t)B * H);
     EMO_LAUNCH_CHECK();
   }
@@ -805,7 +806,7 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
     favor_bwd_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)q, ld, omega, (const T*)out, (const T*)dout,
                                                                       ld_out, den, seg_rstates, nseg, sc, T_, H);
     EMO_LAUNCH_CHECK();
-    const int64_t n = (int64_t)B * H * FM * FV;
+    const int64_t n = (int64_t)B * H * FM * FV / 4;
     favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_rstates, nseg, 1, (int64_t)B * H);
     EMO_LAUNCH_CHECK();
   }

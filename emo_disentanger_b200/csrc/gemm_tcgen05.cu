@@ -51,17 +51,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  long long start = clock64();
+  uint32_t spins = 0;
   while (true) {
+    // try_wait blocks in hardware up to the suspend hint (ns): waiting warps stay out of the issue slots that the
+    // epilogue warps need (a clock64-polling loop was 10% of the kernel's executed instructions)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
-    if (clock64() - start > 8000000000LL) __trap();   // watchdog: never hang the GPU on a protocol bug
+    if (++spins > (1u << 22)) __trap();   // watchdog (seconds): never hang the GPU on a protocol bug
   }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
@@ -140,6 +142,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -179,8 +192,14 @@ struct Params {
 // Every branch below is warp-uniform and sits OUTSIDE the per-element loops.  Order of operations =
 // include/emo_b200.h (emo_epilogue): alpha, rowscale, bias, activation (aux), dropout.
 // `a` = the 32 aux values of this row chunk (acts 3, 4), already in registers.
+__device__ __forceinline__ void load_bias32(float4 (&b)[8], const float* bias, int64_t nb) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + nb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
+}
 template <int PART = 0>   // 0 = everything, 1 = linear part only (alpha, rowscale, bias), 2 = activation + dropout only
-__device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32], int64_t m, int64_t nb, const EpiParams& ep) {
+__device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32], int64_t m, int64_t nb, const EpiParams& ep,
+                                           const float4* bpre = nullptr /* bias values already in registers */) {
   if (PART != 2) {
   if (ep.alpha != 1.f) {
 #pragma unroll
@@ -195,7 +214,7 @@ __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32],
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + nb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
+      float4 b = bpre ? bpre[j] : __ldg(b4 + j);
       v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
@@ -374,7 +393,7 @@ __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t 
 // reads B from both CTAs' shared memory -- a third less L2->smem traffic and smem fill per flop than CG = 1, which
 // is what bounds the K = 512 shapes (profiles/).  Each CTA runs its own epilogue on its 128 accumulator rows.
 template <int BN, bool A_MN, bool B_MN, typename TOut, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> 168 registers / thread at most
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ Params p) {
@@ -559,9 +578,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) { r0[j] = 0x3f800000u; r1[j] = 0x3f800000u; }
           } else {
-            tmem_ld32(taddr, r0);
-            tmem_ld32(taddr + 32, r1);
+            tmem_ld32_issue(taddr, r0);
+            tmem_ld32_issue(taddr + 32, r1);
           }
+          tmem_ld_wait();
           if (p.has_r) {
             if (lane == 0) {
               tma_store_wait_read<0>();          // the store of group g-1 has drained buffer b^1
