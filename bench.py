@@ -206,7 +206,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (sequences of 2048 tokens)")
+    ap.add_argument("--batch", type=int, default=74,
+                    help="per-GPU batch (sequences of 2048 tokens); 74 = 2 per SM pair: every GEMM and FAVOR+ launch is a "
+                         "whole number of waves on 148 SMs (swept 4..74 in profiles/)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the 1-GPU autoregressive decode measurement")

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(BG_THREADS, 2)
 favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ld,
                  const float* __restrict__ omega, T* __restrict__ out, int64_t ld_out, float* __restrict__ den_out,
                  const float* __restrict__ state_in, float* __restrict__ state_out,
-                 const float* __restrict__ seg_states, int nseg, int seg_chunks, int Tlen, int H) {
+                 float* __restrict__ seg_states, int nseg, int seg_chunks, int Tlen, int H) {
   constexpr int C = FavorCfg<T>::C;
   using S = FavorSmemFwd<T, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -240,7 +240,7 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     const float* si = state_in + (int64_t)bh * FM * FV;
     gs.foreach ([&](int row, int col, float& x) { x = si[row * FV + col]; });
   }
-  if (seg_states) {          // exclusive prefix over the earlier segments (favor_segsum_kernel + favor_prefix_kernel)
+  if (seg_states && seg > 0) {   // exclusive prefix over the earlier segments (favor_segsum_kernel + favor_prefix_kernel)
     const float* si = seg_states + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
     gs.foreach ([&](int row, int col, float& x) { x += si[row * FV + col]; });
   }
@@ -310,9 +310,19 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     cp_commit();
   }
   cp_wait<0>();
-  if (state_out && seg == nseg - 1) {
-    float* so = state_out + (int64_t)bh * FM * FV;
-    gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+  if (seg == nseg - 1) {       // the last segment ends on the final prefix state
+    if (state_out) {
+      float* so = state_out + (int64_t)bh * FM * FV;
+      gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+    }
+    if (seg_states) {          // ... which is also the last slot of the workspace (what the backward starts from)
+      float* so = seg_states + ((int64_t)bh * (nseg + 1) + nseg) * FM * FV;
+      gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
+    }
+  }
+  if (seg_states && seg == 0) {  // slot 0 = the empty prefix (kept defined for readers of the workspace)
+    float* so = seg_states + (int64_t)bh * (nseg + 1) * FM * FV;
+    for (int i = threadIdx.x; i < FM * FV; i += BG_THREADS) so[i] = 0.f;
   }
 }
 
@@ -325,7 +335,9 @@ favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld
   using S = FavorSmemSeg<T, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
-  const int bh = blockIdx.x / nseg, seg = blockIdx.x % nseg;
+  // one CTA per (b, h, segment) for every segment but the last (whose sum no later segment needs): the local
+  // sum of segment s lands in slot s + 1, where the in-place scan turns it into the prefix of segment s + 1
+  const int bh = blockIdx.x / (nseg - 1), seg = blockIdx.x % (nseg - 1);
   const int b = bh / H, h = bh % H;
   const int64_t base = (int64_t)b * Tlen * ld + (int64_t)h * FE;
   load_omega<T>(omega, sm.om);
@@ -359,12 +371,12 @@ favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld
     gs.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[buf][0][0], bg_ld<T>(FV), C);
   }
   cp_wait<0>();
-  float* so = seg_states + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
+  float* so = seg_states + ((int64_t)bh * (nseg + 1) + seg + 1) * FM * FV;
   gs.foreach ([&](int row, int col, float& x) { so[row * FV + col] = x; });
 }
 
-// In-place scan over the nseg (+1) slots of every (b,h): forward -> slot s = sum of the local sums of segments < s
-// (slot nseg = total); reverse -> slot s = sum of the local sums of segments > s.  One thread per state element.
+// In-place scan over the slots of every (b,h): forward -> slot s = sum of the local sums of segments < s (slot 0 and
+// slot nseg, the total, are written by the main kernel); reverse -> slot s = sum of the local sums of segments > s.
 __global__ void favor_prefix_kernel(float* __restrict__ states, int nseg, int reverse, int64_t n_bh) {
   constexpr int64_t per4 = (int64_t)FM * FV / 4;          // float4 per slot
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,11 +384,10 @@ __global__ void favor_prefix_kernel(float* __restrict__ states, int nseg, int re
   float4* p = reinterpret_cast<float4*>(states) + (i / per4) * (nseg + 1) * per4 + (i % per4);
   float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
   auto add = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
-  if (!reverse) {
-    for (int s = 0; s <= nseg; ++s) {
-      float4 t = (s < nseg) ? p[s * per4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!reverse) {            // slots 1..nseg-1 hold the local sums of segments 0..nseg-2 -> running (inclusive) sums
+    for (int s = 1; s < nseg; ++s) {
+      add(run, p[s * per4]);
       p[s * per4] = run;
-      add(run, t);
     }
   } else {
     for (int s = nseg - 1; s >= 0; --s) {
@@ -775,12 +786,14 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
     EMO_CHECK_CUDA(cudaFuncSetAttribute(favor_segsum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FavorSmemSeg<T, C>)));
     configured = true;
   }
-  if (seg_states) {
-    favor_segsum_kernel<T><<<B * H * nseg, BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)k, (const T*)v, ld, omega, seg_states, nseg, sc, T_, H);
+  if (seg_states && nseg > 1) {
+    favor_segsum_kernel<T><<<B * H * (nseg - 1), BG_THREADS, sizeof(FavorSmemSeg<T, C>), s>>>((const T*)k, (const T*)v, ld, omega, seg_states, nseg, sc, T_, H);
     EMO_LAUNCH_CHECK();
-    const int64_t n = (int64_t)B * H * FM * FV / 4;
-    favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_states, nseg, 0, (int64_t)B * H);
-    EMO_LAUNCH_CHECK();
+    if (nseg > 2) {          // with two segments slot 1 already is the prefix of segment 1
+      const int64_t n = (int64_t)B * H * FM * FV / 4;
+      favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_states, nseg, 0, (int64_t)B * H);
+      EMO_LAUNCH_CHECK();
+    }
   }
   favor_fwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
                                                              den, state_in, state_out, seg_states, nseg, sc, T_, H);
