@@ -101,6 +101,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(kernel_substr):
+    """mean DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from the ncu
+    pass over this same command that is committed under profiles/ (profiles/r01_traffic.json, written by
+    scripts/ncu_traffic.py); None when no capture for this batch size has been committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return d
+    except Exception:
+        return None
+
+
 def make_batches(n, B, T, V, seed0, pinned):
     from oracle.cpu_train import synthetic_batch       # data generator only (shared with the CPU arm)
     out = []
@@ -123,7 +134,8 @@ def run_reference(args):
             "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, 1, "cpu host cores; one bounded sample (B=1 sequence) per step"),
+            "config": workload_config(args.batch, 1, "n/a (CPU arm: each step is a bounded sample of the workload -- ONE "
+                                      "2048-token sequence through the same train step, see cpu_baseline.sample)"),
             "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -308,6 +320,7 @@ def main():
         roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM: QKV/out/FFN/logits fwd, dgrad, wgrad)",
                 "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "launches": n,
+                "algorithmic_flops_per_launch": round(flops / max(n, 1)),
                 "avg_launch_us": round(1e3 * kms / max(n, 1), 2), "share_of_step": round(kms / (ms or 1), 4),
                 "work_per_launch": "2*M*N*K flops of each launch, summed (%.3f GFLOP/token)" % (flops / (B * T * args.steps) / 1e9),
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"}
@@ -322,6 +335,11 @@ def main():
                 "avg_launch_us": round(1e3 * kms / max(n, 1), 2), "share_of_step": round(kms / (ms or 1), 4),
                 "work_per_launch": "bf16 bytes: fwd 4*512*2 B/token/layer (q,k,v in, out), bwd 8*512*2 B/token/layer",
                 "peak_source": pk["source"]}
+
+    tr = measured_traffic("gemm_tc_kernel")
+    if tr and tr.get("per_gpu_batch") == B and dominant == "gemm":
+        roof["traffic"] = tr["gemm_mean_dram_bytes_per_launch"]
+        roof["traffic_source"] = tr.get("source")
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region -----------------------------------------
     def step_e2e(i):
