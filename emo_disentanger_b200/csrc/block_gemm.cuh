@@ -126,6 +126,66 @@ template <int M, int N> struct BlockGemm<M, N, bf16> {
     }
   }
 
+  // compile-time K: the k loop is fully unrolled, so ptxas can hoist the ldmatrix of step k+1 above the MMAs of
+  // step k (with a run-time trip count every step is load -> wait -> mma)
+  template <bool A_KMAJ, bool B_KMAJ, int K>
+  __device__ __forceinline__ void mma_k(const bf16* A, int lda, const bf16* B, int ldb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m_base = (warp / WN) * (MT * 16);
+    const int n_base = (warp % WN) * (NT * 8);
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        int m0 = m_base + mt * 16;
+        if (A_KMAJ) {
+          int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          int kk = k0 + (lane >> 4) * 8;
+          ldsm_x4(a[mt][0], a[mt][1], a[mt][2], a[mt][3], A + row * lda + kk);
+        } else {
+          int mat = lane >> 3;
+          int kk = k0 + (lane & 7) + (mat >> 1) * 8;
+          int mm = m0 + (mat & 1) * 8;
+          ldsm_x4_t(a[mt][0], a[mt][1], a[mt][2], a[mt][3], A + kk * lda + mm);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; nt += 2) {
+        uint32_t b[4];
+        int n0 = n_base + nt * 8;
+        if (nt + 1 < NT) {
+          if (B_KMAJ) {
+            int nn = n0 + (lane & 7) + (lane >> 4) * 8;
+            int kk = k0 + ((lane >> 3) & 1) * 8;
+            ldsm_x4(b[0], b[1], b[2], b[3], B + nn * ldb + kk);
+          } else {
+            int kk = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            int nn = n0 + (lane >> 4) * 8;
+            ldsm_x4_t(b[0], b[1], b[2], b[3], B + kk * ldb + nn);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16_16816(acc[mt][nt], a[mt], b[0], b[1]);
+            mma_bf16_16816(acc[mt][nt + 1], a[mt], b[2], b[3]);
+          }
+        } else {
+          int l = lane & 15;
+          if (B_KMAJ) {
+            int nn = n0 + (l & 7);
+            int kk = k0 + ((l >> 3) & 1) * 8;
+            ldsm_x2(b[0], b[1], B + nn * ldb + kk);
+          } else {
+            int kk = k0 + (l & 7) + ((l >> 3) & 1) * 8;
+            ldsm_x2_t(b[0], b[1], B + kk * ldb + n0);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) mma_bf16_16816(acc[mt][nt], a[mt], b[0], b[1]);
+        }
+      }
+    }
+  }
+
   template <typename F> __device__ __forceinline__ void foreach (F f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m_base = (warp / WN) * (MT * 16);
@@ -191,6 +251,9 @@ template <int M, int N> struct BlockGemm<M, N, float> {
         for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
   }
+
+  template <bool A_KMAJ, bool B_KMAJ, int K>
+  __device__ __forceinline__ void mma_k(const float* A, int lda, const float* B, int ldb) { mma<A_KMAJ, B_KMAJ>(A, lda, B, ldb, K); }
 
   template <typename F> __device__ __forceinline__ void foreach (F f) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;

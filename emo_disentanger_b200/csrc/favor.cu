@@ -210,7 +210,7 @@ template <typename T, int C, int LDX, int LDO, int LDP>
 __device__ __forceinline__ void phi_rows(T (*x)[LDX], T (*om)[LDO], const float* off, int valid, T (*phi)[LDP]) {
   BlockGemm<C, FE, T> g;
   g.clear();
-  g.template mma<true, false>(&x[0][0], LDX, &om[0][0], LDO, FE);
+  g.template mma_k<true, false, FE>(&x[0][0], LDX, &om[0][0], LDO);
   acc_to_smem(g, &phi[0][0], LDP, [&](int row, int col, float u) { return row < valid ? FavorMath<T>::ex(u - off[row]) : 0.f; });
   acc_to_smem(g, &phi[0][FE], LDP, [&](int row, int col, float u) { return row < valid ? FavorMath<T>::ex(-u - off[row]) : 0.f; });
 }
@@ -281,7 +281,7 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, C, T> ga;
       ga.clear();
-      ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
+      ga.template mma_k<true, true, FM>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM));
       acc_to_smem(ga, &sm.a[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
     }
     cp_wait<1>();            // v of this chunk has landed
@@ -289,8 +289,8 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FV, T> go;
       go.clear();
-      go.template mma<true, false>(&sm.a[0][0], bg_ld<T>(C), &sm.v[0][0], bg_ld<T>(FV), C);
-      go.template mma<true, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.s[0][0], bg_ld<T>(FV), FM);
+      go.template mma_k<true, false, C>(&sm.a[0][0], bg_ld<T>(C), &sm.v[0][0], bg_ld<T>(FV));
+      go.template mma_k<true, false, FM>(&sm.pq[0][0], bg_ld<T>(FM), &sm.s[0][0], bg_ld<T>(FV));
       go.foreach ([&](int row, int col, float& x) { if (col == FE) { sm.den[row] = x + F_EPS; sm.oq[row] = 1.f / (x + F_EPS); } });
       __syncthreads();     // oq (the phi(q) offsets) is dead here: it carries 1/den to the output scaling
       if constexpr (sizeof(T) == 2) {
@@ -303,7 +303,7 @@ favor_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     store_rows<T, C>(out + obase + (int64_t)t0 * ld_out, ld_out, valid, stage);
     if (den_out)
       for (int i = threadIdx.x; i < valid; i += BG_THREADS) den_out[((int64_t)b * Tlen + t0 + i) * H + h] = sm.den[i];
-    gs.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV), C);
+    gs.template mma_k<false, false, C>(&sm.pk[0][0], bg_ld<T>(FM), &sm.v[0][0], bg_ld<T>(FV));
     __syncthreads();         // every warp is done reading v and s
     acc_to_smem(gs, &sm.s[0][0], bg_ld<T>(FV), [](int, int, float x) { return x; });
     issue_rows<T, C>(v + base + (int64_t)tn * ld, ld, validn, sm.v, more);      // prefetch the next chunk's v
@@ -368,7 +368,7 @@ favor_segsum_kernel(const T* __restrict__ k, const T* __restrict__ v, int64_t ld
     __syncthreads();
     phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
     __syncthreads();
-    gs.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[buf][0][0], bg_ld<T>(FV), C);
+    gs.template mma_k<false, false, C>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[buf][0][0], bg_ld<T>(FV));
   }
   cp_wait<0>();
   float* so = seg_states + ((int64_t)bh * (nseg + 1) + seg + 1) * FM * FV;
@@ -490,7 +490,7 @@ favor_bwd_segsum_kernel(const T* __restrict__ q, int64_t ld, const float* __rest
     __syncthreads();
     phi_rows<T, C>(sm.x[buf], sm.om, sm.off, valid, sm.p);
     __syncthreads();
-    gr.template mma<false, false>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[0][0][0], bg_ld<T>(FV), C);
+    gr.template mma_k<false, false, C>(&sm.p[0][0], bg_ld<T>(FM), &sm.w[0][0][0], bg_ld<T>(FV));
   }
   cp_wait<0>();
   float* so = seg_rstates + ((int64_t)bh * (nseg + 1) + seg) * FM * FV;
@@ -580,7 +580,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {  // roll the prefix state back to the start of this chunk
       BlockGemm<FM, FV, T> tmp;
       tmp.clear();
-      tmp.template mma<false, false>(&sm.pk[0][0], bg_ld<T>(FM), &vv[0][0], bg_ld<T>(FV), C);
+      tmp.template mma_k<false, false, C>(&sm.pk[0][0], bg_ld<T>(FM), &vv[0][0], bg_ld<T>(FV));
       constexpr int NA = sizeof(gs.acc) / sizeof(float);
       float* a = reinterpret_cast<float*>(gs.acc);
       const float* t = reinterpret_cast<const float*>(tmp.acc);
@@ -591,10 +591,10 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, C, T> ga;
       ga.clear();
-      ga.template mma<true, true>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM), FM);
+      ga.template mma_k<true, true, FM>(&sm.pq[0][0], bg_ld<T>(FM), &sm.pk[0][0], bg_ld<T>(FM));
       acc_to_smem(ga, &sm.a[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
       ga.clear();
-      ga.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &vv[0][0], bg_ld<T>(FV), FV);
+      ga.template mma_k<true, true, FV>(&sm.g[0][0], bg_ld<T>(FV), &vv[0][0], bg_ld<T>(FV));
       acc_to_smem(ga, &sm.p[0][0], bg_ld<T>(C), [](int row, int col, float x) { return col <= row ? x : 0.f; });
     }
     __syncthreads();
@@ -602,8 +602,8 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FM, T> gd;
       gd.clear();
-      gd.template mma<true, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pk[0][0], bg_ld<T>(FM), C);
-      gd.template mma<true, true>(&sm.g[0][0], bg_ld<T>(FV), &sm.s[0][0], bg_ld<T>(FV), FV);
+      gd.template mma_k<true, false, C>(&sm.p[0][0], bg_ld<T>(C), &sm.pk[0][0], bg_ld<T>(FM));
+      gd.template mma_k<true, true, FV>(&sm.g[0][0], bg_ld<T>(FV), &sm.s[0][0], bg_ld<T>(FV));
       acc_to_smem(gd, &sm.w[0][0], bg_ld<T>(FM), [&](int row, int col, float x) { return x * to_f(sm.pq[row][col]); });
     }
     __syncthreads();
@@ -612,7 +612,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FE, T> gx;
       gx.clear();
-      gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      gx.template mma_k<true, true, FE>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE));
       __syncthreads();       // du is re-used as the store staging buffer
       acc_to_smem(gx, &sm.du[0][0], bg_ld<T>(FE), [&](int row, int col, float x) {
         return x * FavorMath<T>::kInv + sm.dof[row] * F_S2 * to_f(xq[row][col]);
@@ -624,8 +624,8 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FM, T> gd;
       gd.clear();
-      gd.template mma<false, false>(&sm.p[0][0], bg_ld<T>(C), &sm.pq[0][0], bg_ld<T>(FM), C);
-      gd.template mma<true, true>(&vv[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV), FV);
+      gd.template mma_k<false, false, C>(&sm.p[0][0], bg_ld<T>(C), &sm.pq[0][0], bg_ld<T>(FM));
+      gd.template mma_k<true, true, FV>(&vv[0][0], bg_ld<T>(FV), &sm.r[0][0], bg_ld<T>(FV));
       acc_to_smem(gd, &sm.w[0][0], bg_ld<T>(FM), [&](int row, int col, float x) { return x * to_f(sm.pk[row][col]); });
     }
     __syncthreads();         // also: the dq store has finished reading du
@@ -634,7 +634,7 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FE, T> gx;
       gx.clear();
-      gx.template mma<true, true>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE), FE);
+      gx.template mma_k<true, true, FE>(&sm.du[0][0], bg_ld<T>(FE), &sm.om[0][0], bg_ld<T>(FE));
       __syncthreads();
       acc_to_smem(gx, &sm.du[0][0], bg_ld<T>(FE), [&](int row, int col, float x) {
         return x * FavorMath<T>::kInv + sm.dof[row] * F_S2 * to_f(xk[row][col]);
@@ -647,14 +647,14 @@ favor_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     {
       BlockGemm<C, FV, T> gv;
       gv.clear();
-      gv.template mma<false, false>(&sm.a[0][0], bg_ld<T>(C), &sm.g[0][0], bg_ld<T>(FV), C);
-      gv.template mma<true, false>(&sm.pk[0][0], bg_ld<T>(FM), &sm.r[0][0], bg_ld<T>(FV), FM);
+      gv.template mma_k<false, false, C>(&sm.a[0][0], bg_ld<T>(C), &sm.g[0][0], bg_ld<T>(FV));
+      gv.template mma_k<true, false, FM>(&sm.pk[0][0], bg_ld<T>(FM), &sm.r[0][0], bg_ld<T>(FV));
       gv.foreach ([&](int row, int col, float& x) { if (col < FE) sm.du[row][col] = from_f<T>(x); });
     }
     __syncthreads();
     store_rows<T, C>(dv + dbase + (int64_t)t0 * ld_d, ld_d, valid, sm.du);
     // ---- reverse state ----
-    gr.template mma<false, false>(&sm.pq[0][0], bg_ld<T>(FM), &sm.g[0][0], bg_ld<T>(FV), C);
+    gr.template mma_k<false, false, C>(&sm.pq[0][0], bg_ld<T>(FM), &sm.g[0][0], bg_ld<T>(FV));
     __syncthreads();         // every warp is done with r (dk, dv) and with du (dv store)
     acc_to_smem(gr, &sm.r[0][0], bg_ld<T>(FV), [](int, int, float x) { return x; });
   }
