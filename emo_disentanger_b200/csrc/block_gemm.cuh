@@ -1,7 +1,7 @@
 // Block-level small-GEMM helper over shared-memory operands, used by the attention-type kernels
 // (FAVOR+ chunked scan, causal softmax attention, rel-pos attention).
 //
-//   C[M x N] += A[M x K] . B[K x N]         256 threads (8 warps) cooperate on one product.
+//   C[M x N] += A[M x K] . B[K x N]         BG_WARPS warps (8 by default, 16 on request) cooperate on one product.
 //
 // Storage flags describe how an operand sits in shared memory:
 //   A_KMAJ = true : A stored [M][K] (K contiguous);  false: stored [K][M] (M contiguous)
@@ -16,7 +16,10 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int BG_THREADS = 256;
+#ifndef BG_WARPS
+#define BG_WARPS 8       // warps per CTA cooperating on one product (a translation unit may set 16 before including)
+#endif
+constexpr int BG_THREADS = 32 * BG_WARPS;
 
 template <typename T> struct BGPad;
 template <> struct BGPad<bf16> { static constexpr int PAD = 8; };
@@ -53,8 +56,8 @@ template <int M, int N, typename T> struct BlockGemm;
 // ---------------------------------------------------------------------------------------------
 template <int M, int N> struct BlockGemm<M, N, bf16> {
   static_assert(M % 16 == 0 && N % 8 == 0, "tile shape");
-  static constexpr int WM = (M >= 128) ? 8 : (M >= 64 ? 4 : (M >= 32 ? 2 : 1));
-  static constexpr int WN = 8 / WM;
+  static constexpr int WM = (M >= 128) ? 8 : (M >= 64 ? 4 : ((M >= 32 || BG_WARPS > 8) ? 2 : 1));
+  static constexpr int WN = BG_WARPS / WM;
   static_assert(M % (16 * WM) == 0 && N % (8 * WN) == 0, "warp split");
   static constexpr int MT = M / WM / 16;
   static constexpr int NT = N / WN / 8;
@@ -224,6 +227,7 @@ template <int M, int N> struct BlockGemm<M, N, bf16> {
 // ---------------------------------------------------------------------------------------------
 template <int M, int N> struct BlockGemm<M, N, float> {
   static_assert(M % 16 == 0 && N % 16 == 0, "tile shape");
+  static_assert(BG_WARPS == 8 || M < 0, "the fp32 SIMT implementation is a 16 x 16 thread grid");
   static constexpr int MT = M / 16;
   static constexpr int NT = N / 16;
   float acc[MT][NT];

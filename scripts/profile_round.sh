@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round profile pass (run on the GPU box through gpurun): launch list of the bench command with per-launch DRAM
+# bytes, and one `ncu --set full` capture of each hot kernel.  Outputs land in gpurun_out/ and are summarised into
+# profiles/ by scripts/ncu_traffic.py / scripts/ncu_summary.py.  Numbers printed under ncu are never bench values.
+set -u
+TAG=${1:-r01}
+mkdir -p gpurun_out
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -c 1400 --csv --log-file gpurun_out/${TAG}_launches_all.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-decode \
+  > gpurun_out/${TAG}_ncu_bench.log 2>&1
+# keep the last ~300 launches (one full step) to stay small
+python - <<PY
+import csv
+rows = list(csv.reader(open("gpurun_out/${TAG}_launches_all.csv")))
+hdr = [r for r in rows if r and r[0] == "ID"]
+body = [r for r in rows if len(r) > 10 and r[0].isdigit()]
+ids = sorted({int(r[0]) for r in body})
+keep = set(ids[-300:])
+w = csv.writer(open("gpurun_out/${TAG}_launches_bench.csv", "w"))
+w.writerow(hdr[0])
+for r in body:
+    if int(r[0]) in keep: w.writerow(r)
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o gpurun_out/${TAG}_gemm python scripts/gemm_shapes.py > /dev/null 2>&1
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+ls -la gpurun_out/${TAG}_*
