@@ -132,6 +132,26 @@ __device__ __forceinline__ float gelu_new_grad_f(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * dt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (decode step): a kernel launched with the attribute may start while its
+// predecessor drains; it must not touch the predecessor's outputs before pdl_wait().  Both instructions are
+// no-ops for a normally launched kernel.  emo_set_pdl(1) switches the decode-step kernels to these launches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int emo_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t emo_launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = emo_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int emo_num_sms() {
   static int n = 0;
   if (n == 0) {

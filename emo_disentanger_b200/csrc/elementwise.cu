@@ -90,26 +90,38 @@ template <typename T>
 __global__ void embed_rows_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ seg,
                                   const int64_t* __restrict__ pos, const float* __restrict__ e_tok,
                                   const float* __restrict__ e_seg, const float* __restrict__ pe,
-                                  T* __restrict__ out, int rows, int d, float scale) {
+                                  T* __restrict__ out, int rows, int d, float scale, int64_t* __restrict__ pos_advance) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x;
   if (row >= rows) return;
   const float* e = e_tok + tok[row] * d;
   const float* s = (seg && e_seg) ? e_seg + seg[row] * d : nullptr;
-  const float* p = (pos && pe) ? pe + pos[row] * d : nullptr;
+  const int64_t pr = pos ? pos[row] : 0;
+  const float* p = (pos && pe) ? pe + pr * d : nullptr;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float v = e[c] * scale;
     if (s) v += s[c] * scale;
     if (p) v += p[c];
     out[(int64_t)row * d + c] = from_f<T>(v);
   }
+  if (pos_advance) {          // the sequence moves on by one position (every thread has read pos[row] by now)
+    __syncthreads();
+    if (threadIdx.x == 0) pos_advance[row] = pr + 1;
+  }
 }
+static int g_emo_pdl = 0;
+int emo_pdl_enabled() { return g_emo_pdl; }
+extern "C" void emo_set_pdl(int on) { g_emo_pdl = on; }
 extern "C" int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, const float* e_tok,
                               const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
-                              int out_dtype, void* stream) {
+                              int64_t* pos_advance, int out_dtype, void* stream) {
   if (rows == 0) return EMO_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (out_dtype == EMO_BF16) embed_rows_kernel<bf16><<<rows, 128, 0, s>>>(tok, seg, pos, e_tok, e_seg, pe, (bf16*)out, rows, d, scale);
-  else embed_rows_kernel<float><<<rows, 128, 0, s>>>(tok, seg, pos, e_tok, e_seg, pe, (float*)out, rows, d, scale);
+  if (out_dtype == EMO_BF16)
+    EMO_CHECK_CUDA(emo_launch_dep(embed_rows_kernel<bf16>, dim3(rows), dim3(128), 0, s, tok, seg, pos, e_tok, e_seg, pe, (bf16*)out, rows, d, scale, pos_advance));
+  else
+    EMO_CHECK_CUDA(emo_launch_dep(embed_rows_kernel<float>, dim3(rows), dim3(128), 0, s, tok, seg, pos, e_tok, e_seg, pe, (float*)out, rows, d, scale, pos_advance));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -154,9 +154,11 @@ extern "C" int emo_favor_step(const void* q, const void* k, const void* v, int64
   if (B * H == 0) return EMO_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == EMO_BF16)
-    favor_step_kernel<bf16><<<B * H, 256, 0, s>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, ld_qkv, omega, state, (bf16*)out, ld_out, H);
+    EMO_CHECK_CUDA(emo_launch_dep(favor_step_kernel<bf16>, dim3(B * H), dim3(256), 0, s, (const bf16*)q, (const bf16*)k, (const bf16*)v,
+                                  ld_qkv, omega, state, (bf16*)out, ld_out, H));
   else
-    favor_step_kernel<float><<<B * H, 256, 0, s>>>((const float*)q, (const float*)k, (const float*)v, ld_qkv, omega, state, (float*)out, ld_out, H);
+    EMO_CHECK_CUDA(emo_launch_dep(favor_step_kernel<float>, dim3(B * H), dim3(256), 0, s, (const float*)q, (const float*)k,
+                                  (const float*)v, ld_qkv, omega, state, (float*)out, ld_out, H));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -674,8 +674,30 @@ __global__ void __launch_bounds__(256) favor_step_kernel(const T* __restrict__ q
   __shared__ float xq[FE], xk[FE], pq[FM], pk[FM];
   __shared__ __align__(16) float vv[FS_CG * 4];
   __shared__ float red[FS_RL][FS_CG * 4];
+  __shared__ __align__(16) float om_s[FE * FE];
   const int b = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x;
   const float s = 0.35355339059327373f;
+  {  // Omega (constant) -> shared memory with one batch of coalesced 16-byte loads (a 64-step chain of strided global
+     // loads per feature was most of this kernel's 8 us)
+    float4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(omega) + tid + 256 * u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(om_s)[tid + 256 * u] = t[u];
+  }
+  pdl_trigger();
+  pdl_wait();
+  // the state rows of this thread: all 9 loads in flight now, consumed after the feature map is ready
+  constexpr int NR = (FM + FS_RL - 1) / FS_RL;
+  float4 st[NR];
+  if (tid < FS_CG * FS_RL) {
+    const float* sb0 = state + (int64_t)blockIdx.x * FM * FV + (tid % FS_CG) * 4;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int f = tid / FS_CG + i * FS_RL;
+      if (f < FM) st[i] = *reinterpret_cast<const float4*>(sb0 + f * FV);
+    }
+  }
   if (tid < FE) {
     xq[tid] = to_f(q[(int64_t)b * ld + h * FE + tid]) * s;
     xk[tid] = to_f(k[(int64_t)b * ld + h * FE + tid]) * s;
@@ -689,7 +711,7 @@ __global__ void __launch_bounds__(256) favor_step_kernel(const T* __restrict__ q
     int f = tid & (FE - 1);
     float u = 0.f, n2 = 0.f;
 #pragma unroll 8
-    for (int e = 0; e < FE; ++e) { u = fmaf(x[e], omega[e * FE + f], u); n2 = fmaf(x[e], x[e], n2); }
+    for (int e = 0; e < FE; ++e) { u = fmaf(x[e], om_s[e * FE + f], u); n2 = fmaf(x[e], x[e], n2); }
     float o = 0.5f * n2 + F_HALF_LOG_M;
     float* p = (tid < FE) ? pq : pk;
     p[f] = expf(u - o);
@@ -701,10 +723,12 @@ __global__ void __launch_bounds__(256) favor_step_kernel(const T* __restrict__ q
     const float4 v4 = *reinterpret_cast<const float4*>(&vv[cg * 4]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float* sbase = state + (int64_t)blockIdx.x * FM * FV + cg * 4;
-#pragma unroll 3
-    for (int f = rl; f < FM; f += FS_RL) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int f = rl + i * FS_RL;
+      if (f >= FM) break;
       float4* sp = reinterpret_cast<float4*>(sbase + f * FV);
-      float4 sv = *sp;
+      float4 sv = st[i];
       const float a = pk[f], c = pq[f];
       sv.x = fmaf(a, v4.x, sv.x); sv.y = fmaf(a, v4.y, sv.y); sv.z = fmaf(a, v4.z, sv.z); sv.w = fmaf(a, v4.w, sv.w);
       *sp = sv;

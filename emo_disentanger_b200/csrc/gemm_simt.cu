@@ -137,6 +137,25 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, in
     int c = lane + 32 * u;
     bw0[u] = (c < kv) ? __ldg(reinterpret_cast<const uint4*>(brow) + c) : make_uint4(0, 0, 0, 0);
   }
+  // constants of the epilogue / prologue ride with the weight prefetch: every dependent global round trip that
+  // can be taken off the critical path of these ~4 us kernels counts
+  const float bias_n = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.f;
+  float4 lg[4], lb[4];
+  if (ep.ln_gamma) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = (lane + 32 * h) * 8;
+      lg[2 * h] = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + c0));
+      lg[2 * h + 1] = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + c0 + 4));
+      lb[2 * h] = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + c0));
+      lb[2 * h + 1] = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + c0 + 4));
+    }
+  }
+  pdl_trigger();
+  pdl_wait();              // everything below reads what the previous kernel of the step wrote
+  // residual element of (row = lane, column n): in flight together with the activation rows
+  float res_mn = 0.f;
+  if (ep.residual && lane < M && n < N) res_mn = to_f(reinterpret_cast<const TOut*>(ep.residual)[(int64_t)lane * ep.ld_res + n]);
   for (int i0 = threadIdx.x; i0 < M * kv; i0 += SK_WARPS * 32 * 4) {      // 4 activation vectors in flight per thread
     uint4 t[4];
 #pragma unroll
@@ -176,8 +195,10 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, in
       for (int h = 0; h < 2; ++h) {
         const int c0 = (lane + 32 * h) * 8;
         float y[8];
+        const float gq[8] = {lg[2 * h].x, lg[2 * h].y, lg[2 * h].z, lg[2 * h].w, lg[2 * h + 1].x, lg[2 * h + 1].y, lg[2 * h + 1].z, lg[2 * h + 1].w};
+        const float bq[8] = {lb[2 * h].x, lb[2 * h].y, lb[2 * h].z, lb[2 * h].w, lb[2 * h + 1].x, lb[2 * h + 1].y, lb[2 * h + 1].z, lb[2 * h + 1].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (x[8 * h + j] - mu) * rs * ep.ln_gamma[c0 + j] + ep.ln_beta[c0 + j];
+        for (int j = 0; j < 8; ++j) y[j] = (x[8 * h + j] - mu) * rs * gq[j] + bq[j];
         uint4 t;
         t.x = pack_bf16x2(y[0], y[1]); t.y = pack_bf16x2(y[2], y[3]); t.z = pack_bf16x2(y[4], y[5]); t.w = pack_bf16x2(y[6], y[7]);
         row[lane + 32 * h] = t;
@@ -225,7 +246,17 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_nt_kernel(int M, in
   // lane m finishes row m (epilogue reads bias / residual / aux for one element)
 #pragma unroll
   for (int m = 0; m < SK_MAXM; ++m) {
-    if (m < M && lane == m) C[(int64_t)m * ldc + n] = from_f<TOut>(epi_full<bf16, TOut>(acc[m], m, n, ep));
+    if (m < M && lane == m) {
+      EpiParams e2 = ep;                 // bias and residual were fetched up front
+      e2.bias = nullptr;
+      e2.residual = nullptr;
+      float v = acc[m] * ep.alpha;
+      if (ep.rowscale) v *= ep.rowscale[m];
+      e2.alpha = 1.f;
+      e2.rowscale = nullptr;
+      v = epi_full<bf16, TOut>(v + bias_n, m, n, e2) + res_mn;
+      C[(int64_t)m * ldc + n] = from_f<TOut>(v);
+    }
   }
 }
 
@@ -234,9 +265,11 @@ int emo_gemm_skinny_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t l
   const size_t smem = (size_t)M * K * sizeof(bf16);
   const unsigned grid = (unsigned)((N + SK_WARPS - 1) / SK_WARPS);
   if (out_dtype == EMO_BF16)
-    gemm_skinny_nt_kernel<bf16><<<grid, SK_WARPS * 32, smem, s>>>((int)M, N, (int)K, (const bf16*)A, lda, (const bf16*)B, ldb, (bf16*)C, ldc, ep);
+    EMO_CHECK_CUDA(emo_launch_dep(gemm_skinny_nt_kernel<bf16>, dim3(grid), dim3(SK_WARPS * 32), smem, s, (int)M, N, (int)K,
+                                  (const bf16*)A, lda, (const bf16*)B, ldb, (bf16*)C, ldc, ep));
   else
-    gemm_skinny_nt_kernel<float><<<grid, SK_WARPS * 32, smem, s>>>((int)M, N, (int)K, (const bf16*)A, lda, (const bf16*)B, ldb, (float*)C, ldc, ep);
+    EMO_CHECK_CUDA(emo_launch_dep(gemm_skinny_nt_kernel<float>, dim3(grid), dim3(SK_WARPS * 32), smem, s, (int)M, N, (int)K,
+                                  (const bf16*)A, lda, (const bf16*)B, ldb, (float*)C, ldc, ep));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

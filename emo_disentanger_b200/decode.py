@@ -26,7 +26,7 @@ E = 64
 
 
 class Stage2Decoder:
-    def __init__(self, model, batch=1, max_len=2048, omegas=None, use_graph=True):
+    def __init__(self, model, batch=1, max_len=2048, omegas=None, use_graph=True, use_pdl=True):
         if model.training:
             raise RuntimeError("decode needs model.eval() (dropout off)")
         self.m = model
@@ -57,6 +57,7 @@ class Stage2Decoder:
         # static step buffers (graph inputs / outputs)
         self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and self.is_performer
+        self.use_pdl = bool(use_pdl)      # step kernels overlap their prologue with the predecessor's tail (graph only)
         self.graph = None
         # pinned staging ring for the step inputs (tokens | segments): a slot is rewritten only after the
         # async H2D copy that read it has completed
@@ -190,14 +191,16 @@ class Stage2Decoder:
         ops.embed_rows(self.tok_in, self.seg_in if m.use_segment_emb else None, self.pos if m.use_pe else None,
                        m._wv(m._flat, "token_emb.emb_lookup.weight"),
                        m._wv(m._flat, "segemb.emb_lookup.weight") if m.use_segment_emb else None,
-                       m.pe.pe if m.use_pe else None, h, d ** 0.5)
+                       m.pe.pe if m.use_pe else None, h, d ** 0.5,
+                       advance_pos=self.pos if m.use_pe else None)          # pos += 1 inside the kernel
 
         def favor(l, qkv, att):
             q, k, v = (qkv[:, i * d:(i + 1) * d].unflatten(-1, (H, E)) for i in range(3))
             ops.favor_step(q, k, v, self.omegas[l], self.state[l], att)
         hid, norm = self._performer_rows(h, B, 1, favor)
         self._logits_into(hid, self.logits, norm)
-        self.pos.add_(1)
+        if not m.use_pe:
+            self.pos.add_(1)
 
     @torch.no_grad()
     def step(self, tokens, segs):
@@ -243,8 +246,13 @@ class Stage2Decoder:
                 self._performer_step_body()
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._performer_step_body()
+        from . import _lib
+        _lib.lib().emo_set_pdl(1 if self.use_pdl else 0)    # programmatic dependent launches inside the step graph
+        try:
+            with torch.cuda.graph(g):
+                self._performer_step_body()
+        finally:
+            _lib.lib().emo_set_pdl(0)
         self.state.copy_(state0)                      # undo the warm-up / capture-time state advance
         self.pos.copy_(pos0)
         self.graph = g

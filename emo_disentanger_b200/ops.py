@@ -92,10 +92,11 @@ def embed_fwd(tok, seg, e_tok, e_seg, pe, out, scale, drop_p=0.0, seed=0, batch_
     return out
 
 
-def embed_rows(tok, seg, pos, e_tok, e_seg, pe, out, scale):
-    """decode: tok/seg/pos int64 [rows] on the device; out [rows, d]."""
+def embed_rows(tok, seg, pos, e_tok, e_seg, pe, out, scale, advance_pos=None):
+    """decode: tok/seg/pos int64 [rows] on the device; out [rows, d]; advance_pos (int64 [rows], may be `pos`)
+    receives pos + 1."""
     _call("emo_embed_rows", _p(tok), _p(seg), _p(pos), _p(e_tok), _p(e_seg), _p(pe), _p(out), tok.shape[0],
-          e_tok.shape[1], float(scale), _dt(out), _stream())
+          e_tok.shape[1], float(scale), _p(advance_pos), _dt(out), _stream())
     return out
 
 

@@ -45,7 +45,13 @@ int emo_embed_fwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int6
  * pe[pos[b]], with tok / seg / pos read from DEVICE memory (ragged batch, CUDA-graph capturable). */
 int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, const float* e_tok,
                    const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
+                   int64_t* pos_advance /* NULL, or where pos[row] + 1 is written (may be pos) */,
                    int out_dtype, void* stream);
+/* 1: the decode-step kernels (emo_embed_rows, the M <= 8 path of emo_gemm, emo_favor_step) are launched as
+ * programmatic dependent launches -- each may start while its predecessor on the stream drains (its weight
+ * prefetch overlaps the predecessor's tail) and waits (griddepcontrol.wait) before touching its inputs.  Meant
+ * to be switched on around the capture of the per-token CUDA graph; 0 (default) = ordinary launches. */
+void emo_set_pdl(int on);
 /* d_e_tok[tok] += dout*scale*mask (fp32 atomics); rows == pad_idx get no gradient (pass -1 for
  * none: nn.Embedding(padding_idx) in stage1 transformer_helpers.py:104-108). */
 int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,

@@ -20,7 +20,7 @@ for kind in sys.argv[1:] or ["performer", "gpt2"]:
             m = MusicGPT2(V, 12, 8, 512, 2048, 512, use_segment_emb=True, n_segment_types=2)
     m = m.cuda().eval()
     for B in (1, 4):
-        dec = Stage2Decoder(m, batch=B, max_len=2048)
+        dec = Stage2Decoder(m, batch=B, max_len=2048, use_pdl=bool(int(os.environ.get("PDL", "0"))))
         smp = DeviceSampler(dec.dev, rows=B)
         for b in range(B):
             dec.append(b, list(range(3, 40)), [0] * 37)
