@@ -12,7 +12,13 @@ for r in rows:
     d[r[-3]] = float(r[-1]) * U.get(r[-2], 1)
 L = list(by.values())
 ad = [i for i, d in enumerate(L) if d["name"].startswith("adam")]
-step = L[ad[-2] + 1: ad[-1] + 1] if len(ad) >= 2 else L          # the last complete step
+if len(ad) >= 2:
+    step = L[ad[-2] + 1: ad[-1] + 1]                               # the last complete step
+elif ad:                                                           # trimmed list: the step opens with the Omega draw (randn)
+    st = [i for i, d in enumerate(L[:ad[-1]]) if "distribution_elementwise" in d["name"]]
+    step = L[(st[-1] if st else 0): ad[-1] + 1]
+else:
+    step = L
 agg = collections.OrderedDict()
 for d in step:
     a = agg.setdefault(d["name"], [0, 0.0, 0.0])

@@ -8,20 +8,27 @@ mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   -c 1400 --csv --log-file gpurun_out/${TAG}_launches_all.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-decode \
   > gpurun_out/${TAG}_ncu_bench.log 2>&1
-# keep the last ~300 launches (one full step) to stay small
+# keep the last two complete steps (adam kernel = end of a step) to stay small
 python - <<PY
 import csv
 rows = list(csv.reader(open("gpurun_out/${TAG}_launches_all.csv")))
 hdr = [r for r in rows if r and r[0] == "ID"]
 body = [r for r in rows if len(r) > 10 and r[0].isdigit()]
-ids = sorted({int(r[0]) for r in body})
-keep = set(ids[-300:])
+adam = sorted({int(r[0]) for r in body if "adam_kernel" in r[4]})
+lo, hi = (adam[-3] + 1, adam[-1]) if len(adam) >= 3 else (0, 10 ** 9)
 w = csv.writer(open("gpurun_out/${TAG}_launches_bench.csv", "w"))
 w.writerow(hdr[0])
 for r in body:
-    if int(r[0]) in keep: w.writerow(r)
+    if lo <= int(r[0]) <= hi: w.writerow(r)
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o gpurun_out/${TAG}_gemm python scripts/gemm_shapes.py > /dev/null 2>&1
+# ncu --set full of every GEMM shape of a layer (12 launches): the raw metric page goes to CSV on the box and the
+# (large) report is dropped -- gpurun brings back at most 64 MiB; one single-kernel report with source is kept
+timeout 900 ncu --set full --clock-control none -k regex:gemm_tc -c 12 -o gpurun_out/${TAG}_gemm_all python scripts/gemm_shapes.py > /dev/null 2>&1
+ncu -i gpurun_out/${TAG}_gemm_all.ncu-rep --page raw --csv > gpurun_out/${TAG}_gemm_shapes_raw.csv 2>/dev/null
+rm -f gpurun_out/${TAG}_gemm_all.ncu-rep
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -s 2 -o gpurun_out/${TAG}_gemm_ffn1 python scripts/gemm_shapes.py > /dev/null 2>&1
 B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
 B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+rm -f gpurun_out/${TAG}_launches_all.csv
+du -sh gpurun_out
 ls -la gpurun_out/${TAG}_*
