@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      int64_t rows, float eps) {
-  // persistent warps: gamma / beta stay in registers, each warp streams rows with the NEXT row's loads
-  // already in flight while the current one is reduced (memory-bound: 2 x 1 KiB per row at bf16)
+  // persistent warps: gamma / beta stay in registers; each warp streams rows with the loads of the next DEPTH rows
+  // already in flight, kept as packed 16-byte vectors (memory-bound: 2 x 1 KiB per row at bf16 -- bytes in flight
+  // per SM, not arithmetic, set the achieved bandwidth)
   using R = RowRegs<T>;
   constexpr int E = R::NV * R::N;
+  constexpr int DEPTH = 3;
   const int lane = threadIdx.x & 31;
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -246,29 +248,46 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
       g_[j * R::N + i] = g4.x; g_[j * R::N + i + 1] = g4.y; g_[j * R::N + i + 2] = g4.z; g_[j * R::N + i + 3] = g4.w;
       b_[j * R::N + i] = b4.x; b_[j * R::N + i + 1] = b4.y; b_[j * R::N + i + 2] = b4.z; b_[j * R::N + i + 3] = b4.w;
     }
-  R r, nxt;
-  r.load(x + row * LN_D, lane);
+  uint4 q[DEPTH][R::NV];                  // ring of raw rows: q[k] = row + k * wstride
+  auto fetch = [&](uint4 (&dst)[R::NV], int64_t r) {
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < R::NV; ++j) dst[j] = *reinterpret_cast<const uint4*>(x + r * LN_D + R::col(j, lane));
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) fetch(q[k], row + k * wstride);
   for (; row < rows; row += wstride) {
-    const bool more = row + wstride < rows;
-    if (more) nxt.load(x + (row + wstride) * LN_D, lane);
+    R r;
+#pragma unroll
+    for (int j = 0; j < R::NV; ++j) {
+      if constexpr (sizeof(T) == 2) {
+        unpack_bf16x2(q[0][j].x, r.v[j * 8], r.v[j * 8 + 1]); unpack_bf16x2(q[0][j].y, r.v[j * 8 + 2], r.v[j * 8 + 3]);
+        unpack_bf16x2(q[0][j].z, r.v[j * 8 + 4], r.v[j * 8 + 5]); unpack_bf16x2(q[0][j].w, r.v[j * 8 + 6], r.v[j * 8 + 7]);
+      } else {
+        r.v[j * 4] = __uint_as_float(q[0][j].x); r.v[j * 4 + 1] = __uint_as_float(q[0][j].y);
+        r.v[j * 4 + 2] = __uint_as_float(q[0][j].z); r.v[j * 4 + 3] = __uint_as_float(q[0][j].w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k + 1 < DEPTH; ++k)
+#pragma unroll
+      for (int j = 0; j < R::NV; ++j) q[k][j] = q[k + 1][j];
+    fetch(q[DEPTH - 1], row + DEPTH * wstride);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < E; ++i) s += r.v[i];
     float mu = warp_sum(s) * (1.f / LN_D);
-    float q = 0.f;
+    float qq = 0.f;
 #pragma unroll
-    for (int i = 0; i < E; ++i) { float dlt = r.v[i] - mu; q += dlt * dlt; }
-    float rs = rsqrtf(warp_sum(q) * (1.f / LN_D) + eps);
+    for (int i = 0; i < E; ++i) { float dlt = r.v[i] - mu; qq += dlt * dlt; }
+    float rs = rsqrtf(warp_sum(qq) * (1.f / LN_D) + eps);
 #pragma unroll
     for (int i = 0; i < E; ++i) r.v[i] = (r.v[i] - mu) * rs * g_[i] + b_[i];
     r.store(y + row * LN_D, lane);
     if (lane == 0) {
       if (mean) mean[row] = mu;
       if (rstd) rstd[row] = rs;
-    }
-    if (more) {
-#pragma unroll
-      for (int i = 0; i < E; ++i) r.v[i] = nxt.v[i];
     }
   }
 }
