@@ -236,14 +236,17 @@ __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32],
   if (ep.drop_thr) {
     const uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
     if ((e0 & 1) == 0 && ((e0 >> 33) == ((e0 + 31) >> 33))) {
-      // same value as emo_drop_hash(seed, e0 + j): the high half of the pair index is constant here
-      const uint32_t base = (uint32_t)ep.seed ^ emo_mix32((uint32_t)(e0 >> 33) + (uint32_t)(ep.seed >> 32) + 0x7f4a7c15u);
+      // same value as emo_drop_hash(seed, e0 + j): the high half of the pair index is constant here, so the key
+      // is hoisted; lane tests are done on the whole word (h >= thr << 16  <=>  (h >> 16) >= thr, and the low
+      // lane after a 16-bit shift) -- no field extraction
+      const uint32_t key = emo_drop_key(ep.seed, (uint32_t)(e0 >> 33));
       const uint32_t lo0 = (uint32_t)(e0 >> 1);
+      const uint32_t thr_hi = ep.drop_thr << 16;
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        uint32_t h = emo_mix32(((lo0 + (j >> 1)) * 0x9E3779B9u) ^ base);
-        v[j] = ((h & 0xffffu) >= ep.drop_thr) ? v[j] * ep.keep_scale : 0.f;
-        v[j + 1] = ((h >> 16) >= ep.drop_thr) ? v[j + 1] * ep.keep_scale : 0.f;
+        const uint32_t h = emo_drop_mix(lo0 + (j >> 1), key);
+        v[j] = ((h << 16) >= thr_hi) ? v[j] * ep.keep_scale : 0.f;
+        v[j + 1] = (h >= thr_hi) ? v[j + 1] * ep.keep_scale : 0.f;
       }
     } else {
 #pragma unroll
