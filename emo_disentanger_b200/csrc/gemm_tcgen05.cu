@@ -255,20 +255,23 @@ __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32],
   }
 }
 
-// column sums of a 32(rows = lanes) x 32(columns = v[]) block: butterfly transpose-reduce, lane l ends
-// with the sum of column l; one coalesced fp32 red per warp (bias gradient fused into the dgrad GEMM)
-__device__ __forceinline__ void epi_colsum32(float (&v)[32], int lane, float* dst) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      float send = up ? v[j] : v[j + s];
-      float keep = up ? v[j + s] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
+// column sums (bias gradient) of the 32-row x 64-column bf16 block a warp has just staged for its TMA store: lane l
+// walks the rows of column pair (2l, 2l+1) in the swizzled buffer (one conflict-free 4-byte read per row -- a third
+// fewer instructions than a register butterfly) and issues two fp32 reds.  Sums exactly the values stored to C.
+__device__ __forceinline__ void epi_colsum_staged(uint32_t buf, int lane, int nvalid, float* dst) {
+  float s0 = 0.f, s1 = 0.f;
+  const uint32_t chunk = (uint32_t)lane >> 2, word = ((uint32_t)lane & 3u) << 2;
+#pragma unroll 8
+  for (int r = 0; r < nvalid; ++r) {
+    uint32_t w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(buf + r * 128 + ((chunk ^ (r & 7)) << 4) + word) : "memory");
+    float lo, hi;
+    unpack_bf16x2(w, lo, hi);
+    s0 += lo;
+    s1 += hi;
   }
-  atomicAdd(dst + lane, v[0]);
+  atomicAdd(dst + 2 * lane, s0);
+  atomicAdd(dst + 2 * lane + 1, s1);
 }
 
 // direct path (fp32 outputs, split-K accumulate, gelu aux_out): row-per-lane 16-byte global accesses
@@ -368,13 +371,6 @@ __device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t b
     t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
     t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
     if (!(p.debug & 64)) sts128(rowp + (((half * 4 + c) ^ sw) << 4), t);
-  }
-  if (ep.colsum) {
-    if (!row_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    }
-    epi_colsum32(v, row, ep.colsum + nb);
   }
 }
 
@@ -610,6 +606,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (!(p.debug & 16)) fence_proxy_async();
           __syncwarp();
+          if (ep.colsum) {
+            int64_t left = p.M - rowc;
+            epi_colsum_staged(buf, lane, left >= 32 ? 32 : (left > 0 ? (int)left : 0), ep.colsum + col);
+          }
           if (lane == 0 && !(p.debug & 8)) tma_store_2d(&tmC, mybuf_u32 + b * EPI_BUF_BYTES, col, rowc);
           ++g;
         }

@@ -148,7 +148,8 @@ def test_gemm_tma_store_epilogue_equals_direct_epilogue(ops, M, N, K):
     ops.linear_fwd(a, w, out, act=ops.ACT_RELU_MASK_BWD, aux=h, ld_aux=N, aux_scale=1.25, colsum_out=cs)
     ref = (a.float() @ w.float().T) * (h.float() != 0) * 1.25
     assert rms_rel(out.float(), ref) < 6e-3
-    assert rel_err(cs, 1.0 + ref.sum(0)) < 2e-3
+    assert rel_err(cs, 1.0 + out.float().sum(0)) < 1e-4        # sums exactly the (bf16) values it stored
+    assert rel_err(cs, 1.0 + ref.sum(0)) < 5e-3
     # same API on the fp32 path falls back to a separate column-sum launch
     cs32 = torch.zeros(N, device=DEV)
     o32 = torch.empty(M, N, device=DEV)
