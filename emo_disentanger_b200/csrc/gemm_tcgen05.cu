@@ -391,7 +391,9 @@ __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t 
 // each CTA stages its own 128 A rows and HALF of the B tile, the leader's single MMA drives both tensor cores and
 // reads B from both CTAs' shared memory -- a third less L2->smem traffic and smem fill per flop than CG = 1, which
 // is what bounds the K = 512 shapes (profiles/).  Each CTA runs its own epilogue on its 128 accumulator rows.
-template <int BN, bool A_MN, bool B_MN, typename TOut, int CG>
+// TMA_EPI selects the epilogue at compile time (smem-staged TMA store vs direct stores): the two paths have very
+// different register needs, and one kernel carrying both spilled in the hot loop.
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> 168 registers / thread at most
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -527,7 +529,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         (ep.aux == nullptr || (((ep.ld_aux % 8) == 0) && al16(ep.aux))) &&
                         (ep.aux_out == nullptr || (((ep.ld_aux % VEC) == 0) && al16(ep.aux_out)));
     constexpr int CH_PER_WARP = BN / 64;
-    if (p.tma_epi) {
+    if constexpr (TMA_EPI) {
       // ---- smem-staged path: this warp owns rows quad*32.. of the tile and the 64-column groups
       //      [half*BN/2, (half+1)*BN/2); group g of the warp's sequence uses staging buffer g & 1 ----
       constexpr int GROUPS = BN / 128;           // 64-column groups per warp per tile
@@ -688,12 +690,12 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t ou
 
 struct Maps { CUtensorMap a, b, c, r; };
 
-template <int BN, bool A_MN, bool B_MN, typename TOut, int CG>
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI>
 static int launch(const Maps& mp, const Params& p, cudaStream_t s) {
   constexpr int STAGES = StageCfg<BN, CG>::STAGES;
   constexpr int smem = STAGES * StageCfg<BN, CG>::STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 512;
   static_assert(smem <= 227 * 1024, "GEMM smem exceeds the CTA limit");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, CG, TMA_EPI>;
   static bool configured = false;
   static int max_units = 0;           // co-resident CTAs (CG 1) or CTA pairs (CG 2)
   if (!configured) {
@@ -734,12 +736,12 @@ static int launch(const Maps& mp, const Params& p, cudaStream_t s) {
   return EMO_OK;
 }
 
-template <int BN, typename TOut, int CG>
+template <int BN, typename TOut, int CG, bool TMA_EPI>
 static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
   switch (op) {
-    case EMO_GEMM_NT: return launch<BN, false, false, TOut, CG>(mp, p, s);
-    case EMO_GEMM_NN: return launch<BN, false, true, TOut, CG>(mp, p, s);
-    case EMO_GEMM_TN: return launch<BN, true, true, TOut, CG>(mp, p, s);
+    case EMO_GEMM_NT: return launch<BN, false, false, TOut, CG, TMA_EPI>(mp, p, s);
+    case EMO_GEMM_NN: return launch<BN, false, true, TOut, CG, TMA_EPI>(mp, p, s);
+    case EMO_GEMM_TN: return launch<BN, true, true, TOut, CG, TMA_EPI>(mp, p, s);
   }
   emo_set_error("emo_gemm: bad op %d", op);
   return EMO_ERR_ARG;
@@ -747,8 +749,11 @@ static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
 
 template <int CG>
 static int launch_any(int op, int BN, int out_dtype, const Maps& mp, const Params& p, cudaStream_t s) {
-  if (out_dtype == EMO_BF16) return BN == 256 ? launch_op<256, bf16, CG>(op, mp, p, s) : launch_op<128, bf16, CG>(op, mp, p, s);
-  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float, CG>(op, mp, p, s) : launch_op<128, float, CG>(op, mp, p, s);
+  if (out_dtype == EMO_BF16) {
+    if (p.tma_epi) return BN == 256 ? launch_op<256, bf16, CG, true>(op, mp, p, s) : launch_op<128, bf16, CG, true>(op, mp, p, s);
+    return BN == 256 ? launch_op<256, bf16, CG, false>(op, mp, p, s) : launch_op<128, bf16, CG, false>(op, mp, p, s);
+  }
+  if (out_dtype == EMO_F32) return BN == 256 ? launch_op<256, float, CG, false>(op, mp, p, s) : launch_op<128, float, CG, false>(op, mp, p, s);
   emo_set_error("emo_gemm: bad out dtype %d", out_dtype);
   return EMO_ERR_ARG;
 }
