@@ -289,8 +289,7 @@ class PlainTransformer(FlatModule):
             ops.linear_wgrad(g2, ff, self._gv(nm + "pos_ff.CoreNet.3.weight"))
             dff = new(R, f)
             ops.linear_dgrad(g2, self._wv(Wc, nm + "pos_ff.CoreNet.3.weight"), dff, act=ops.ACT_RELU_MASK_BWD, aux=ff,
-                             ld_aux=f, aux_scale=keep_scale)
-            ops.colsum(dff, self._gv(nm + "pos_ff.CoreNet.0.bias"))
+                             ld_aux=f, aux_scale=keep_scale, colsum_out=self._gv(nm + "pos_ff.CoreNet.0.bias"))
             ops.linear_wgrad(dff, c, self._gv(nm + "pos_ff.CoreNet.0.weight"))
             dc = new(R, d)
             ops.linear_dgrad(dff, self._wv(Wc, nm + "pos_ff.CoreNet.0.weight"), dc)

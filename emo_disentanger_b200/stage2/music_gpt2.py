@@ -115,8 +115,8 @@ class MusicGPT2(Stage2Base):
             ops.colsum(gp2, self._gv(nm + "mlp.c_proj.bias"))
             ops.linear_wgrad_t(gp2, g, self._gv(nm + "mlp.c_proj.weight"))
             du = new(R, f)
-            ops.linear_dgrad_t(gp2, self._wv(Wc, nm + "mlp.c_proj.weight"), du, act=ops.ACT_GELU_NEW_BWD, aux=u, ld_aux=f)
-            ops.colsum(du, self._gv(nm + "mlp.c_fc.bias"))
+            ops.linear_dgrad_t(gp2, self._wv(Wc, nm + "mlp.c_proj.weight"), du, act=ops.ACT_GELU_NEW_BWD, aux=u, ld_aux=f,
+                               colsum_out=self._gv(nm + "mlp.c_fc.bias"))            # bias gradient rides in the epilogue
             ops.linear_wgrad_t(du, c, self._gv(nm + "mlp.c_fc.weight"))
             dc = new(R, d)
             ops.linear_dgrad_t(du, self._wv(Wc, nm + "mlp.c_fc.weight"), dc)
@@ -124,9 +124,9 @@ class MusicGPT2(Stage2Base):
             dh = new(R, d)
             dhd = new(R, d) if p > 0 else None
             ops.ln_bwd(dc, h, m2, r2, self._wv(Wf, nm + "ln_2.weight"), dh, self._gv(nm + "ln_2.weight"),
-                       self._gv(nm + "ln_2.bias"), add_in=dout, dx_drop=dhd, drop_p=p, seed=site_seed(seed, 4 * l + 2))
+                       self._gv(nm + "ln_2.bias"), add_in=dout, dx_drop=dhd, drop_p=p, seed=site_seed(seed, 4 * l + 2),
+                       dxsum=self._gv(nm + "attn.c_proj.bias"))
             gp = dhd if p > 0 else dh
-            ops.colsum(gp, self._gv(nm + "attn.c_proj.bias"))
             ops.linear_wgrad_t(gp, att, self._gv(nm + "attn.c_proj.weight"))
             datt = dc      # reuse
             ops.linear_dgrad_t(gp, self._wv(Wc, nm + "attn.c_proj.weight"), datt)
