@@ -159,7 +159,8 @@ def bench_decode(model, V, n_tokens=384, prompt=64, cpu=True):
     model.eval()
     out = {"metric": "stage2_performer_decode_tokens_per_sec", "unit": "tokens/s", "temperature": 1.2, "top_p": 0.9,
            "prompt_tokens": prompt, "generated_tokens_per_sequence": n_tokens, "dtype": "bf16",
-           "api": "Stage2Decoder.step + DeviceSampler.draw (host loop, D2H of the sampled ids every step)"}
+           "api": "Stage2Decoder.step_sample (model step + temperature/top-p sampler in one CUDA graph; host loop, one H2D of "
+                  "tokens/uniforms and one D2H of the sampled ids every step)"}
     np.random.seed(0)
     for B in (1, 4):
         dec = Stage2Decoder(model, batch=B, max_len=2048)
@@ -172,8 +173,7 @@ def bench_decode(model, V, n_tokens=384, prompt=64, cpu=True):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(n):
-                lg = dec.step(toks, [1] * B)
-                toks = smp.draw(lg, V, 1.2, 0.9)
+                toks, _st = dec.step_sample(toks, [1] * B, rng.random_sample(B), 1.2, 0.9)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         out["batch%d" % B] = {"value": B * n_tokens / dt, "us_per_step": 1e6 * dt / n_tokens}

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   __shared__ int s_first, s_choice;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* row = logits + (int64_t)blockIdx.x * ld;
+  pdl_trigger();
+  pdl_wait();                       // (no-ops unless launched as a dependent of the decode step, emo_set_pdl)
 
   // ---- max / argmax ----
   float mx = -INFINITY;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   // ---- softmax(l / t) ----
   float se = 0.f;
   for (int c = tid; c < SMP_N; c += SMP_THREADS) {
-    float e = (c < V) ? expf((row[c] - mx) * inv_t) : -1.f;   // pads sort to the end
+    float e = (c < V) ? expf((row[c] - mx) * inv_t) : -1.f;
     key[c] = e;
     idx[c] = c;
     if (c < V) se += e;
@@ -62,19 +64,33 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   for (int i = 0; i < SMP_THREADS / 32; ++i) se += red[i];
   const float inv_se = 1.f / se;
 
-  // ---- bitonic sort, descending by key (ties: lower index first) ----
-  for (int k = 2; k <= SMP_N; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncthreads();
-      for (int t = tid; t < SMP_N / 2; t += SMP_THREADS) {
-        int i = 2 * t - (t & (j - 1));   // index with bit j clear
-        int l = i + j;
-        bool desc = ((i & k) == 0);
-        float a = key[i], b = key[l];
-        int ia = idx[i], ib = idx[l];
-        bool a_first = (a > b) || (a == b && ia < ib);   // a should precede b in descending order
-        if (a_first != desc) { key[i] = b; key[l] = a; idx[i] = ib; idx[l] = ia; }
+  // ---- sort descending by key (ties: lower index first) by RANK COUNTING: element c goes to position
+  //      #{j : key[j] > key[c] or (key[j] == key[c] and j < c)}.  V^2 / 256 broadcast smem reads per thread and
+  //      two barriers instead of the ~50 barrier-separated passes of a bitonic network (the sampler sits on the
+  //      critical path of every generated token) ----
+  __syncthreads();
+  {
+    float myk[SMP_N / SMP_THREADS];
+    int myr[SMP_N / SMP_THREADS];
+#pragma unroll
+    for (int i = 0; i < SMP_N / SMP_THREADS; ++i) {
+      const int c = tid + i * SMP_THREADS;
+      myk[i] = (c < V) ? key[c] : -1.f;
+      myr[i] = 0;
+    }
+    for (int j = 0; j < V; ++j) {
+      const float kj = key[j];
+#pragma unroll
+      for (int i = 0; i < SMP_N / SMP_THREADS; ++i) {
+        const int c = tid + i * SMP_THREADS;
+        myr[i] += (kj > myk[i] || (kj == myk[i] && j < c)) ? 1 : 0;
       }
+    }
+    __syncthreads();                       // everyone has read the unsorted keys
+#pragma unroll
+    for (int i = 0; i < SMP_N / SMP_THREADS; ++i) {
+      const int c = tid + i * SMP_THREADS;
+      if (c < V) { key[myr[i]] = myk[i]; idx[myr[i]] = c; }
     }
   }
   __syncthreads();
@@ -96,6 +112,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   }
   if (lane == 31) wsum[w] = incl;
   if (tid == 0) { s_first = SMP_N; s_choice = -1; }
+  (void)s_choice;
   __syncthreads();
   float base = incl - run;
   for (int i = 0; i < w; ++i) base += wsum[i];
@@ -135,8 +152,8 @@ extern "C" int emo_sample(const float* logits, int64_t ld, int rows, int V, floa
   EMO_REQUIRE(V > 0 && V <= SMP_N, "emo_sample: V must be in [1, %d]", SMP_N);
   EMO_REQUIRE(greedy || (u != nullptr && temperature > 0.f), "emo_sample: sampling needs u and temperature > 0");
   if (rows == 0) return EMO_OK;
-  sample_kernel<<<rows, SMP_THREADS, 0, (cudaStream_t)stream>>>(logits, ld, V, greedy ? 1.f : 1.f / temperature, top_p, u,
-                                                                greedy, out, status);
+  EMO_CHECK_CUDA(emo_launch_dep(sample_kernel, dim3(rows), dim3(SMP_THREADS), 0, (cudaStream_t)stream, logits, ld, V,
+                                greedy ? 1.f : 1.f / temperature, top_p, u, greedy, out, status));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -61,11 +61,17 @@ class Stage2Decoder:
         self.graph = None
         # pinned staging ring for the step inputs (tokens | segments): a slot is rewritten only after the
         # async H2D copy that read it has completed
-        self._ring = [torch.zeros(2, batch, dtype=torch.int64).pin_memory() for _ in range(8)]
+        self._ring = [torch.zeros(3, batch, dtype=torch.int64).pin_memory() for _ in range(8)]
         self._ring_ev = [None] * 8
         self._ring_i = 0
-        self._dev_in = torch.zeros(2, batch, dtype=torch.int64, device=dev)
+        self._dev_in = torch.zeros(3, batch, dtype=torch.int64, device=dev)    # tokens | segments | uniforms (as fp32)
         self.tok_in, self.seg_in = self._dev_in[0], self._dev_in[1]
+        self.u_in = self._dev_in[2].view(torch.float32)[:batch]
+        # fused step + sample (one graph): sampled ids | status words, read back through pinned memory
+        self._sampled = torch.zeros(2 * batch, dtype=torch.int64, device=dev)
+        self._sampled_host = torch.zeros(2 * batch, dtype=torch.int64).pin_memory()
+        self.sample_cfg = None            # (temperature, top_p, greedy) baked into the fused graph
+        self.graph_sample = None
 
     def reset(self, b=None):
         sl = slice(None) if b is None else slice(b, b + 1)
@@ -210,18 +216,7 @@ class Stage2Decoder:
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
         if self.is_performer:
-            i = self._ring_i
-            self._ring_i = (i + 1) % len(self._ring)
-            if self._ring_ev[i] is not None:
-                self._ring_ev[i].synchronize()
-            host = self._ring[i]
-            for b in range(self.B):
-                host[0, b] = int(tokens[b])
-                host[1, b] = int(segs[b])
-            self._dev_in.copy_(host, non_blocking=True)               # ONE small H2D per step (stream-ordered)
-            ev = torch.cuda.Event()
-            ev.record()
-            self._ring_ev[i] = ev
+            self._stage_inputs(tokens, segs, None)
             if self.use_graph:
                 if self.graph is None:
                     self._capture()
@@ -235,7 +230,49 @@ class Stage2Decoder:
                 self.append(b, [tokens[b]], [segs[b]])
         return self.logits[:, :m.n_token]
 
-    def _capture(self):
+    def _stage_inputs(self, tokens, segs, us):
+        """ONE small stream-ordered H2D per step from a pinned ring slot (rewritten only after its copy completed)"""
+        i = self._ring_i
+        self._ring_i = (i + 1) % len(self._ring)
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()
+        host = self._ring[i]
+        for b in range(self.B):
+            host[0, b] = int(tokens[b])
+            host[1, b] = int(segs[b])
+        if us is not None:
+            hu = host[2].view(torch.float32)
+            for b in range(self.B):
+                hu[b] = float(us[b])
+        self._dev_in.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+
+    @torch.no_grad()
+    def step_sample(self, tokens, segs, us, temperature, top_p, greedy=False):
+        """step() fused with the device sampler in ONE CUDA graph: tokens / segs / uniforms in by one H2D copy, the
+        sampled ids (and the sampler's status words) back by one D2H copy.  Returns (ids, status) python lists;
+        self.logits still holds the step's logits (a rejected draw is re-drawn from them by DeviceSampler)."""
+        if not (self.is_performer and self.use_graph):
+            raise RuntimeError("step_sample needs the Performer graph path")
+        if max(self.pos_host) + 1 > self.max_len:
+            raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
+        cfg = (float(temperature), float(top_p), bool(greedy))
+        if self.graph_sample is None or self.sample_cfg != cfg:
+            self.sample_cfg = cfg
+            self._capture(with_sampler=True)
+        self._stage_inputs(tokens, segs, us if not greedy else [0.0] * self.B)
+        self.graph_sample.replay()
+        self._sampled_host.copy_(self._sampled, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        for b in range(self.B):
+            self.pos_host[b] += 1
+        ids = self._sampled_host[:self.B].tolist()
+        st = self._sampled_host[self.B:].view(torch.int32)[:self.B].tolist()
+        return ids, st
+
+    def _capture(self, with_sampler=False):
         m = self.m
         m.weights()                                   # make sure the bf16 shadow exists before capture
         state0, pos0 = self.state.clone(), self.pos.clone()
@@ -251,8 +288,15 @@ class Stage2Decoder:
         try:
             with torch.cuda.graph(g):
                 self._performer_step_body()
+                if with_sampler:
+                    t, p, greedy = self.sample_cfg
+                    ops.sample(self.logits, m.n_token, t, p, self.u_in, self._sampled[:self.B],
+                               self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy)
         finally:
             _lib.lib().emo_set_pdl(0)
         self.state.copy_(state0)                      # undo the warm-up / capture-time state advance
         self.pos.copy_(pos0)
-        self.graph = g
+        if with_sampler:
+            self.graph_sample = g
+        else:
+            self.graph = g

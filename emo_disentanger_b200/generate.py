@@ -80,6 +80,7 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
     V = model.n_token
     fed = 0                       # tokens of `generated` already folded into the decode state
     logits = None
+    predrawn = None               # token drawn inside the fused step graph, not yet consumed by the rules below
 
     steps = 0
     time_st = time.time()
@@ -91,7 +92,15 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
         if len(generated) < MAX_DEC_INP_LEN:
             if fed < len(generated):          # fold the not-yet-seen suffix (primer, new token, lead-sheet bar)
                 n_new = len(generated) - fed
-                if n_new == 1 and fed > 0:
+                if n_new == 1 and fed > 0 and dec.is_performer and dec.use_graph:
+                    # the common case: one new token -> model step and draw fused in one CUDA graph
+                    u = 0.0 if greedy else (np.random if rng is None else rng).random_sample()
+                    ids, st = dec.step_sample([generated[-1]], [seg_inp[-1]], [u], temp, top_p, greedy=greedy)
+                    if st[0] != 0:
+                        raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+                    logits = dec.logits[0:1, :V]
+                    predrawn = ids[0]
+                elif n_new == 1 and fed > 0:
                     logits = dec.step([generated[-1]], [seg_inp[-1]])[0:1]
                 else:
                     logits = dec.append(0, generated[fed:], seg_inp[fed:])[None]
@@ -105,7 +114,10 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
             with torch.no_grad():
                 logits = model(dec_input, seg_inp=dec_seg_inp, keep_last_only=True).float().contiguous()
 
-        word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
+        if predrawn is not None:
+            word, predrawn = predrawn, None
+        else:
+            word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
         word_event = idx2event[word]
 
         if not skip_check:

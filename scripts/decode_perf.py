@@ -30,8 +30,11 @@ for kind in sys.argv[1:] or ["performer", "gpt2"]:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(n):
-                lg = dec.step(toks, [1] * B)
-                toks = smp.draw(lg, V, 1.2, 0.9)
+                if kind == "performer":
+                    toks, _ = dec.step_sample(toks, [1] * B, np.random.random_sample(B), 1.2, 0.9)
+                else:
+                    lg = dec.step(toks, [1] * B)
+                    toks = smp.draw(lg, V, 1.2, 0.9)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         # model step alone (no sampler / no D2H)
