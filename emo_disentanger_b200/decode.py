@@ -26,7 +26,7 @@ E = 64
 
 
 class Stage2Decoder:
-    def __init__(self, model, batch=1, max_len=2048, omegas=None, use_graph=True, use_pdl=True):
+    def __init__(self, model, batch=1, max_len=2048, omegas=None, use_graph=True, use_pdl=True, one_kernel=None):
         if model.training:
             raise RuntimeError("decode needs model.eval() (dropout off)")
         self.m = model
@@ -58,6 +58,22 @@ class Stage2Decoder:
         self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and self.is_performer
         self.use_pdl = bool(use_pdl)      # step kernels overlap their prologue with the predecessor's tail (graph only)
+        # the whole step as ONE kernel, a 16-CTA cluster per sequence (bf16 Performer; csrc/decode_step.cu).  Opt-in:
+        # bit-identical to the kernel chain, sequences scale almost for free (one cluster each), but at batch 1-4 it
+        # measured 312-326 us per step against 200-300 us for the PDL graph of small kernels
+        can_one = self.is_performer and self.dt == torch.bfloat16
+        self.one_kernel = bool(one_kernel) and can_one
+        if self.one_kernel:
+            sl = model._sl
+            rows = []
+            for l in range(L):
+                nm = model._layer_names(l)
+                rows.append([sl[nm + k][0] for k in (
+                    "attention.query_projection.weight", "attention.out_projection.weight", "linear1.weight", "linear2.weight",
+                    "attention.query_projection.bias", "attention.out_projection.bias", "linear1.bias", "linear2.bias",
+                    "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")])
+            self._offs = torch.tensor(rows, dtype=torch.int64, device=dev)
+            self._scratch = torch.zeros(batch * 6144, dtype=torch.bfloat16, device=dev)
         self.graph = None
         # pinned staging ring for the step inputs (tokens | segments): a slot is rewritten only after the
         # async H2D copy that read it has completed
@@ -193,6 +209,16 @@ class Stage2Decoder:
     def _performer_step_body(self):
         m = self.m
         B, d, H = self.B, m.d_model, m.n_head
+        if self.one_kernel:
+            sl = m._sl
+            ops.performer_decode_step(m.weights(), m._flat, self._offs, sl["token_emb.emb_lookup.weight"][0],
+                                      sl["segemb.emb_lookup.weight"][0] if m.use_segment_emb else -1,
+                                      sl["dec_out_proj.weight"][0], sl["dec_out_proj.bias"][0],
+                                      m.pe.pe if m.use_pe else None, self.omegas, self.state, self.tok_in, self.seg_in,
+                                      self.pos, self._scratch, self.logits, m.n_layer, B, m.n_token, d ** 0.5)
+            if not m.use_pe:
+                self.pos.add_(1)
+            return
         h = torch.empty(B, d, dtype=self.dt, device=self.dev)
         ops.embed_rows(self.tok_in, self.seg_in if m.use_segment_emb else None, self.pos if m.use_pe else None,
                        m._wv(m._flat, "token_emb.emb_lookup.weight"),

@@ -360,3 +360,11 @@ def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False):
     _call("emo_sample", _p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
                                1 if greedy else 0, _p(out), _p(status), _stream())
     return out
+
+
+def performer_decode_step(w_bf16, w_f32, layer_offs, off_tok, off_seg, off_outw, off_outb, pe, omegas, state, tok, seg, pos,
+                          scratch, logits, n_layer, batch, n_token, emb_scale):
+    """one cooperative kernel = one decode step of the stage-2 Performer (include/emo_b200.h)"""
+    _call("emo_performer_decode_step", _p(w_bf16), _p(w_f32), _p(layer_offs), int(off_tok), int(off_seg), int(off_outw),
+          int(off_outb), _p(pe), _p(omegas), _p(state), _p(tok), _p(seg), _p(pos), _p(scratch), _p(logits), n_layer, batch,
+          n_token, logits.stride(0), float(emb_scale), _stream())

@@ -47,6 +47,22 @@ int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, c
                    const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
                    int64_t* pos_advance /* NULL, or where pos[row] + 1 is written (may be pos) */,
                    int out_dtype, void* stream);
+/* ---- A11: the whole per-token step of the stage-2 Performer in ONE kernel --------------------------------
+ * stage2_accompaniment/inference.py:252-272 (one model call per generated token).  One thread-block cluster (16
+ * CTAs) per sequence: embedding row -> 12 post-LN layers (qkv GEMV, FAVOR+ recurrent step, out-proj + residual, LN,
+ * FFN1 + ReLU, FFN2 + residual, LN) -> logits; the 61 phase boundaries are hardware cluster barriers and the
+ * weights of a warp's next phase are in flight before it enters the barrier.  bf16 weights / activations, fp32
+ * accumulation; bit-identical to the same step issued as emo_embed_rows / emo_gemm / emo_favor_step calls.
+ * w_bf16 / w_f32: the model's flat parameter buffer in bf16 and fp32 (same element offsets); layer_offs [n_layer][12]
+ * int64 element offsets (DEVICE memory): Wqkv Wo W1 W2 | bqkv bo b1 b2 | norm1.w norm1.b norm2.w norm2.b;
+ * off_seg < 0 / pe == NULL: no segment embedding / positional encoding.  tok, seg, pos: int64 [batch] on the
+ * device (pos is advanced by one).  state [n_layer, batch, 8, 128, 80] fp32 (updated in place), omegas
+ * [n_layer, 64, 64] fp32, scratch: batch * 6144 bf16, logits [batch, ld_logits] fp32. */
+int emo_performer_decode_step(const void* w_bf16, const float* w_f32, const int64_t* layer_offs,
+                              int64_t off_tok, int64_t off_seg, int64_t off_outw, int64_t off_outb,
+                              const float* pe, const float* omegas, float* state, const int64_t* tok,
+                              const int64_t* seg, int64_t* pos, void* scratch, float* logits, int n_layer,
+                              int batch, int n_token, int ld_logits, float emb_scale, void* stream);
 /* 1: the decode-step kernels (emo_embed_rows, the M <= 8 path of emo_gemm, emo_favor_step) are launched as
  * programmatic dependent launches -- each may start while its predecessor on the stream drains (its weight
  * prefetch overlaps the predecessor's tail) and waits (griddepcontrol.wait) before touching its inputs.  Meant

@@ -128,3 +128,35 @@ def test_stage1_generate_plain_xl_vs_reference_loop():
     ref = g["s1_sampled"].tolist()
     n = next((i for i, (a, b) in enumerate(zip(toks, ref)) if a != b), min(len(toks), len(ref)))
     assert n >= 20, (n, toks, ref)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_one_kernel_step_is_bit_identical_to_the_kernel_chain(B):
+    """bf16 Performer decode: the cooperative one-kernel step (decode_step.cu) and the chain of embed / GEMV /
+    FAVOR+ step launches produce the same logits and the same prefix state bit for bit, graph or not."""
+    from emo_disentanger_b200.decode import Stage2Decoder
+    V, L = 329, 3
+    m = _stage2("performer", V, L, 11, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(3)
+    om = torch.randn(L, 64, 64, generator=gen)
+    tok = torch.randint(0, V - 1, (B, 40), generator=gen)
+    seg = torch.randint(0, 2, (B, 40), generator=gen)
+    decs = [Stage2Decoder(m, batch=B, max_len=64, omegas=om, use_graph=g, one_kernel=o)
+            for g, o in ((False, False), (False, True), (True, True))]
+    for d in decs:
+        for b in range(B):
+            d.append(b, tok[b, :5 + b].tolist(), seg[b, :5 + b].tolist())        # ragged primers
+    for s_ in range(10):
+        outs = []
+        for d in decs:
+            lg = d.step([int(tok[b, 5 + b + s_]) for b in range(B)], [int(seg[b, 5 + b + s_]) for b in range(B)])
+            outs.append(lg.clone())
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), s_
+    assert torch.equal(decs[0].state, decs[1].state) and torch.equal(decs[0].state, decs[2].state)
+    assert torch.equal(decs[0].pos, decs[1].pos) and torch.equal(decs[0].pos, decs[2].pos)
+    # against the full-prefix forward (bf16 tolerance of the north star: 1e-2 on hidden states / logits)
+    m.fixed_omegas = om.cuda()
+    with torch.no_grad():
+        full = m(tok.cuda(), seg_inp=seg.cuda())
+    for b in range(B):
+        assert rel_err(outs[1][b].float(), full[b, 5 + b + 9].float()) < 2e-2
