@@ -9,7 +9,8 @@ Differences by design: the epoch loop calls the fused `train_step` (no autograd 
 copied to the host: loss / accuracy come back as 3 floats) and `FusedAdam` (clip 0.5 + Adam in one launch);
 under torchrun the batches are rank-strided and gradients all-reduced once per optimiser step; rank 0
 alone logs and checkpoints.  Datasets stay the reference's (imported from the reference tree) unless the
-config has a `synthetic` data section."""
+config has a `synthetic` data section or sets `data_loader.gpu_token_store: true` (pieces resident in HBM, batches
+assembled on the device: data/token_store.py)."""
 import argparse
 import os
 import shutil
@@ -86,6 +87,24 @@ def main(argv=None):
         dset = common.SyntheticStage2(sy['vocab_size'], dc['batch_size'], T, sy['n_train_batches'], 0)
         vset = common.SyntheticStage2(sy['vocab_size'], dc['batch_size'], T, sy['n_val_batches'], 10 ** 6)
         dloader, vloader = dset, vset
+    elif dc.get('gpu_token_store'):
+        # pieces tokenised once into HBM, batches assembled by one kernel launch (data/token_store.py): same batch
+        # dicts as the reference Dataset + DataLoader, same start-bar choice (`random.choice` over the admissible bars)
+        import pickle
+        from ..data import Stage2TokenStore
+        ddir, vfile = dc['data_path'].format(rep), dc['vocab_path'].format(rep)
+        mk = lambda split: Stage2TokenStore.from_files([os.path.join(ddir, p_) for p_ in pickle.load(open(split, 'rb'))], vfile,
+                                                       model_dec_seqlen=mc['max_len'], predict_key=False, device='cuda:%d' % gpuid)
+        dset, vset = mk(dc['train_split']), mk(dc['val_split'])
+
+        class _Epochs:                                   # a fresh shuffled pass per `for batch in loader`
+            def __init__(self, store):
+                self.store = store
+
+            def __iter__(self):
+                return self.store.loader(dc['batch_size'], shuffle=True)
+
+        dloader, vloader = _Epochs(dset), _Epochs(vset)
     else:
         from torch.utils.data import DataLoader
         dl = common.reference_module('stage2_accompaniment', 'dataloader')

@@ -47,6 +47,22 @@ int emo_embed_rows(const int64_t* tok, const int64_t* seg, const int64_t* pos, c
                    const float* e_seg, const float* pe, void* out, int rows, int d, float scale,
                    int64_t* pos_advance /* NULL, or where pos[row] + 1 is written (may be pos) */,
                    int out_dtype, void* stream);
+/* ---- 8f rank 1: stage-2 training batches from a GPU-resident token store ---------------------------------
+ * stage2_accompaniment/dataloader.py:178-231 (REMISkylineToMidiTransformerDataset.__getitem__) + DataLoader
+ * collation + the H2D copies of train.py:44-50.  tokens: every piece's event ids, concatenated (int32);
+ * piece_off [P+1] / bar_off [P+1] (int64) index tokens / the per-bar tables; mel_start[b] = melody_pos[b][0],
+ * [ch_start[b], ch_end[b]) = chord_pos[b] (the Full-track span of bar b); flags [V]: bit 0 = 'Chord_*', bit 1 =
+ * 'Note_*'.  sel_piece / sel_stbar [B]: the sample picks (piece index, start bar).  Outputs [B, T] int64:
+ * dec_input (header + events from the start bar, PAD-filled / truncated to T), dec_target (next token inside the
+ * Full-track spans, EOS closing the last bar, PAD elsewhere), track_mask, chord_idx, melody_idx; length [B].
+ * Integer work: bit-exact against the reference. */
+int emo_stage2_batch(const int32_t* tokens, const int64_t* piece_off, const int64_t* bar_off,
+                     const int32_t* mel_start, const int32_t* ch_start, const int32_t* ch_end,
+                     const uint8_t* flags, const int32_t* sel_piece, const int32_t* sel_stbar,
+                     int64_t* dec_input, int64_t* dec_target, int64_t* track_mask, int64_t* chord_idx,
+                     int64_t* melody_idx, int64_t* length, int B, int T, int pad_token, int eos_token,
+                     int predict_key, void* stream);
+
 /* ---- A11: the whole per-token step of the stage-2 Performer in ONE kernel --------------------------------
  * stage2_accompaniment/inference.py:252-272 (one model call per generated token).  One thread-block cluster (16
  * CTAs) per sequence: embedding row -> 12 post-LN layers (qkv GEMV, FAVOR+ recurrent step, out-proj + residual, LN,
