@@ -50,7 +50,7 @@ SIGNATURES = {
     "emo_sumsq": ([vp, i64, vp, vp], i32),
     "emo_adam_step": ([vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, vp, f32, f32, i32, vp], i32),
     "emo_cast": ([vp, vp, i64, i32, i32, vp], i32),
-    "emo_sample": ([vp, i64, i32, i32, f32, f32, vp, i32, vp, vp, vp], i32),
+    "emo_sample": ([vp, i64, i32, i32, f32, f32, vp, i32, vp, vp, vp, vp], i32),
 }
 
 _lib = None

@@ -11,7 +11,8 @@ constexpr int SMP_THREADS = 256;
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __restrict__ logits, int64_t ld, int V,
                                                              float inv_t, float top_p, const float* __restrict__ u,
                                                              int greedy, int64_t* __restrict__ out,
-                                                             int32_t* __restrict__ status) {
+                                                             int32_t* __restrict__ status,
+                                                             const uint8_t* __restrict__ banned) {
   __shared__ float key[SMP_N];
   __shared__ int idx[SMP_N];
   __shared__ float red[SMP_THREADS / 32];
@@ -130,7 +131,42 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   if (first >= V) ncand = V < 3 ? V : 3;              // nothing above p: reference takes the top 3
   else if (first + 1 >= V) { ncand = V; st = 1; }     // exactly one index above: reference IndexError
   else ncand = first + 1;                             // `where(..)[0][1]` == first + 1 candidates
-  const float total = key[ncand - 1];
+  float total = key[ncand - 1];
+  if (banned) {
+    // Grammar-constrained draw (opt-in): the reference draws from the nucleus candidates and REJECTS
+    // inadmissible tokens (Beat going backwards, PAD, early EOS: inference.py:279-310), re-running the model and
+    // re-drawing -- i.e. it samples from the candidate distribution restricted to the admissible tokens.  Here the
+    // inadmissible candidates get zero mass and the cumulative sums are rebuilt over the SAME candidate set: the same
+    // distribution in one draw.  status 2 = every candidate is inadmissible (the reference would spin to its 256-retry
+    // abort).
+    const uint8_t* brow = banned + (int64_t)blockIdx.x * V;
+    __syncthreads();
+    float run2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid * 4 + i;
+      float prev = (c == 0) ? 0.f : key[c - 1];
+      float pr = (c < ncand && !brow[idx[c]]) ? (p4[i] - prev) : 0.f;       // this candidate's own mass
+      run2 += pr;
+      p4[i] = run2;
+    }
+    __syncthreads();                                   // all reads of the unmasked cumulative sums are done
+    float incl2 = run2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, incl2, o);
+      if (lane >= o) incl2 += t;
+    }
+    if (lane == 31) wsum[w] = incl2;
+    __syncthreads();
+    float base2 = incl2 - run2;
+    for (int i = 0; i < w; ++i) base2 += wsum[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p4[i] += base2; key[tid * 4 + i] = p4[i]; }
+    __syncthreads();
+    total = key[ncand - 1];
+    if (total <= 0.f) st = 2;
+  }
   const float thresh = u[blockIdx.x] * total;         // cdf_i = cum_i / total > u  <=>  cum_i > u * total
   __syncthreads();
   if (tid == 0) s_first = ncand - 1;                  // fallback: last candidate
@@ -148,12 +184,13 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
 }
 
 extern "C" int emo_sample(const float* logits, int64_t ld, int rows, int V, float temperature, float top_p,
-                          const float* u, int greedy, int64_t* out, int32_t* status, void* stream) {
+                          const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned,
+                          void* stream) {
   EMO_REQUIRE(V > 0 && V <= SMP_N, "emo_sample: V must be in [1, %d]", SMP_N);
   EMO_REQUIRE(greedy || (u != nullptr && temperature > 0.f), "emo_sample: sampling needs u and temperature > 0");
   if (rows == 0) return EMO_OK;
   EMO_CHECK_CUDA(emo_launch_dep(sample_kernel, dim3(rows), dim3(SMP_THREADS), 0, (cudaStream_t)stream, logits, ld, V,
-                                greedy ? 1.f : 1.f / temperature, top_p, u, greedy, out, status));
+                                greedy ? 1.f : 1.f / temperature, top_p, u, greedy, out, status, banned));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

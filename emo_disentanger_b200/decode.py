@@ -276,7 +276,7 @@ class Stage2Decoder:
         self._ring_ev[i] = ev
 
     @torch.no_grad()
-    def step_sample(self, tokens, segs, us, temperature, top_p, greedy=False):
+    def step_sample(self, tokens, segs, us, temperature, top_p, greedy=False, banned=None):
         """step() fused with the device sampler in ONE CUDA graph: tokens / segs / uniforms in by one H2D copy, the
         sampled ids (and the sampler's status words) back by one D2H copy.  Returns (ids, status) python lists;
         self.logits still holds the step's logits (a rejected draw is re-drawn from them by DeviceSampler)."""
@@ -284,7 +284,10 @@ class Stage2Decoder:
             raise RuntimeError("step_sample needs the Performer graph path")
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
-        cfg = (float(temperature), float(top_p), bool(greedy))
+        # banned: uint8 [B, V] device mask of inadmissible tokens (its ADDRESS is baked into the graph; the caller
+        # updates the contents in place)
+        cfg = (float(temperature), float(top_p), bool(greedy), None if banned is None else banned.data_ptr())
+        self._banned = banned
         if self.graph_sample is None or self.sample_cfg != cfg:
             self.sample_cfg = cfg
             self._capture(with_sampler=True)
@@ -315,9 +318,10 @@ class Stage2Decoder:
             with torch.cuda.graph(g):
                 self._performer_step_body()
                 if with_sampler:
-                    t, p, greedy = self.sample_cfg
-                    ops.sample(self.logits, m.n_token, t, p, self.u_in, self._sampled[:self.B],
-                               self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy)
+                    t, p, greedy, _ = self.sample_cfg
+                    ops.sample(self.logits, m.n_token, t, p, self.u_in,
+                               self._sampled[:self.B], self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy,
+                               banned=self._banned)
         finally:
             _lib.lib().emo_set_pdl(0)
         self.state.copy_(state0)                      # undo the warm-up / capture-time state advance

@@ -34,22 +34,24 @@ class DeviceSampler:
         self._u_host = torch.zeros(rows, dtype=torch.float32).pin_memory()
         self._host = torch.zeros(2 * rows, dtype=torch.int64).pin_memory()
 
-    def draw(self, logits, V, temp, top_p, greedy=False, rng=None):
+    def draw(self, logits, V, temp, top_p, greedy=False, rng=None, banned=None):
         """logits fp32 [rows, >=V] (device).  Returns python ints (tokens); raises IndexError where the
-        reference would (exactly one index above top_p, inference.py:93)."""
+        reference would (exactly one index above top_p, inference.py:93).  banned: uint8 [rows, V] device mask of
+        inadmissible tokens (grammar-constrained draw); a row whose candidates are all banned returns -1."""
         rows = logits.shape[0]
         if not greedy:
             r = np.random if rng is None else rng
             for i in range(rows):
                 self._u_host[i] = r.random_sample()
             self.u.copy_(self._u_host, non_blocking=True)
-        ops.sample(logits, V, temp, top_p, self.u, self.out, self.status, greedy=greedy)
+        ops.sample(logits, V, temp, top_p, self.u, self.out, self.status, greedy=greedy, banned=banned)
         self._host.copy_(self._buf, non_blocking=True)                          # ONE small D2H into pinned memory
         torch.cuda.current_stream().synchronize()
-        st = self._host[self.rows:].view(torch.int32)[:rows]
-        if int(st.max()) != 0:
+        st = self._host[self.rows:].view(torch.int32)[:rows].tolist()
+        if 1 in st:
             raise IndexError("index 1 is out of bounds for axis 0 with size 1")
-        return self._host[:rows].tolist()
+        ids = self._host[:rows].tolist()
+        return [(-1 if s_ == 2 else t) for t, s_ in zip(ids, st)]
 
 
 def get_position_idx(event):
@@ -62,7 +64,13 @@ def get_position_idx(event):
 def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
                          max_events=10000, skip_check=False, max_bars=None,
                          temp=1.2, top_p=0.9, inadmissibles=None,
-                         model_type="performer", greedy=False, decoder=None, rng=None, verbose=True):
+                         model_type="performer", greedy=False, decoder=None, rng=None, verbose=True,
+                         device_grammar=False):
+    """device_grammar=True (opt-in): the rejection rules of the loop below (Beat positions must not
+    go backwards, no PAD, no EOS before the last bar) are applied INSIDE the device sampler as a mask over the nucleus
+    candidates -- the distribution the reference's reject-and-redraw loop samples from, without the wasted model calls.
+    The numpy RNG stream is consumed differently (one uniform per accepted token), so seeded runs differ from the
+    reference's; off by default."""
     if inadmissibles is not None:
         raise NotImplementedError("the reference always passes inadmissibles=None (inference.py:467)")
     say = print if verbose else (lambda *a, **k: None)
@@ -81,6 +89,28 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
     fed = 0                       # tokens of `generated` already folded into the decode state
     logits = None
     predrawn = None               # token drawn inside the fused step graph, not yet consumed by the rules below
+    banned = banned_host = None
+    if device_grammar and not skip_check and not greedy:
+        beat_pos = {i: get_position_idx(e) for i, e in idx2event.items() if 'Beat' in e}
+        pad_id, eos_id = event2idx.get('PAD_None', V - 1), event2idx['EOS_None']
+        banned_host = torch.zeros(1, V, dtype=torch.uint8).pin_memory()
+        banned = torch.zeros(1, V, dtype=torch.uint8, device=dec.dev)
+        ban_state = None
+
+        def update_banned(cur_pos_, last_bar_):
+            nonlocal ban_state
+            if ban_state == (cur_pos_, last_bar_):
+                return
+            ban_state = (cur_pos_, last_bar_)
+            banned_host.zero_()
+            for i, ppos in beat_pos.items():
+                if ppos < cur_pos_:
+                    banned_host[0, i] = 1
+            banned_host[0, pad_id] = 1
+            if not last_bar_:
+                banned_host[0, eos_id] = 1
+            banned.copy_(banned_host, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the pinned buffer is rewritten on the next change
 
     steps = 0
     time_st = time.time()
@@ -89,15 +119,19 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
 
     while generated_bars < target_bars:
         assert len(generated) == len(seg_inp)
+        if banned is not None:
+            update_banned(cur_pos, generated_bars >= target_bars - 1)
         if len(generated) < MAX_DEC_INP_LEN:
             if fed < len(generated):          # fold the not-yet-seen suffix (primer, new token, lead-sheet bar)
                 n_new = len(generated) - fed
                 if n_new == 1 and fed > 0 and dec.is_performer and dec.use_graph:
                     # the common case: one new token -> model step and draw fused in one CUDA graph
                     u = 0.0 if greedy else (np.random if rng is None else rng).random_sample()
-                    ids, st = dec.step_sample([generated[-1]], [seg_inp[-1]], [u], temp, top_p, greedy=greedy)
-                    if st[0] != 0:
+                    ids, st = dec.step_sample([generated[-1]], [seg_inp[-1]], [u], temp, top_p, greedy=greedy, banned=banned)
+                    if st[0] == 1:
                         raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+                    if st[0] == 2:
+                        ids = [-1]
                     logits = dec.logits[0:1, :V]
                     predrawn = ids[0]
                 elif n_new == 1 and fed > 0:
@@ -117,7 +151,10 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
         if predrawn is not None:
             word, predrawn = predrawn, None
         else:
-            word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
+            word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng, banned=banned)[0]
+        if word < 0:                  # every nucleus candidate is inadmissible: the reference would retry 256 times
+            say('[FATAL] model stuck, exiting with generated events ...')
+            return generated
         word_event = idx2event[word]
 
         if not skip_check:

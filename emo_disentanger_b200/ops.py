@@ -355,10 +355,13 @@ def cast(src, dst):
     return dst
 
 
-def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False):
+def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False, banned=None):
+    """banned: uint8 [rows, V] (non-zero = inadmissible token) or None"""
     rows = logits.shape[0]
+    if banned is not None:
+        assert banned.dtype == torch.uint8 and banned.shape[-1] == V and banned.is_contiguous()
     _call("emo_sample", _p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
-                               1 if greedy else 0, _p(out), _p(status), _stream())
+                               1 if greedy else 0, _p(out), _p(status), _p(banned), _stream())
     return out
 
 

@@ -252,9 +252,14 @@ int emo_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype
  * index wins ties like numpy.argmax).  Otherwise softmax(l/t), descending sort, cut at the second
  * index whose cumulative mass exceeds top_p (top-3 fallback), renormalise, inverse-CDF draw with
  * the caller-provided uniform u[row] in [0,1).  out int64 [rows]; status[row] = 1 when exactly
- * one index exceeded top_p (the reference raises IndexError there). */
+ * one index exceeded top_p (the reference raises IndexError there).
+ * banned (NULL = off; uint8 [rows, V], non-zero = inadmissible): grammar-constrained draw.  The
+ * decode loops reject inadmissible samples and re-draw (inference.py:279-310, inference_utils.py:80-118), i.e. they
+ * sample from the nucleus candidates restricted to the admissible tokens; with `banned` those candidates get zero
+ * mass inside the kernel -- the same distribution in one draw, no wasted model calls.  status 2 = every candidate is
+ * inadmissible. */
 int emo_sample(const float* logits, int64_t ld, int rows, int V, float temperature, float top_p,
-               const float* u, int greedy, int64_t* out, int32_t* status, void* stream);
+               const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned, void* stream);
 
 #ifdef __cplusplus
 }

@@ -160,3 +160,38 @@ def test_one_kernel_step_is_bit_identical_to_the_kernel_chain(B):
         full = m(tok.cuda(), seg_inp=seg.cuda())
     for b in range(B):
         assert rel_err(outs[1][b].float(), full[b, 5 + b + 9].float()) < 2e-2
+
+
+def test_generate_conditional_device_grammar_obeys_the_rules_without_rejections():
+    """opt-in grammar-constrained decoding: Beat positions never go backwards inside a bar, no PAD, EOS only in the
+    last bar -- and not a single reject-and-redraw round trip (every draw is accepted)."""
+    from emo_disentanger_b200.generate import generate_conditional, get_position_idx
+    from emo_disentanger_b200.synth import synthetic_vocab, synthetic_lead_sheet
+    V, L = 120, 2
+    e2i, i2e = synthetic_vocab(V, 2)
+    m = _stage2("performer", V, L, 41, dtype=torch.bfloat16)
+    lead = synthetic_lead_sheet(e2i, 4, seed=2)
+    primer = [e2i['Emotion_Q2'], e2i['Key_C'], e2i['Tempo_110']]
+    np.random.seed(9)
+    msgs = []
+    import builtins
+    real_print = builtins.print
+    builtins.print = lambda *a, **k: msgs.append(" ".join(str(x) for x in a))
+    try:
+        toks = generate_conditional(m, e2i, i2e, lead, primer, max_events=300, skip_check=False, temp=1.2, top_p=0.97,
+                                    model_type="performer", device_grammar=True, verbose=True)
+    finally:
+        builtins.print = real_print
+    assert not any("position not increasing" in s for s in msgs)
+    ev = [i2e[t] for t in toks]
+    assert 'PAD_None' not in ev
+    cur, full = 0, False
+    for e in ev:
+        if e == 'Track_Full':
+            full, cur = True, 0
+        elif e == 'Track_LeadSheet':
+            full = False
+        elif full and 'Beat' in e:
+            assert get_position_idx(e) >= cur
+            cur = get_position_idx(e)
+    assert len(toks) > len(primer) + len(lead[0]) + 2

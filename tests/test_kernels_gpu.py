@@ -569,3 +569,46 @@ def test_sampler_distribution(ops):
     assert set(np.unique(o)) <= set(cand.tolist())
     top = cand[0]
     assert abs((o == top).mean() - cp[0]) < 0.03
+
+
+def test_sampler_grammar_mask_equals_rejection_sampling_distribution(ops):
+    """banned tokens get zero mass INSIDE the nucleus candidate set: the distribution of the reference's
+    reject-and-redraw loop, in one draw."""
+    rng = np.random.RandomState(0)
+    V, N = 96, 8192
+    logits1 = (rng.randn(V) * 2.0).astype(np.float32)
+    temp, top_p = 1.2, 0.9
+    # expected candidate set / probabilities, as the reference computes them (inference.py:71-100)
+    pr = np.exp(logits1 / temp - (logits1 / temp).max()); pr /= pr.sum()
+    order = np.argsort(-pr, kind="stable")
+    cum = np.cumsum(pr[order])
+    ncand = int(np.where(cum > top_p)[0][1])                    # cut at the SECOND index above top_p
+    cand = order[:ncand]
+    banned1 = np.zeros(V, dtype=np.uint8)
+    banned1[cand[[0, 3, 4]]] = 1                                # ban the top candidate and two more
+    banned1[order[ncand:ncand + 5]] = 1                         # (and some non-candidates: no effect)
+    w = pr[cand] * (1 - banned1[cand]); w /= w.sum()
+    logits = torch.tensor(logits1, device=DEV).repeat(N, 1).contiguous()
+    banned = torch.tensor(banned1, device=DEV).repeat(N, 1).contiguous()
+    u = torch.tensor(rng.random_sample(N).astype(np.float32), device=DEV)
+    out = torch.empty(N, dtype=torch.int64, device=DEV)
+    st = torch.empty(N, dtype=torch.int32, device=DEV)
+    ops.sample(logits, V, temp, top_p, u, out, st, banned=banned)
+    got = out.cpu().numpy()
+    assert int(st.max()) == 0
+    assert not banned1[got].any() and set(got.tolist()) <= set(cand.tolist())
+    # exact inverse-CDF check against numpy (float32 boundary flips aside)
+    cw = np.cumsum(w)
+    exp = cand[np.minimum(np.searchsorted(cw, u.cpu().numpy().astype(np.float64), side="right"), ncand - 1)]
+    assert (exp == got).mean() > 0.995
+    freq = np.bincount(got, minlength=V)[cand] / N
+    assert np.abs(freq - w).sum() < 0.06                        # total variation, N = 8192
+    # unmasked rows are unchanged by the feature; all candidates banned -> status 2
+    out2 = torch.empty_like(out)
+    ops.sample(logits, V, temp, top_p, u, out2, st, banned=torch.zeros_like(banned))
+    out3 = torch.empty_like(out)
+    ops.sample(logits, V, temp, top_p, u, out3, st)
+    assert torch.equal(out2, out3)
+    allb = torch.ones_like(banned)
+    ops.sample(logits[:4], V, temp, top_p, u[:4], out[:4], st[:4], banned=allb[:4].contiguous())
+    assert st[:4].tolist() == [2, 2, 2, 2]
