@@ -25,6 +25,13 @@ using namespace FAVOR_NS;
 // nseg_b ~ SMs / (B*H) segments, the forward (2 CTAs / SM) twice as many while that still adds parallelism.
 // Backward segment boundaries are a subset of the forward's (sc_b = ratio * sc_f), so the forward's prefix slots
 // serve both.
+int emo_favor_fwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
+                          int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
+                          int nseg, int sc, int B, int T_, int H, cudaStream_t s);       // favor_fwd2.cu
+#ifndef FAVOR_FWD2_DEFAULT
+#define FAVOR_FWD2_DEFAULT 1
+#endif
+
 struct FavorPlan { int nseg_f, sc_f, nseg_b, sc_b, ratio; };
 template <typename T> static FavorPlan favor_plan(int B, int T_, int H) {
   constexpr int C = FavorCfg<T>::C;
@@ -85,6 +92,10 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
       EMO_LAUNCH_CHECK();
     }
   }
+  static int fwd2 = -1;       // EMO_FAVOR_FWD2=0: A/B switch back to the block-GEMM forward
+  if (fwd2 < 0) { const char* e = getenv("EMO_FAVOR_FWD2"); fwd2 = e ? atoi(e) : FAVOR_FWD2_DEFAULT; }
+  if (sizeof(T) == 2 && fwd2)
+    return emo_favor_fwd2_launch(q, k, v, ld, omega, out, ld_out, den, state_in, state_out, seg_states, nseg, sc, B, T_, H, s);
   favor_fwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,
                                                              den, state_in, state_out, seg_states, nseg, sc, T_, H);
   EMO_LAUNCH_CHECK();
