@@ -28,6 +28,13 @@ using namespace FAVOR_NS;
 int emo_favor_fwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
                           int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
                           int nseg, int sc, int B, int T_, int H, cudaStream_t s);       // favor_fwd2.cu
+int emo_favor_bwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, const void* out,
+                          const void* dout, int64_t ld_out, const float* den, const float* seg_states,
+                          const float* seg_rstates, int nseg, int sc, int fwd_nseg, int ratio, void* dq, void* dk, void* dv,
+                          int64_t ld_d, int B, int T_, int H, cudaStream_t s);
+#ifndef FAVOR_BWD2_DEFAULT
+#define FAVOR_BWD2_DEFAULT 1
+#endif
 #ifndef FAVOR_FWD2_DEFAULT
 #define FAVOR_FWD2_DEFAULT 1
 #endif
@@ -124,6 +131,11 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
     favor_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seg_rstates, nseg, 1, (int64_t)B * H);
     EMO_LAUNCH_CHECK();
   }
+  static int bwd2 = -1;       // EMO_FAVOR_BWD2=0/1: A/B switch between the block-GEMM and the register-resident backward
+  if (bwd2 < 0) { const char* e = getenv("EMO_FAVOR_BWD2"); bwd2 = e ? atoi(e) : FAVOR_BWD2_DEFAULT; }
+  if (sizeof(T) == 2 && bwd2)
+    return emo_favor_bwd2_launch(q, k, v, ld, omega, out, dout, ld_out, den, seg_states, seg_rstates, nseg, sc, pl.nseg_f, pl.ratio,
+                                 dq, dk, dv, ld_d, B, T_, H, s);
   favor_bwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (const T*)out,
                                                              (const T*)dout, ld_out, den, seg_states, seg_rstates, nseg, sc,
                                                              pl.nseg_f, pl.ratio, (T*)dq, (T*)dk, (T*)dv, ld_d, T_, H);
