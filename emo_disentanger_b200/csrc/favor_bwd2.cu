@@ -9,7 +9,7 @@
 //                                dq  = du Om^T / k2 + do s^2 x_q      -> staged in place of x_q, 16-byte stores
 //                                R  += phi(q)^T G                     (each warp owns 32 feature rows, fp32, persistent)
 //                                phi(k) R                             (half of dv, handed to the key side in fp32)
-//   key warps (4-7), rows j:     S  -= phi(k)^T V'                    (rolled back to the chunk start, 32 rows per warp)
+//   key warps (4-7), rows j:     S  -= phi(k)^T V'                    (rolled back to the chunk start, 32 rows per warp, kept as -S)
 //                                P^T = triu(V' G^T);  dPk = P^T phi(q) + V' R^T  -> dk like dq
 //                                A^T = triu(phi(k) phi(q)^T);  dv = A^T G + [phi(k) R]
 //
@@ -35,6 +35,9 @@ struct Smem {
   bf16 s[FM][LD80];
   bf16 r[FM][LD80];
   float4 dvp[4][8][32];            // phi(k) R partial of dv: [key warp][n-tile][lane] in accumulator layout
+  bf16 ro[2][C][LD64];             // out / dout rows and den of the chunk (prefetched one chunk ahead like q, k, v)
+  bf16 rd[2][C][LD64];
+  float den[2][C];
 };
 static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "one CTA per SM");
 
@@ -232,6 +235,15 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
       issue_tile(q + base + (int64_t)t0 * ld, ld, valid, sm.xq[buf]);
       issue_tile(k + base + (int64_t)t0 * ld, ld, valid, sm.xk[buf]);
       issue_tile(v + base + (int64_t)t0 * ld, ld, valid, sm.xv[buf]);
+      issue_tile(out + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.ro[buf]);
+      issue_tile(dout + obase + (int64_t)t0 * ld_out, ld_out, valid, sm.rd[buf]);
+      if (threadIdx.x < C) {
+        const bool ok = threadIdx.x < valid;
+        const float* src = den_in + ((int64_t)b * Tlen + t0 + (ok ? threadIdx.x : 0)) * H + h;
+        uint32_t d = (uint32_t)__cvta_generic_to_shared(&sm.den[buf][threadIdx.x]);
+        int n = ok ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -269,19 +281,21 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
           lo = *reinterpret_cast<const float2*>(src + (f0 + 16 * mt + g) * FV + 8 * j + 2 * t4);
           hi = *reinterpret_cast<const float2*>(src + (f0 + 16 * mt + g + 8) * FV + 8 * j + 2 * t4);
         }
-        st[mt][j][0] = lo.x; st[mt][j][1] = lo.y; st[mt][j][2] = hi.x; st[mt][j][3] = hi.y;
+        // the key side carries -S, so that the roll-back S -= phi(k)^T V' is a plain accumulation
+        const float sg = qside ? 1.f : -1.f;
+        st[mt][j][0] = sg * lo.x; st[mt][j][1] = sg * lo.y; st[mt][j][2] = sg * hi.x; st[mt][j][3] = sg * hi.y;
       }
   }
-  auto store_state_bf16 = [&](bf16 (*dst)[LD80]) {
+  auto store_state_bf16 = [&](bf16 (*dst)[LD80], float sg) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int j = 0; j < 10; ++j) {
-        *reinterpret_cast<uint32_t*>(&dst[f0 + 16 * mt + g][8 * j + 2 * t4]) = pack_bf16x2(st[mt][j][0], st[mt][j][1]);
-        *reinterpret_cast<uint32_t*>(&dst[f0 + 16 * mt + g + 8][8 * j + 2 * t4]) = pack_bf16x2(st[mt][j][2], st[mt][j][3]);
+        *reinterpret_cast<uint32_t*>(&dst[f0 + 16 * mt + g][8 * j + 2 * t4]) = pack_bf16x2(sg * st[mt][j][0], sg * st[mt][j][1]);
+        *reinterpret_cast<uint32_t*>(&dst[f0 + 16 * mt + g + 8][8 * j + 2 * t4]) = pack_bf16x2(sg * st[mt][j][2], sg * st[mt][j][3]);
       }
   };
-  if (qside) store_state_bf16(sm.r);
+  if (qside) store_state_bf16(sm.r, 1.f);
 
   int buf = 0;
   for (int c = c_end - 1; c >= c_begin; --c, buf ^= 1) {
@@ -294,29 +308,18 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
 
     if (qside) {
       // ================================ query side ================================
-      // G rows of this warp straight from global: lane -> (row r0 + lane / 2, 32-column half lane % 2)
-      uint4 od[4], dd[4];
-      float inv = 0.f;
-      {
-        const int row = r0 + (lane >> 1), half = lane & 1;
-        const bool ok = row < valid;
-        const int64_t off = obase + (int64_t)(t0 + (ok ? row : 0)) * ld_out + half * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          od[i] = ok ? __ldg(reinterpret_cast<const uint4*>(out + off) + i) : make_uint4(0, 0, 0, 0);
-          dd[i] = ok ? __ldg(reinterpret_cast<const uint4*>(dout + off) + i) : make_uint4(0, 0, 0, 0);
-        }
-        if (ok) inv = 1.f / __ldg(den_in + ((int64_t)b * Tlen + t0 + row) * H + h);
-      }
       uint32_t ph[8][4];
       phi16(sm.xq[buf], sm.om, r0, valid, ph, sm.pq);
-      {
+      {  // G rows of this warp: lane -> (row r0 + lane / 2, 32-column half lane % 2); rows >= valid are zero tiles
         const int row = r0 + (lane >> 1), half = lane & 1;
+        const float inv = row < valid ? 1.f / sm.den[buf][row] : 0.f;
         float dot = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t* po = reinterpret_cast<const uint32_t*>(&od[i]);
-          const uint32_t* pd = reinterpret_cast<const uint32_t*>(&dd[i]);
+          const uint4 od = *reinterpret_cast<const uint4*>(&sm.ro[buf][row][half * 32 + i * 8]);
+          const uint4 dd = *reinterpret_cast<const uint4*>(&sm.rd[buf][row][half * 32 + i * 8]);
+          const uint32_t* po = reinterpret_cast<const uint32_t*>(&od);
+          const uint32_t* pd = reinterpret_cast<const uint32_t*>(&dd);
           uint4 gq;
           uint32_t* pg = reinterpret_cast<uint32_t*>(&gq);
 #pragma unroll
@@ -429,13 +432,13 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         }
       }
       bar_wait<BAR_R>();                               // the key side is done with r
-      store_state_bf16(sm.r);
+      store_state_bf16(sm.r, 1.f);
     } else {
       // ================================= key side =================================
       uint32_t ph[8][4];
       phi16(sm.xk[buf], sm.om, r0, valid, ph, sm.pk);
       block_bar();                                     // [S2]
-      // S -= phi(k)^T V' (roll back to the start of this chunk): A = -phi(k)^T
+      // (-S) += phi(k)^T V' (roll back to the start of this chunk)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t a[2][4];
@@ -443,8 +446,6 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         for (int mt = 0; mt < 2; ++mt) {
           const int mat = lane >> 3;
           ldsm4t(a[mt], &sm.pk[kk * 16 + (lane & 7) + (mat >> 1) * 8][f0 + 16 * mt + (mat & 1) * 8]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[mt][i] ^= 0x80008000u;
         }
 #pragma unroll
         for (int j = 0; j < 10; j += 2) {
@@ -457,7 +458,7 @@ favor_bwd2_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
           }
         }
       }
-      store_state_bf16(sm.s);
+      store_state_bf16(sm.s, -1.f);
       bar_arrive<BAR_S>();
       uint32_t va[5][4];                               // V' rows of this warp as A fragments
 #pragma unroll

@@ -4,7 +4,9 @@
 # profiles/ by scripts/ncu_traffic.py / scripts/ncu_summary.py.  Numbers printed under ncu are never bench values.
 set -u
 TAG=${1:-r01}
+PARTS=${PARTS:-launches gemm favor}       # which passes to run
 mkdir -p gpurun_out
+if [[ " $PARTS " == *" launches "* ]]; then
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   -c 1400 --csv --log-file gpurun_out/${TAG}_launches_all.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-decode \
   > gpurun_out/${TAG}_ncu_bench.log 2>&1
@@ -21,14 +23,19 @@ w.writerow(hdr[0])
 for r in body:
     if lo <= int(r[0]) <= hi: w.writerow(r)
 PY
+fi
+if [[ " $PARTS " == *" gemm "* ]]; then
 # ncu --set full of every GEMM shape of a layer (12 launches): the raw metric page goes to CSV on the box and the
 # (large) report is dropped -- gpurun brings back at most 64 MiB; one single-kernel report with source is kept
 timeout 900 ncu --set full --clock-control none -k regex:gemm_tc -c 12 -o gpurun_out/${TAG}_gemm_all python scripts/gemm_shapes.py > /dev/null 2>&1
 ncu -i gpurun_out/${TAG}_gemm_all.ncu-rep --page raw --csv > gpurun_out/${TAG}_gemm_shapes_raw.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_gemm_all.ncu-rep
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -s 2 -o gpurun_out/${TAG}_gemm_ffn1 python scripts/gemm_shapes.py > /dev/null 2>&1
-B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
-B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+fi
+if [[ " $PARTS " == *" favor "* ]]; then
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd2?_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd2?_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+fi
 rm -f gpurun_out/${TAG}_launches_all.csv
 du -sh gpurun_out
 ls -la gpurun_out/${TAG}_*
