@@ -18,26 +18,11 @@ import yaml
 from ..decode import Stage2Decoder
 from ..generate import generate_conditional
 from ..synth import synthetic_vocab, synthetic_lead_sheet
+from ..data.formats import load_dictionary, read_lead_sheet, lead_sheet_files, emotions_for
 from . import common
 from .stage2_train import build_model, load_params
 
 MAX_BARS = 128
-
-
-def read_generated_events(events_file, event2idx):
-    events = open(events_file).read().splitlines()
-    key = events[0] if 'Key' in events[0] else 'Key_C'
-    bar_pos = [i for i, e in enumerate(events) if e == 'Bar_None'] + [len(events)]
-    bars = [[event2idx[e] for e in events[bar_pos[b]:bar_pos[b + 1]]] for b in range(len(bar_pos) - 1)]
-    return key, bars
-
-
-def emotions_for(name):
-    for tag, quads in (('Positive', ['Q1', 'Q4']), ('Negative', ['Q2', 'Q3']), ('Q1', ['Q1']), ('Q2', ['Q2']),
-                       ('Q3', ['Q3']), ('Q4', ['Q4']), ('None', ['None'])):
-        if tag in name:
-            return quads
-    raise ValueError('wrong emotion label')
 
 
 def main(argv=None):
@@ -69,12 +54,8 @@ def main(argv=None):
                 with open(path, 'w') as f:
                     print('Key_C', *[idx2event[t] for t in chain(*bars)], sep='\n', file=f)
     else:
-        dl = common.reference_module('stage2_accompaniment', 'dataloader')
-        ut = common.reference_module('stage2_accompaniment', 'utils')
-        dset = dl.REMISkylineToMidiTransformerDataset(
-            conf['data_loader']['data_path'].format(rep), conf['data_loader']['vocab_path'].format(rep),
-            model_dec_seqlen=mc['max_len'], pieces=ut.pickle_load(conf['data_loader']['val_split']), pad_to_same=True)
-        event2idx, idx2event, vocab_size = dset.event2idx, dset.idx2event, dset.vocab_size
+        # the reference builds the validation dataset only to read the vocabulary off it (inference.py:374-381)
+        event2idx, idx2event, vocab_size = load_dictionary(conf['data_loader']['vocab_path'].format(rep))
 
     model = build_model(args.model_type, vocab_size, mc, gpuid)
     temp, top_p = (1.1, 0.99) if args.model_type == "performer" else (1.2, 0.97)
@@ -90,8 +71,7 @@ def main(argv=None):
         print('[info] event->MIDI conversion unavailable (%s); writing token-event text only' % type(e).__name__)
         event_to_midi = None
 
-    tag = 'roman.txt' if rep == 'functional' else '.txt'
-    files = sorted(os.path.join(out_dir, f) for f in os.listdir(out_dir) if tag in f and '_full' not in f)
+    files = lead_sheet_files(out_dir, rep)
     print('[# pieces]', len(files))
     dec = Stage2Decoder(model, batch=1)
     n_tok, t0 = 0, time.time()
@@ -102,7 +82,7 @@ def main(argv=None):
             if os.path.exists(out_txt):
                 print('[info] {} exists, skipping ...'.format(out_txt))
                 continue
-            key, lead = read_generated_events(file, event2idx)
+            key, lead = read_lead_sheet(file, event2idx)
             primer = [event2idx['Emotion_{}'.format(e)]] + ([event2idx[key]] if rep == 'functional' else []) + \
                      [event2idx['Tempo_{}'.format(110)]]
             generated = generate_conditional(model, event2idx, idx2event, lead, primer=primer, max_bars=args.max_bars,
