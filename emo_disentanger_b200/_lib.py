@@ -27,6 +27,7 @@ SIGNATURES = {
     "emo_embed_rows": ([vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, i32, vp], i32),
     "emo_set_pdl": ([i32], None),
     "emo_stage2_batch": ([vp] * 15 + [i32, i32, i32, i32, i32, vp], i32),
+    "emo_stage1_batch": ([vp] * 10 + [i32, i32, i32, vp], i32),
     "emo_performer_decode_step": ([vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32,
                                    vp], i32),
     "emo_embed_bwd": ([vp, vp, i64, i64, vp, vp, vp, i32, i32, i32, f32, f32, u64, i64, i32, vp], i32),

@@ -82,7 +82,59 @@ __global__ void __launch_bounds__(256) stage2_batch_kernel(const BatchArgs a) {
   if (t == 0) a.length[b] = seqlen < T ? seqlen : T;
 }
 
+// Stage-1 (lead-sheet) batches, reference stage1_compose/dataloader.py:408-445,469-520 (__getitem__ with the
+// training configuration: first segment only, no augmentation) + collate_fn :194-255.  The store keeps, per piece,
+// the sample's token sequence (events up to the last registered bar + the closing EOS / Bar token) and the number of
+// positions E its first segment covers; input = tok[0:E], target = tok[1:E+1], truncated / PAD-filled to T; the
+// chord / melody masks classify the TARGET event and are PAD-filled too (the reference pads them with pad_token).
+struct Stage1Args {
+  const int32_t* tokens;
+  const int64_t* piece_off;   // [P + 1]
+  const int32_t* seg_len;     // [P]: E
+  const uint8_t* flags;
+  const int32_t* sel_piece;   // [B]
+  int64_t *inp, *tgt, *chord_idx, *melody_idx, *length;
+  int T, pad;
+};
+
+__global__ void __launch_bounds__(256) stage1_batch_kernel(const Stage1Args a) {
+  const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  const int p = a.sel_piece[b];
+  const int64_t base = a.piece_off[p];
+  const int E = a.seg_len[p];
+  int64_t in = a.pad, tg = a.pad, ch = a.pad, me = a.pad;
+  if (t < E) {
+    in = a.tokens[base + t];
+    tg = a.tokens[base + t + 1];
+    const uint8_t f = a.flags[tg];
+    ch = f & 1;
+    me = (f >> 1) & 1;
+  }
+  const int64_t o = (int64_t)b * a.T + t;
+  a.inp[o] = in;
+  a.tgt[o] = tg;
+  a.chord_idx[o] = ch;
+  a.melody_idx[o] = me;
+  if (t == 0) a.length[b] = E;                           // dec_seg_len: the UNtruncated segment length (:492)
+}
+
 }  // namespace
+
+extern "C" int emo_stage1_batch(const int32_t* tokens, const int64_t* piece_off, const int32_t* seg_len,
+                                const uint8_t* flags, const int32_t* sel_piece, int64_t* dec_inp, int64_t* dec_tgt,
+                                int64_t* inp_chord, int64_t* inp_melody, int64_t* dec_seg_len, int B, int T,
+                                int pad_token, void* stream) {
+  EMO_REQUIRE(B >= 0 && T >= 1, "emo_stage1_batch: need T >= 1");
+  if (B == 0) return EMO_OK;
+  Stage1Args a;
+  a.tokens = tokens; a.piece_off = piece_off; a.seg_len = seg_len; a.flags = flags; a.sel_piece = sel_piece;
+  a.inp = dec_inp; a.tgt = dec_tgt; a.chord_idx = inp_chord; a.melody_idx = inp_melody; a.length = dec_seg_len;
+  a.T = T; a.pad = pad_token;
+  stage1_batch_kernel<<<dim3((T + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(a);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
 
 extern "C" int emo_stage2_batch(const int32_t* tokens, const int64_t* piece_off, const int64_t* bar_off,
                                 const int32_t* mel_start, const int32_t* ch_start, const int32_t* ch_end,

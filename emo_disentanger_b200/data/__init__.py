@@ -1,1 +1,1 @@
-from .token_store import Stage2TokenStore  # noqa: F401
+from .token_store import Stage2TokenStore, Stage1TokenStore  # noqa: F401

@@ -60,6 +60,26 @@ def main(argv=None):
         T = conf['model']['decoder']['tgt_len']
         dloader = SyntheticStage1(vocab_size, dc['batch_size'], T, sy['n_train_batches'], 0)
         vloader = SyntheticStage1(vocab_size, dc['batch_size'], T, sy['n_val_batches'], 10 ** 6)
+    elif dc.get('gpu_token_store'):
+        # pieces tokenised once into HBM, a batch = one kernel launch (data/token_store.py: Stage1TokenStore); same batch
+        # dicts as the reference Dataset + collate_fn, minus the encoder features the loop never reads
+        import pickle
+        from ..data import Stage1TokenStore
+        ddir, vfile = dc['data_dir'].format(rep), dc['vocab_path'].format(rep)
+        mk = lambda split: Stage1TokenStore.from_files(
+            [os.path.join(ddir, p_) for p_ in pickle.load(open(split, 'rb')) if os.path.exists(os.path.join(ddir, p_))], vfile,
+            model_dec_seqlen=conf['model']['decoder']['tgt_len'], device='cuda')
+        dset, vset = mk(dc['train_split']), mk(dc['val_split'])
+        vocab_size = dset.vocab_size
+
+        class _Epochs:                                   # a fresh pass per `for batch in loader`
+            def __init__(self, store, shuffle):
+                self.store, self.shuffle = store, shuffle
+
+            def __iter__(self):
+                return self.store.loader(dc['batch_size'], shuffle=self.shuffle)
+
+        dloader, vloader = _Epochs(dset, True), _Epochs(vset, False)
     else:
         from torch.utils.data import DataLoader
         dl = common.reference_module('stage1_compose', 'dataloader')

@@ -63,6 +63,17 @@ int emo_stage2_batch(const int32_t* tokens, const int64_t* piece_off, const int6
                      int64_t* melody_idx, int64_t* length, int B, int T, int pad_token, int eos_token,
                      int predict_key, void* stream);
 
+/* ---- stage-1 dataset: SkylineFullSongTransformerDataset.__getitem__ + collate_fn -------------------------
+ * stage1_compose/dataloader.py:408-445,469-520,194-255 as train.py:230-262 configures it (first segment of a piece,
+ * no augmentation).  tokens / piece_off: per piece the sample's token sequence (events up to the last registered bar
+ * + the closing EOS / Bar id); seg_len[p] = positions covered by the first segment.  Writes [B, T] int64 dec_inp,
+ * dec_tgt (next token), inp_chord / inp_melody (the TARGET is a Chord_* / Note_* event), all PAD-filled past the
+ * segment, and dec_seg_len [B] (untruncated).  The unused encoder features (enc_*) are not produced. */
+int emo_stage1_batch(const int32_t* tokens, const int64_t* piece_off, const int32_t* seg_len,
+                     const uint8_t* flags, const int32_t* sel_piece, int64_t* dec_inp, int64_t* dec_tgt,
+                     int64_t* inp_chord, int64_t* inp_melody, int64_t* dec_seg_len, int B, int T,
+                     int pad_token, void* stream);
+
 /* ---- A11: the whole per-token step of the stage-2 Performer in ONE kernel --------------------------------
  * stage2_accompaniment/inference.py:252-272 (one model call per generated token).  One thread-block cluster (16
  * CTAs) per sequence: embedding row -> 12 post-LN layers (qkv GEMV, FAVOR+ recurrent step, out-proj + residual, LN,

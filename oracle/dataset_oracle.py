@@ -90,3 +90,94 @@ def synthetic_piece(event2idx, n_bars, rng, lead_len=(3, 9), full_len=(5, 40), a
     if as_dicts:
         ev = [{'name': e.split('_')[0], 'value': '_'.join(e.split('_')[1:])} for e in ev]
     return mel, ch, ev
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stage-1 dataset: SkylineFullSongTransformerDataset as stage1_compose/train.py:230-262 builds it
+# (max_n_seg from the YAML = 1, do_augment=False): one sample = the FIRST segment of a piece.
+#   reference stage1_compose/dataloader.py
+#     :354-384  build_dataset        bar positions: appended marker / trailing empty bar removed, sentinel appended
+#     :386-406  register_segments    first segment = bars [0, b) fitting model_dec_seqlen
+#     :408-445  get_sample_from_file events up to the last registered bar + closing EOS_None / Bar_None
+#     :469-520  get_decoder_input_data   input / shifted target / Chord- and Note-target masks of the segment
+#     :194-255  collate_fn           PAD-fill to model_dec_seqlen (the two masks are PAD-filled as well)
+# The encoder-side features (enc_inp, chroma, groove, masks: :533-608) are never read by train.py and are not restated.
+# Pinned against the unmodified class by tests/golden/make_stage1_dataset_golden.py (tests/golden/stage1_dataset.npz).
+# ---------------------------------------------------------------------------------------------------------
+def stage1_bar_positions(bar_pos, n_events, max_bars):
+    """:354-384 -> (registered bar positions incl. the sentinel, sample closes with EOS (else Bar))"""
+    bp, n = list(bar_pos), n_events
+    if bp[-1] == n:                       # appended bar marker
+        bp = bp[:-1]
+    if n - bp[-1] == 2:                   # trailing empty bar: [Bar_None, EOS_None]
+        n = bp[-1]
+        bp = bp[:-1]
+    if len(bp) <= max_bars:
+        bp.append(n - 1)                  # the position of <EOS>
+    else:
+        bp = bp[:max_bars + 1]
+    return bp, len(bp) <= max_bars        # :431 tests the list WITH the sentinel
+
+
+def stage1_first_segment(bp, seqlen):
+    """:386-406 with the break after the first cut: (start bar, end bar) of segment 0"""
+    for b in range(len(bp) - 1):
+        if bp[b + 1] - bp[0] > seqlen - 1 and b > 0:
+            return 0, b
+    return 0, len(bp) - 1
+
+
+def stage1_sample_tokens(piece_tokens, bp, closes_with_eos, eos_token, bar_token):
+    """:408-437: ids of events[: bp[-1]] + the closing token"""
+    return list(piece_tokens[:bp[-1]]) + [eos_token if closes_with_eos else bar_token]
+
+
+def stage1_assemble(piece_tokens, bar_pos, seqlen, max_bars, pad_token, eos_token, bar_token, is_chord, is_note):
+    """one collated row: dict(dec_inp, dec_tgt, inp_chord, inp_melody [seqlen] int64, dec_seg_len)"""
+    bp, eos = stage1_bar_positions(bar_pos, len(piece_tokens), max_bars)
+    toks = stage1_sample_tokens(piece_tokens, bp, eos, eos_token, bar_token)
+    s, e = stage1_first_segment(bp, seqlen)
+    E = bp[e] - bp[s] + 1                                           # :483-484 (segment offsets are relative to bp[0],
+    inp, tgt = toks[0:E], toks[1:E + 1]                             #           the slices start at token 0)
+    if len(inp) != len(tgt):
+        raise AssertionError("segment runs past the sample (the reference asserts, :512)")
+    seg_len = len(inp)                                              # recorded before truncation (:492)
+    tgt_a = np.asarray(tgt[:seqlen], dtype=np.int64)
+    out = {k: np.full(seqlen, pad_token, dtype=np.int64) for k in ("dec_inp", "dec_tgt", "inp_chord", "inp_melody")}
+    n = len(tgt_a)
+    out["dec_inp"][:n] = inp[:seqlen]
+    out["dec_tgt"][:n] = tgt_a
+    out["inp_chord"][:n] = np.asarray(is_chord)[tgt_a]
+    out["inp_melody"][:n] = np.asarray(is_note)[tgt_a]
+    out["dec_seg_len"] = seg_len
+    return out
+
+
+def synthetic_stage1_piece(rng, n_bars, bar_len=(3, 14), tail="eos", relative=True):
+    """(bar_pos, events) in the stage-1 pickle layout: [Emotion, Key] header, bars of Beat / Chord / Note events.
+    tail: 'eos' (.. EOS), 'empty_bar' (.. Bar, EOS), 'marker' (bar_pos has len(events) appended)."""
+    deg = ('I', 'II', 'III', 'IV', 'V', 'VI', 'VII')
+    ev = [{'name': 'Emotion', 'value': ('Positive', 'Negative')[rng.randint(2)]}, {'name': 'Key', 'value': 'C'}]
+    bar_pos = []
+    for _ in range(n_bars):
+        bar_pos.append(len(ev))
+        ev.append({'name': 'Bar', 'value': None})
+        n, beat = rng.randint(*bar_len), 0
+        while n > 0:
+            ev.append({'name': 'Beat', 'value': beat})
+            ev.append({'name': 'Chord', 'value': '%s_%s' % (deg[rng.randint(7)], ('M', 'm', '7')[rng.randint(3)])})
+            if relative:
+                ev.append({'name': 'Note_Octave', 'value': int(rng.randint(3, 7))})
+                ev.append({'name': 'Note_Degree', 'value': deg[rng.randint(7)]})
+            else:
+                ev.append({'name': 'Note_Pitch', 'value': int(rng.randint(48, 84))})
+            ev.append({'name': 'Note_Duration', 'value': 120 * int(rng.randint(1, 9))})
+            n -= 5
+            beat = min(15, beat + int(rng.randint(1, 5)))
+    if tail == "empty_bar":
+        bar_pos.append(len(ev))
+        ev.append({'name': 'Bar', 'value': None})
+    ev.append({'name': 'EOS', 'value': None})
+    if tail == "marker":
+        bar_pos.append(len(ev))
+    return bar_pos, ev

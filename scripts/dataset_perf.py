@@ -54,3 +54,29 @@ for i, b in zip(idx, bars):
 dt = time.perf_counter() - t0
 print("host : %8.1f us per batch (oracle port, 1 core, events already converted to ids; the reference additionally unpickles "
       "the piece and maps strings per item)  -> %.0fx" % (dt * 1e6, dt * 1e6 / us))
+
+# ---- stage 1 (lead sheets): Stage1TokenStore vs the oracle port of SkylineFullSongTransformerDataset + collate_fn ----
+from emo_disentanger_b200.data import Stage1TokenStore, formats as F
+T1, B1 = int(os.environ.get("T1", 2400)), int(os.environ.get("B1", 64))
+rng = np.random.RandomState(1)
+p1 = [DO.synthetic_stage1_piece(rng, int(rng.randint(20, 160)), bar_len=(10, 40)) for _ in range(256)]
+e2, i2 = F.build_dictionary([ev for _, ev in p1], relative=True, **F.VOCAB_FLAGS["stage1_lead_sheet"])
+s1 = Stage1TokenStore(p1, e2, i2, model_dec_seqlen=T1, device="cuda")
+idx = [int(i) for i in rng.randint(0, len(s1), B1)]
+for _ in range(3):
+    s1.batch(idx)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(n):
+    s1.batch(idx)
+e1.record(); torch.cuda.synchronize()
+us1 = e0.elapsed_time(e1) / n * 1e3
+print("stage-1 GPU : %8.1f us per batch of %d x %d (%.0f GB/s of the 32 B/token written)" % (us1, B1, T1, B1 * T1 * 32 / us1 / 1e3))
+ic, inn = DO.vocab_flags(i2, s1.pad_token)
+tk = [[e2[F.event_name(e)] for e in ev] for _, ev in p1]
+t0 = time.perf_counter()
+for i in idx:
+    DO.stage1_assemble(tk[i], p1[i][0], T1, 192, s1.pad_token, s1.eos_token, s1.bar_token, ic, inn)
+dt = time.perf_counter() - t0
+print("stage-1 host: %8.1f us per batch (oracle port, 1 core, ids pre-converted, decoder side only; the reference also unpickles, "
+      "deep-copies and builds the unused encoder features per item)  -> %.0fx" % (dt * 1e6, dt * 1e6 / us1))

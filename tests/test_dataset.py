@@ -110,3 +110,102 @@ def test_token_store_full_size_vs_oracle_and_loader():
                 assert np.array_equal(batch[k][row].cpu().numpy(), ref[k]), (p, cands[0], k)
             assert int(batch["length"][row]) == ref["length"]
     assert sorted(seen) == list(range(len(pieces)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stage-1 dataset: oracle vs the goldens of the UNMODIFIED SkylineFullSongTransformerDataset +
+# collate_fn (tests/golden/make_stage1_dataset_golden.py), and the GPU token store vs both
+# ------------------------------------------------------------------------------------------------------------
+S1_KEYS = ("dec_inp", "dec_tgt", "inp_chord", "inp_melody")
+
+
+def _s1_pieces(g):
+    i2e = {i: str(n) for i, n in enumerate(g["vocab"].tolist())}
+    e2i = {n: i for i, n in i2e.items()}
+    pieces = [(g["p%d_bar_pos" % p].tolist(), [i2e[t] for t in g["p%d_tokens" % p].tolist()]) for p in range(int(g["n_pieces"]))]
+    return e2i, i2e, pieces
+
+
+def test_stage1_oracle_matches_reference_golden():
+    g = golden("stage1_dataset.npz")
+    e2i, i2e, pieces = _s1_pieces(g)
+    pad = len(e2i)
+    is_chord, is_note = DO.vocab_flags(i2e, pad)
+    for ci, (seqlen, max_bars) in enumerate(g["configs"].tolist()):
+        for p, (bp, ev) in enumerate(pieces):
+            o = DO.stage1_assemble([e2i[e] for e in ev], bp, seqlen, max_bars, pad, e2i["EOS_None"], e2i["Bar_None"], is_chord, is_note)
+            for k in S1_KEYS:
+                assert np.array_equal(o[k], g["c%d_%s_0" % (ci, k)][p]), (ci, p, k)
+            assert o["dec_seg_len"] == int(g["c%d_dec_seg_len_0" % ci][p])
+    # the goldens cover: truncation (segment longer than the window), the max-bars cut (closing Bar instead of EOS)
+    assert (g["c0_dec_seg_len_0"] > 64).any() and (g["c1_dec_tgt_0"] == e2i["Bar_None"]).any()
+
+
+def test_stage1_oracle_edge_cases():
+    bp, eos = DO.stage1_bar_positions([2, 6, 9], 12, 192)
+    assert bp == [2, 6, 9, 11] and eos                                  # sentinel = position of EOS
+    bp, eos = DO.stage1_bar_positions([2, 6, 9, 12], 12, 192)           # appended marker dropped
+    assert bp == [2, 6, 9, 11]
+    bp, eos = DO.stage1_bar_positions([2, 6, 10], 12, 192)              # trailing [Bar, EOS]: the empty bar goes
+    assert bp == [2, 6, 9]
+    bp, eos = DO.stage1_bar_positions([2, 6, 9], 12, 2)                 # more bars than max_bars: cut, closes with Bar
+    assert bp == [2, 6, 9] and not eos
+    assert DO.stage1_first_segment([2, 40, 80, 120], 64) == (0, 1)
+    assert DO.stage1_first_segment([2, 90, 120, 150], 64) == (0, 1)     # a first bar longer than the window still ends at bar 1
+    assert DO.stage1_first_segment([2, 10, 20], 64) == (0, 2)
+    with pytest.raises(AssertionError):                                 # no event before the first bar: the reference asserts
+        DO.stage1_assemble(list(range(8)), [0, 4], 64, 192, 99, 98, 97, np.zeros(100, int), np.zeros(100, int))
+
+
+def test_stage1_token_store_tables_cpu():
+    from emo_disentanger_b200.data import Stage1TokenStore
+    g = golden("stage1_dataset.npz")
+    e2i, i2e, pieces = _s1_pieces(g)
+    for ci, (seqlen, max_bars) in enumerate(g["configs"].tolist()):
+        st = Stage1TokenStore(pieces, e2i, i2e, model_dec_seqlen=seqlen, model_max_bars=max_bars, device="cpu")
+        assert len(st) == len(pieces) and st.pad_token == len(e2i) and st.vocab_size == len(e2i) + 1
+        assert st.seg_len.tolist() == g["c%d_dec_seg_len_0" % ci].tolist()
+        for p, (bp, ev) in enumerate(pieces):
+            rbp, eos = DO.stage1_bar_positions(bp, len(ev), max_bars)
+            assert st.piece_bar_pos[p] == rbp and st.piece_segments[p] == [DO.stage1_first_segment(rbp, seqlen)]
+            a, b = int(st.piece_off[p]), int(st.piece_off[p + 1])
+            assert st.tokens[a:b].tolist() == DO.stage1_sample_tokens([e2i[e] for e in ev], rbp, eos, e2i["EOS_None"], e2i["Bar_None"])
+        with pytest.raises(Exception):
+            st.batch([0])                                               # no CPU path
+    with pytest.raises(ValueError):
+        Stage1TokenStore([([0, 4], ["Bar_None"] * 7 + ["EOS_None"])], e2i, i2e, device="cpu")
+
+
+@pytest.mark.gpu
+def test_stage1_token_store_batches_equal_reference_golden():
+    from emo_disentanger_b200.data import Stage1TokenStore
+    g = golden("stage1_dataset.npz")
+    e2i, i2e, pieces = _s1_pieces(g)
+    for ci, (seqlen, max_bars) in enumerate(g["configs"].tolist()):
+        st = Stage1TokenStore(pieces, e2i, i2e, model_dec_seqlen=seqlen, model_max_bars=max_bars, device="cuda")
+        order = list(range(len(pieces)))[::-1]
+        batch = st.batch(order)                                         # one launch for all pieces
+        for row, p in enumerate(order):
+            for k in S1_KEYS:
+                assert np.array_equal(batch[k + "_0"][row].cpu().numpy(), g["c%d_%s_0" % (ci, k)][p]), (ci, p, k)
+        assert batch["dec_seg_len_0"].tolist() == g["c%d_dec_seg_len_0" % ci][order].tolist()
+        assert batch["id"].tolist() == order and int(max(batch["n_seg"])) == 1
+        assert st.batch([])["dec_inp_0"].shape == (0, seqlen)           # empty batch
+    # reference-sized window through the epoch iterator: every piece once, rows equal to the oracle
+    rng = np.random.RandomState(2)
+    big = [DO.synthetic_stage1_piece(rng, nb, bar_len=(10, 40)) for nb in (3, 40, 150, 260, 17)]
+    from emo_disentanger_b200.data import formats as F
+    e2, i2 = F.build_dictionary([ev for _, ev in big], relative=True, **F.VOCAB_FLAGS["stage1_lead_sheet"])
+    st = Stage1TokenStore(big, e2, i2, model_dec_seqlen=2400, device="cuda")
+    is_chord, is_note = DO.vocab_flags(i2, st.pad_token)
+    seen = []
+    random.seed(1)
+    for batch in st.loader(batch_size=2):
+        for row, p in enumerate(batch["id"].tolist()):
+            seen.append(p)
+            bp, ev = big[p]
+            o = DO.stage1_assemble([e2[F.event_name(e)] for e in ev], bp, 2400, 192, st.pad_token, st.eos_token, st.bar_token, is_chord, is_note)
+            for k in S1_KEYS:
+                assert np.array_equal(batch[k + "_0"][row].cpu().numpy(), o[k]), (p, k)
+            assert int(batch["dec_seg_len_0"][row]) == o["dec_seg_len"]
+    assert sorted(seen) == list(range(len(big)))
