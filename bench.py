@@ -113,7 +113,7 @@ def measured_traffic(kernel_substr):
 
 
 def make_batches(n, B, T, V, seed0, pinned):
-    from oracle.cpu_train import synthetic_batch       # data generator only (shared with the CPU arm)
+    from emo_disentanger_b200.synth import synthetic_batch
     out = []
     for i in range(n):
         tok, seg, tgt = synthetic_batch(V, B, T, seed0 + i)

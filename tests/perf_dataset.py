@@ -1,7 +1,7 @@
 """Stage-2 batch assembly: GPU token store (one launch per batch) vs the reference algorithm on the host (oracle
 port of REMISkylineToMidiTransformerDataset.__getitem__, one item at a time as the DataLoader workers do)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root (oracle/ is test infrastructure: this timing script lives under tests/)
 import numpy as np
 import torch
 from emo_disentanger_b200.data import Stage2TokenStore
