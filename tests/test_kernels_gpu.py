@@ -459,10 +459,12 @@ def test_favor_forward_vs_oracle(ops, dtype, T):
     assert rel_err(state[:, :, :, 64], K.sum(1).float()) < tol
 
 
-@pytest.mark.parametrize("dtype,T", [(torch.float32, 70), (torch.bfloat16, 300)])
-def test_favor_backward_vs_oracle_autograd(ops, dtype, T):
+@pytest.mark.parametrize("dtype,T,B", [(torch.float32, 70, 2), (torch.bfloat16, 300, 2), (torch.bfloat16, 1, 2),
+                                       (torch.bfloat16, 64, 2), (torch.bfloat16, 129, 3),
+                                       (torch.bfloat16, 200, 20)])      # B * H >= SMs: the one-segment plan of the bench
+def test_favor_backward_vs_oracle_autograd(ops, dtype, T, B):
     from oracle import performer_oracle as PO
-    B, H = 2, 8
+    H = 8
     qkv, omega = _favor_inputs(B, T, H, seed=100 + T)
     qkv_d = qkv.to(DEV).to(dtype)
     q, k, v = _split(qkv_d, H)
@@ -481,8 +483,15 @@ def test_favor_backward_vs_oracle_autograd(ops, dtype, T):
     ref.backward(dout.double().view(B, T, H, 64))
     tol = 1e-3 if dtype == torch.float32 else 3e-2      # north-star: 1e-3 rel in the fp32 mode
     d = H * 64
+    scale = float(x.grad[:, :, 2 * d:].float().pow(2).mean().sqrt())
     for i, name in enumerate("qkv"):
-        e = rms_rel(dqkv[:, :, i * d:(i + 1) * d].float(), x.grad[:, :, i * d:(i + 1) * d].float())
+        got, ref = dqkv[:, :, i * d:(i + 1) * d].float().cpu(), x.grad[:, :, i * d:(i + 1) * d].float()
+        if T == 1 and name != "v":
+            # one key: out = v den / (den + eps) whatever q and k are -- the true gradients are ~0 (only the eps term),
+            # a relative error is meaningless; bound the rounding residue against the scale of dv
+            assert float(ref.abs().max()) < 1e-2 * scale and float((got - ref).pow(2).mean().sqrt()) < 2e-2 * scale, name
+            continue
+        e = rms_rel(got, ref)
         assert e < tol, "d%s rms rel err %.3e" % (name, e)
 
 
