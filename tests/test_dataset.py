@@ -209,3 +209,29 @@ def test_stage1_token_store_batches_equal_reference_golden():
                 assert np.array_equal(batch[k + "_0"][row].cpu().numpy(), o[k]), (p, k)
             assert int(batch["dec_seg_len_0"][row]) == o["dec_seg_len"]
     assert sorted(seen) == list(range(len(big)))
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_token_store_loader_shards_an_epoch_across_ranks(stage, monkeypatch):
+    """data parallel (SURVEY 8e): with the `random` module seeded alike, rank r of `world` takes batches r::world of
+    the same shuffled order -- disjoint, and together one full epoch.  Host logic only (batch() is stubbed)."""
+    from emo_disentanger_b200.data import Stage1TokenStore, Stage2TokenStore
+    if stage == 1:
+        g = golden("stage1_dataset.npz")
+        e2i, i2e, pieces = _s1_pieces(g)
+        st = Stage1TokenStore(pieces, e2i, i2e, model_dec_seqlen=64, device="cpu")
+    else:
+        st = _store(golden("dataset_small.npz"), "cpu")
+    monkeypatch.setattr(type(st), "batch", lambda self, idx, *a: list(idx))
+    per_rank = []
+    for r in range(2):
+        random.seed(123)
+        per_rank.append(list(st.loader(batch_size=2, shuffle=True, rank=r, world=2)))
+    random.seed(123)
+    whole = list(st.loader(batch_size=2, shuffle=True))
+    assert whole[0::2] == per_rank[0] and whole[1::2] == per_rank[1]
+    flat = [p for b in whole for p in b]
+    assert sorted(flat) == list(range(len(st))) and all(len(b) <= 2 for b in whole)
+    random.seed(123)
+    dropped = list(st.loader(batch_size=4, shuffle=True, drop_last=True))
+    assert all(len(b) == 4 for b in dropped) and len(dropped) == len(st) // 4
