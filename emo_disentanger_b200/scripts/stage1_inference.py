@@ -1,8 +1,8 @@
 """Stage-1 generation -- the reference's `python3 stage1_compose/inference.py -c CONFIG -r REPR -m MODE [-i PARAMS]
 [-o OUT_DIR] [-n N_GROUPS]` surface (inference.py:86-298): builds the model with mem_len = tgt_len, generates
 one lead sheet per valence (Positive / Negative) per group with t = 1.2, p = 0.97 (lead_sheet) and writes the
-`samp_XX_<Emotion>[_roman].txt` event files stage 2 consumes.  Event->MIDI conversion and the functional
-(roman -> absolute) conversion are the reference's own host-side code when its tree is importable."""
+`samp_XX_<Emotion>[_roman].txt` event files stage 2 consumes, the absolute-pitch `.txt` and the `.mid`
+(tempo 110, block chords under the melody in lead-sheet mode, inference.py:255-283) through `data/midi_out.py`."""
 import argparse
 import os
 import shutil
@@ -12,8 +12,35 @@ import yaml
 
 from ..generate import generate_plain_xl
 from ..synth import synthetic_vocab
-from . import common
+from ..data.formats import load_dictionary, write_events
+from ..data.midi_out import relative_to_absolute, events_to_score, write_midi
 from .stage1_train import build_model
+
+
+def write_lead_sheet_outputs(out_dir, out_name, events, rep, mode):
+    """what the reference leaves per generated piece (inference.py:252-283): `<name>_roman.txt` (functional events),
+    `<name>.txt` (absolute events) and `<name>.mid` (tempo 110; lead-sheet mode adds the block-chord track).
+    events[0] is the emotion primer and is dropped from all three.  Returns the files written."""
+    written = []
+    key = next((e for e in events if 'Key' in e), 'Key_C')
+    if rep == 'functional':
+        write_events(os.path.join(out_dir, out_name + '_roman.txt'), events[1:])
+        written.append(out_name + '_roman.txt')
+        try:
+            events = relative_to_absolute(key, events, keep_conti_chords=False)
+        except (KeyError, TypeError, ValueError) as e:     # random weights: a degree before any octave event, ...
+            print('[info] {}: functional -> absolute conversion failed ({}); roman events only'.format(out_name, type(e).__name__))
+            return written
+    write_events(os.path.join(out_dir, out_name + '.txt'), events[1:])
+    written.append(out_name + '.txt')
+    try:
+        score = events_to_score(key, events[1:], mode=mode, play_chords=(mode == 'lead_sheet'),
+                                enforce_tempos=[(110, 0)] if mode == 'lead_sheet' else None)
+        write_midi(os.path.join(out_dir, out_name + '.mid'), score)
+        written.append(out_name + '.mid')
+    except (ValueError, AssertionError, KeyError) as e:    # e.g. no complete note in the sequence
+        print('[info] {}: no MIDI written ({})'.format(out_name, type(e).__name__))
+    return written
 
 
 def main(argv=None):
@@ -42,9 +69,7 @@ def main(argv=None):
         vocab_size = args.synthetic
         key_determine = None                         # random weights rarely emit a Key_* first
     else:
-        ut = common.reference_module('stage1_compose', 'utils')
-        event2idx, idx2event = ut.pickle_load(conf['data']['vocab_path'].format(rep))
-        vocab_size = len(event2idx) + 1              # + PAD, as stage1 inference.py read_vocab
+        event2idx, idx2event, vocab_size = load_dictionary(conf['data']['vocab_path'].format(rep))   # + PAD (read_vocab)
         key_determine = 'rule'
     tgt_len = conf['model']['decoder']['tgt_len']
     model = build_model(conf, vocab_size, mem_len=tgt_len)
@@ -63,9 +88,7 @@ def main(argv=None):
             if gen_words is None:
                 continue
             events = [idx2event[w] for w in gen_words]
-            suffix = '_roman.txt' if rep == 'functional' else '.txt'
-            with open(os.path.join(out_dir, out_name + suffix), 'w') as f:
-                print(*events[1:], sep='\n', file=f)
+            write_lead_sheet_outputs(out_dir, out_name, events, rep, mode)
             gen_times.append(t_sec)
     if gen_times:
         print('[info] finished generating {} pieces, avg. time: {:.2f} +/- {:.2f} secs.'.format(

@@ -3,9 +3,8 @@
 
 Reads every generated lead sheet (`*_roman.txt` / `*.txt`) in OUT_DIR, decodes one accompaniment per emotion
 quadrant (Positive -> Q1,Q4; Negative -> Q2,Q3) with the reference's sampling constants (performer: t=1.1,
-p=0.99; gpt2: t=1.2, p=0.97) and writes `<name>_<Q>_full.txt` token-event files; when the reference's
-`convert2midi` (+ miditoolkit) is importable the `.mid` is written too (post-processing is out of scope,
-SURVEY 2 C10).  `--synthetic V` runs on a synthetic vocabulary / random lead sheets / random weights."""
+p=0.99; gpt2: t=1.2, p=0.97) and writes `<name>_<Q>_full.txt` token-event files and the `.mid` of the Full track
+(`data/midi_out.py`, inference.py:462-479).  `--synthetic V` runs on a synthetic vocabulary / random lead sheets / random weights."""
 import argparse
 import os
 import shutil
@@ -19,10 +18,24 @@ from ..decode import Stage2Decoder
 from ..generate import generate_conditional
 from ..synth import synthetic_vocab, synthetic_lead_sheet
 from ..data.formats import load_dictionary, read_lead_sheet, lead_sheet_files, emotions_for
-from . import common
+from ..data.midi_out import relative_to_absolute, full_track_bars, events_to_score, write_midi
 from .stage2_train import build_model, load_params
 
 MAX_BARS = 128
+
+
+def write_accompaniment_midi(out_dir, name, key, events, rep, max_bars=MAX_BARS):
+    """the Full-track events of the generated bars -> `<name>.mid` (inference.py:172-208,468-479); False when the
+    sequence holds no complete note (random weights)"""
+    try:
+        absolute = relative_to_absolute(key, events) if rep == 'functional' else events
+        bars = full_track_bars(absolute)
+        score = events_to_score(key, list(chain(*bars[:max_bars])), mode='full')
+        write_midi(os.path.join(out_dir, name + '.mid'), score)
+        return True
+    except (ValueError, AssertionError, KeyError, TypeError) as err:
+        print('[info] {}: no MIDI written ({})'.format(name, type(err).__name__))
+        return False
 
 
 def main(argv=None):
@@ -65,12 +78,6 @@ def main(argv=None):
     model.eval()
     print('[info] model loaded')
     shutil.copy(args.configuration, os.path.join(out_dir, 'config_full.yaml'))
-    try:
-        event_to_midi = common.reference_module('stage2_accompaniment', 'convert2midi').event_to_midi
-    except Exception as e:                                    # miditoolkit / reference tree absent
-        print('[info] event->MIDI conversion unavailable (%s); writing token-event text only' % type(e).__name__)
-        event_to_midi = None
-
     files = lead_sheet_files(out_dir, rep)
     print('[# pieces]', len(files))
     dec = Stage2Decoder(model, batch=1)
@@ -92,11 +99,7 @@ def main(argv=None):
             events = [idx2event[w] for w in generated]
             with open(out_txt, 'w') as f:
                 print(*events, sep='\n', file=f)
-            if event_to_midi is not None and not args.synthetic:
-                inf = common.reference_module('stage2_accompaniment', 'inference')
-                bars = inf.extract_midi_events_from_generation(key, events, relative_melody=(rep == 'functional'))
-                event_to_midi(key, list(chain(*bars[:args.max_bars])), mode='full',
-                              output_midi_path=os.path.join(out_dir, out_name + '_' + e + '_full.mid'))
+            write_accompaniment_midi(out_dir, out_name + '_' + e + '_full', key, events, rep, args.max_bars)
     dt = time.time() - t0
     print('[info] %d events in %.2f s (%.1f events/s incl. grammar rejections and host loop)' % (n_tok, dt, n_tok / max(dt, 1e-9)))
     return 0
