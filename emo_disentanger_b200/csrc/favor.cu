@@ -28,6 +28,9 @@ using namespace FAVOR_NS;
 int emo_favor_fwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
                           int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
                           int nseg, int sc, int B, int T_, int H, cudaStream_t s);       // favor_fwd2.cu
+int emo_favor_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
+                            int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
+                            int nseg, int sc, int B, int T_, int H, cudaStream_t s);     // favor_tc_fwd.cu (tcgen05 + TMA)
 int emo_favor_bwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, const void* out,
                           const void* dout, int64_t ld_out, const float* den, const float* seg_states,
                           const float* seg_rstates, int nseg, int sc, int fwd_nseg, int ratio, void* dq, void* dk, void* dv,
@@ -39,9 +42,21 @@ int emo_favor_bwd2_launch(const void* q, const void* k, const void* v, int64_t l
 #define FAVOR_FWD2_DEFAULT 1
 #endif
 
-struct FavorPlan { int nseg_f, sc_f, nseg_b, sc_b, ratio; };
+// EMO_FAVOR_TC=0: A/B switch from the tcgen05 kernels (128-token chunks) back to the mma.sync ones
+static int g_favor_tc = -1;
+static int favor_tc_enabled() {
+  if (g_favor_tc < 0) { const char* e = getenv("EMO_FAVOR_TC"); g_favor_tc = e ? atoi(e) : 1; }
+  return g_favor_tc;
+}
+extern "C" void emo_favor_set_tc(int on) { g_favor_tc = on ? 1 : 0; }   // test / A-B hook
+
+struct FavorPlan { int nseg_f, sc_f, nseg_b, sc_b, ratio; };   // sc_* in chunks of FavorCfg<T>::C tokens
 template <typename T> static FavorPlan favor_plan(int B, int T_, int H) {
-  constexpr int C = FavorCfg<T>::C;
+  // the plan is made in units of the main kernels' chunk (128 tokens on the tcgen05 path) and handed out in units of
+  // FavorCfg<T>::C, which is what the segment-sum pre-passes and the mma.sync kernels count in
+  constexpr int C0 = FavorCfg<T>::C;
+  const int C = (sizeof(T) == 2 && favor_tc_enabled()) ? 128 : C0;
+  const int unit = C / C0;
   const int nchunk = (T_ + C - 1) / C;
   const int sms = emo_num_sms();
   const int64_t bh = (int64_t)B * H;
@@ -65,6 +80,8 @@ template <typename T> static FavorPlan favor_plan(int B, int T_, int H) {
   p.ratio = p.sc_b / p.sc_f;
   p.nseg_f = (nchunk + p.sc_f - 1) / p.sc_f;
   p.nseg_b = (nchunk + p.sc_b - 1) / p.sc_b;
+  p.sc_f *= unit;
+  p.sc_b *= unit;
   return p;
 }
 
@@ -101,6 +118,8 @@ static int favor_fwd_launch(const void* q, const void* k, const void* v, int64_t
   }
   static int fwd2 = -1;       // EMO_FAVOR_FWD2=0: A/B switch back to the block-GEMM forward
   if (fwd2 < 0) { const char* e = getenv("EMO_FAVOR_FWD2"); fwd2 = e ? atoi(e) : FAVOR_FWD2_DEFAULT; }
+  if (sizeof(T) == 2 && favor_tc_enabled())
+    return emo_favor_fwd_tc_launch(q, k, v, ld, omega, out, ld_out, den, state_in, state_out, seg_states, nseg, (sc + 1) / 2, B, T_, H, s);
   if (sizeof(T) == 2 && fwd2)
     return emo_favor_fwd2_launch(q, k, v, ld, omega, out, ld_out, den, state_in, state_out, seg_states, nseg, sc, B, T_, H, s);
   favor_fwd_kernel<T><<<B * H * nseg, BG_THREADS, smem, s>>>((const T*)q, (const T*)k, (const T*)v, ld, omega, (T*)out, ld_out,

@@ -76,6 +76,7 @@ class FlatModule(nn.Module):
         self._flat_grad = torch.zeros_like(flat)
         self._flat_lp = None
         self._lp_version = -1
+        self.__dict__.pop("_version_params", None)
         for p, shape, off, n in self._named_flat_params():
             p.data = flat[off:off + n].view(shape)
             p.grad = self._flat_grad[off:off + n].view(shape)
@@ -121,7 +122,7 @@ class FlatModule(nn.Module):
         """Flat buffer in the compute dtype (bf16 shadow refreshed when the fp32 masters changed)."""
         if self.compute_dtype == torch.float32:
             return self._flat
-        ver = self._flat._version
+        ver = self._weights_version()
         if self._flat_lp is None or self._flat_lp.device != self._flat.device:
             self._flat_lp = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
             self._lp_version = -1
@@ -130,9 +131,23 @@ class FlatModule(nn.Module):
             self._lp_version = ver
         return self._flat_lp
 
+    def _weights_version(self):
+        """Changes whenever the fp32 masters may have changed.  `_flat._version` alone is not enough: every
+        Parameter is a view bound with `p.data = ...`, which gives it its OWN version counter, so an external
+        optimizer (`torch.optim.Adam.step`) or `load_state_dict` writes `_flat`'s memory without moving
+        `_flat._version`.  The counters only grow, so their sum is a valid key."""
+        ps = self.__dict__.get("_version_params")
+        if ps is None:
+            ps = [p for p, _, _, _ in self._named_flat_params()]
+            self.__dict__["_version_params"] = ps
+        v = self._flat._version
+        for p in ps:
+            v += p._version
+        return v
+
     def mark_lp_fresh(self):
         """The fused optimizer wrote the shadow weights itself."""
-        self._lp_version = self._flat._version
+        self._lp_version = self._weights_version()
 
     def w(self, flatbuf, name_to_slice):
         off, n, shape = name_to_slice
