@@ -21,6 +21,26 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+
+def epoch_batches(n, batch_size, shuffle=True, rank=0, world=1, drop_last=False, seed=None, epoch=0):
+    """The index lists of one epoch for one rank.  Data parallel needs every rank to cut THE SAME permutation and to
+    take THE SAME number of steps (each optimiser step is a collective): with world > 1 the order comes from
+    random.Random(seed + epoch) -- never the process-global `random` state, which differs per rank -- and the batch
+    list is truncated to a multiple of `world`.  world == 1 with seed None keeps the reference behaviour (global
+    `random`, every batch)."""
+    order = list(range(n))
+    if shuffle:
+        if seed is None and world > 1:
+            seed = 0
+        (random if seed is None else random.Random(seed + epoch)).shuffle(order)
+    batches = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    if drop_last and batches and len(batches[-1]) < batch_size:
+        batches.pop()
+    if world > 1:
+        batches = batches[:len(batches) // world * world]
+    return batches[rank::world]
+
+
 class Stage2TokenStore:
     def __init__(self, pieces, event2idx, idx2event, model_dec_seqlen=10240, predict_key=False, device="cuda",
                  piece_ids=None):
@@ -113,16 +133,10 @@ class Stage2TokenStore:
                 'dec_input': out[0], 'dec_target': out[1], 'chords_mhot': 0, 'track_mask': out[2], 'length': length,
                 'chord_idx': out[3], 'melody_idx': out[4]}
 
-    def loader(self, batch_size, shuffle=True, rank=0, world=1, drop_last=False):
+    def loader(self, batch_size, shuffle=True, rank=0, world=1, drop_last=False, seed=None, epoch=0):
         """epoch iterator with the DataLoader(shuffle=True) semantics of train.py:280-285; under data parallel
-        every rank takes the batches rank::world of the same shuffled order (seed the `random` module alike)."""
-        order = list(range(len(self)))
-        if shuffle:
-            random.shuffle(order)
-        batches = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
-        if drop_last and batches and len(batches[-1]) < batch_size:
-            batches.pop()
-        for bi in batches[rank::world]:
+        every rank takes the batches rank::world of the same shuffled order (see epoch_batches)."""
+        for bi in epoch_batches(len(self), batch_size, shuffle, rank, world, drop_last, seed, epoch):
             yield self.batch(bi)
 
 
@@ -221,13 +235,7 @@ class Stage1TokenStore:
                 'dec_inp_0': out[0], 'dec_tgt_0': out[1], 'dec_seg_len_0': length, 'inp_chord_0': out[2],
                 'inp_melody_0': out[3]}
 
-    def loader(self, batch_size, shuffle=True, rank=0, world=1, drop_last=False):
+    def loader(self, batch_size, shuffle=True, rank=0, world=1, drop_last=False, seed=None, epoch=0):
         """DataLoader(shuffle=True) semantics of stage1_compose/train.py:256-262; rank-strided under data parallel"""
-        order = list(range(len(self)))
-        if shuffle:
-            random.shuffle(order)
-        batches = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
-        if drop_last and batches and len(batches[-1]) < batch_size:
-            batches.pop()
-        for bi in batches[rank::world]:
+        for bi in epoch_batches(len(self), batch_size, shuffle, rank, world, drop_last, seed, epoch):
             yield self.batch(bi)

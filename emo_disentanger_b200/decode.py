@@ -48,12 +48,7 @@ class Stage2Decoder:
             self.kv = torch.zeros(L, batch, max_len, 2 * d, dtype=self.dt, device=dev)
             # HF Conv1D stores weights [in, out]; decode keeps [out, in] copies (weights are frozen while
             # generating) so that the one-row-per-sequence step runs the weight-streaming NT kernel
-            Wc = model.weights()
             self.wT = {}
-            for l in range(L):
-                for nm in ("attn.c_attn", "attn.c_proj", "mlp.c_fc", "mlp.c_proj"):
-                    key = "transformer_decoder.%d.%s.weight" % (l, nm)
-                    self.wT[key] = model._wv(Wc, key).t().contiguous()
         # static step buffers (graph inputs / outputs)
         self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and self.is_performer
@@ -88,6 +83,24 @@ class Stage2Decoder:
         self._sampled_host = torch.zeros(2 * batch, dtype=torch.int64).pin_memory()
         self.sample_cfg = None            # (temperature, top_p, greedy) baked into the fused graph
         self.graph_sample = None
+
+    def _sync_weights(self):
+        """Everything that bakes in weight values or addresses (the [out, in] copies of the Conv1D weights, the
+        captured step graphs) is rebuilt when the model's masters changed (load_state_dict, an optimizer step) or
+        its flat buffer moved (`.to()`); called at the top of every public entry point."""
+        m = self.m
+        key = (m._weights_version(), m._flat.data_ptr())
+        if key == getattr(self, "_wkey", None):
+            return
+        self._wkey = key
+        self.graph = None
+        self.graph_sample = None
+        if not self.is_performer:
+            Wc = m.weights()
+            for l in range(m.n_layer):
+                for nm in ("attn.c_attn", "attn.c_proj", "mlp.c_fc", "mlp.c_proj"):
+                    k = "transformer_decoder.%d.%s.weight" % (l, nm)
+                    self.wT[k] = m._wv(Wc, k).t().contiguous()
 
     def reset(self, b=None):
         sl = slice(None) if b is None else slice(b, b + 1)
@@ -179,6 +192,7 @@ class Stage2Decoder:
     @torch.no_grad()
     def append(self, b, tokens, segs):
         """tokens / segs: python lists (or 1-D int64 tensors).  Returns the fp32 logits [V] after the last one."""
+        self._sync_weights()
         m = self.m
         tok = torch.as_tensor(tokens, dtype=torch.int64).view(1, -1).to(self.dev)
         seg = torch.as_tensor(segs, dtype=torch.int64).view(1, -1).to(self.dev) if m.use_segment_emb else None
@@ -238,6 +252,7 @@ class Stage2Decoder:
     def step(self, tokens, segs):
         """tokens / segs: python lists of length B (one new token per sequence). Returns logits [B, V] (fp32,
         a view of a static buffer: consume before the next call)."""
+        self._sync_weights()
         m = self.m
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
@@ -282,6 +297,7 @@ class Stage2Decoder:
         self.logits still holds the step's logits (a rejected draw is re-drawn from them by DeviceSampler)."""
         if not (self.is_performer and self.use_graph):
             raise RuntimeError("step_sample needs the Performer graph path")
+        self._sync_weights()
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
         # banned: uint8 [B, V] device mask of inadmissible tokens (its ADDRESS is baked into the graph; the caller

@@ -67,6 +67,16 @@ class FlatModule(nn.Module):
             self._container(parts[:-1]).register_parameter(parts[-1], nn.Parameter(view))
         self._bind(flat)
 
+    # ---- reference parameter order ------------------------------------------------------------
+    def _ref_order_key(self, name, index):
+        """sort key that turns the registration order into the order of the REFERENCE module's parameters()
+        (torch.optim state dicts are indexed by it); subclasses override where the two differ"""
+        return index
+
+    def reference_param_names(self):
+        names = [name for name, _ in self.named_parameters()]     # module-tree order, as torch enumerates them
+        return [n for _, n in sorted((self._ref_order_key(n, i), n) for i, n in enumerate(names))]
+
     def _named_flat_params(self):
         d = dict(self.named_parameters())
         return [(d[name], shape, off, n) for name, shape, off, n, _ in self._specs]

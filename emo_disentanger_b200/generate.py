@@ -143,10 +143,15 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
             dev = dec.dev
             dec_input = torch.tensor([generated[-MAX_DEC_INP_LEN:]]).long().to(dev)
             dec_seg_inp = torch.tensor([seg_inp[-MAX_DEC_INP_LEN:]]).long().to(dev)
+            prev_omegas = getattr(model, "fixed_omegas", None)
             if dec.is_performer:
                 model.fixed_omegas = dec.omegas
-            with torch.no_grad():
-                logits = model(dec_input, seg_inp=dec_seg_inp, keep_last_only=True).float().contiguous()
+            try:
+                with torch.no_grad():
+                    logits = model(dec_input, seg_inp=dec_seg_inp, keep_last_only=True).float().contiguous()
+            finally:
+                if dec.is_performer:        # later forward / train_step calls redraw the feature map again
+                    model.fixed_omegas = prev_omegas
 
         if predrawn is not None:
             word, predrawn = predrawn, None

@@ -48,23 +48,28 @@ class FusedAdam:
 
     # ---- torch.optim.Adam-format checkpoints (reference optim/ep*_optim.pt) ------------------------
     def state_dict(self):
+        """indexed like torch.optim.Adam over the REFERENCE module's parameters() (FlatModule.reference_param_names):
+        a reference optim/ep*_optim.pt resumes here and a checkpoint written here resumes there"""
         state = {}
-        named = self.model._named_flat_params()
-        order = {id(p): i for i, p in enumerate(self.model.parameters())}
-        for p, shape, off, n in named:
-            state[order[id(p)]] = {"step": torch.tensor(float(self._step)),
-                                   "exp_avg": self._m[off:off + n].view(shape).clone(),
-                                   "exp_avg_sq": self._v[off:off + n].view(shape).clone()}
+        for name, shape, off, n, idx in self._ref_layout():
+            state[idx] = {"step": torch.tensor(float(self._step)),
+                          "exp_avg": self._m[off:off + n].view(shape).clone(),
+                          "exp_avg_sq": self._v[off:off + n].view(shape).clone()}
         pg = dict(self.param_groups[0])
-        return {"state": state, "param_groups": [pg]}
+        return {"state": dict(sorted(state.items())), "param_groups": [pg]}
+
+    def _ref_layout(self):
+        order = {name: i for i, name in enumerate(self.model.reference_param_names())}
+        return [(name, shape, off, n, order[name]) for name, shape, off, n, _ in self.model._specs]
 
     def load_state_dict(self, sd):
-        named = self.model._named_flat_params()
-        order = {id(p): i for i, p in enumerate(self.model.parameters())}
-        for p, shape, off, n in named:
-            st = sd["state"].get(order[id(p)])
+        for name, shape, off, n, idx in self._ref_layout():
+            st = sd["state"].get(idx)
             if st is None:
                 continue
+            if tuple(st["exp_avg"].shape) != tuple(shape):
+                raise ValueError("optimizer state %d has shape %s, parameter %s has %s: not a checkpoint of this "
+                                 "architecture" % (idx, tuple(st["exp_avg"].shape), name, tuple(shape)))
             self._m[off:off + n].view(shape).copy_(st["exp_avg"])
             self._v[off:off + n].view(shape).copy_(st["exp_avg_sq"])
             self._step = int(float(st["step"]))

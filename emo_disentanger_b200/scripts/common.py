@@ -47,8 +47,44 @@ class SyntheticStage2:
         return iter(self.batches)
 
 
+class StoreEpochs:
+    """a fresh pass over a GPU token store per `for batch in loader`: rank-sharded inside the store (no batch is
+    assembled only to be discarded), the epoch's permutation drawn from Random(seed + epoch) so that every rank cuts
+    the same order, the batch count truncated to a multiple of the world size"""
+    rank_sharded = True
+
+    def __init__(self, store, batch_size, shuffle=True, rank=0, world=1, seed=0):
+        self.store, self.bs, self.shuffle, self.rank, self.world, self.seed = store, batch_size, shuffle, rank, world, seed
+        self.epoch = 0
+
+    def __len__(self):
+        n = (len(self.store) + self.bs - 1) // self.bs
+        return n // self.world if self.world > 1 else n
+
+    def __iter__(self):
+        ep, self.epoch = self.epoch, self.epoch + 1
+        return self.store.loader(self.bs, shuffle=self.shuffle, rank=self.rank, world=self.world,
+                                 seed=self.seed if (self.world > 1 or self.seed) else None, epoch=ep)
+
+
 def rank_strided(loader, rank, world):
-    """data parallel: rank r takes batches r, r+world, ..."""
+    """data parallel: rank r takes batches r, r+world, ... of an order every rank iterates alike; the
+    tail that does not fill a round of `world` batches is dropped so that all ranks take the same number of
+    optimiser steps (each one is a collective).  Loaders that shard themselves (StoreEpochs) pass through."""
+    if getattr(loader, "rank_sharded", False) or world == 1:
+        yield from loader
+        return
+    n = len(loader) // world * world
     for i, b in enumerate(loader):
+        if i >= n:
+            break
         if i % world == rank:
             yield b
+
+
+def shared_generator(seed=0):
+    """a torch.Generator for DataLoader(shuffle=True, generator=...): seeded alike on every rank and advanced only by
+    the train loader, so rank 0's extra validation passes do not shift its training permutation"""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g

@@ -72,14 +72,8 @@ def main(argv=None):
         dset, vset = mk(dc['train_split']), mk(dc['val_split'])
         vocab_size = dset.vocab_size
 
-        class _Epochs:                                   # a fresh pass per `for batch in loader`
-            def __init__(self, store, shuffle):
-                self.store, self.shuffle = store, shuffle
-
-            def __iter__(self):
-                return self.store.loader(dc['batch_size'], shuffle=self.shuffle)
-
-        dloader, vloader = _Epochs(dset, True), _Epochs(vset, False)
+        dloader = common.StoreEpochs(dset, dc['batch_size'], True, rank, world, seed=dc.get('seed', 0))
+        vloader = common.StoreEpochs(vset, dc['batch_size'], False)                # rank 0 validates alone
     else:
         from torch.utils.data import DataLoader
         dl = common.reference_module('stage1_compose', 'dataloader')
@@ -90,7 +84,8 @@ def main(argv=None):
             max_pitch=108, min_pitch=48, convert_dict_event=True)
         dset, vset = mk(dc['train_split']), mk(dc['val_split'])
         vocab_size = dset.vocab_size
-        dloader = DataLoader(dset, batch_size=dc['batch_size'], shuffle=True, num_workers=24, collate_fn=dset.collate_fn)
+        dloader = DataLoader(dset, batch_size=dc['batch_size'], shuffle=True, num_workers=24, collate_fn=dset.collate_fn,
+                             generator=common.shared_generator(dc.get('seed', 0)))   # same permutation on every rank
         vloader = DataLoader(vset, batch_size=dc['batch_size'], num_workers=8, collate_fn=vset.collate_fn)
 
     torch.manual_seed(0)

@@ -97,14 +97,8 @@ def main(argv=None):
                                                        model_dec_seqlen=mc['max_len'], predict_key=False, device='cuda:%d' % gpuid)
         dset, vset = mk(dc['train_split']), mk(dc['val_split'])
 
-        class _Epochs:                                   # a fresh shuffled pass per `for batch in loader`
-            def __init__(self, store):
-                self.store = store
-
-            def __iter__(self):
-                return self.store.loader(dc['batch_size'], shuffle=True)
-
-        dloader, vloader = _Epochs(dset), _Epochs(vset)
+        dloader = common.StoreEpochs(dset, dc['batch_size'], True, rank, world, seed=dc.get('seed', 0))
+        vloader = common.StoreEpochs(vset, dc['batch_size'], True)                 # rank 0 validates alone
     else:
         from torch.utils.data import DataLoader
         dl = common.reference_module('stage2_accompaniment', 'dataloader')
@@ -113,8 +107,10 @@ def main(argv=None):
             data_dir=dc['data_path'].format(rep), vocab_file=dc['vocab_path'].format(rep),
             model_dec_seqlen=mc['max_len'], pieces=ut.pickle_load(split), pad_to_same=True, predict_key=False)
         dset, vset = mk(dc['train_split']), mk(dc['val_split'])
-        dloader = DataLoader(dset, batch_size=dc['batch_size'], shuffle=True, num_workers=8)
-        vloader = DataLoader(vset, batch_size=dc['batch_size'], shuffle=True, num_workers=8)
+        dloader = DataLoader(dset, batch_size=dc['batch_size'], shuffle=True, num_workers=8,
+                             generator=common.shared_generator(dc.get('seed', 0)))   # same permutation on every rank
+        vloader = DataLoader(vset, batch_size=dc['batch_size'], shuffle=True, num_workers=8,
+                             generator=common.shared_generator(1))
 
     torch.manual_seed(0)
     model = build_model(args.model_type, dset.vocab_size, mc, gpuid, torch.float32 if args.fp32 else torch.bfloat16)

@@ -81,6 +81,13 @@ class PlainTransformer(FlatModule):
         self._sl = self._slices()
 
     # ---- helpers ---------------------------------------------------------------------------
+    def _ref_order_key(self, name, index):
+        # RelPartialLearnableMultiHeadAttn registers qkv_net, o_net, layer_norm (base class) and then r_net
+        # (optimus_txl_decoder.py:223-240,305-310); here r_net sits next to qkv_net in the flat buffer
+        if ".dec_attn.r_net." in name:
+            return index + 3.5
+        return index
+
     def _wv(self, buf, name):
         off, n, shape = self._sl[name]
         return buf[off:off + n].view(shape)

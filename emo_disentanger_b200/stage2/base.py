@@ -64,6 +64,10 @@ class Stage2Base(FlatModule):
         print('[info] model init completed')
 
     # ---- helpers ---------------------------------------------------------------------------
+    def _ref_order_key(self, name, index):
+        # reference modules create `segemb` last (music_performer.py:23-47, music_gpt2.py:33-62)
+        return (1 if name.startswith("segemb.") else 0, index)
+
     def _wv(self, buf, name):
         off, n, shape = self._sl[name]
         return buf[off:off + n].view(shape)
