@@ -674,7 +674,41 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 tensor: `inner` contiguous elements, `outer` rows of stride ld elements; box {64, box_outer}
+// Descriptor cache ("per-device immutable handles"): a tensor map depends only on (pointer, dims, leading
+// dimension, box), and a training step presents the same few hundred combinations every iteration (the caching
+// allocator hands back the same blocks), so the driver's encode call -- 2 to 4 per GEMM -- is paid once.  Direct
+// mapped, thread-local (no locking; the ABI is re-entrant across threads), keyed by the full tuple.
+struct MapKey { const void* ptr; int64_t inner, outer, ld; int box_outer; int dev; };
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+static int g_map_cache_on = 1;
+static thread_local uint64_t g_map_hits = 0, g_map_misses = 0;
+extern "C" void emo_gemm_map_cache(int on) { g_map_cache_on = on; }           // test / A-B hook
+extern "C" void emo_gemm_map_cache_stats(uint64_t* hits, uint64_t* misses) { *hits = g_map_hits; *misses = g_map_misses; }
+static int make_map_uncached(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer);
 static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  if (!g_map_cache_on) return make_map_uncached(map, ptr, inner, outer, ld, box_outer);
+  constexpr int SLOTS = 2048;
+  static thread_local MapSlot* cache = nullptr;
+  if (!cache) cache = static_cast<MapSlot*>(calloc(SLOTS, sizeof(MapSlot)));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= (uint64_t)inner * 0xC2B2AE3D27D4EB4Full + (uint64_t)outer * 0x165667B19E3779F9ull + (uint64_t)ld * 0x27D4EB2F165667C5ull +
+       (uint64_t)box_outer * 0x85EBCA77C2B2AE63ull + (uint64_t)dev;
+  h ^= h >> 29;
+  MapSlot& s = cache[h & (SLOTS - 1)];
+  if (s.used && s.key.ptr == ptr && s.key.inner == inner && s.key.outer == outer && s.key.ld == ld && s.key.box_outer == box_outer &&
+      s.key.dev == dev) {
+    *map = s.map;
+    ++g_map_hits;
+    return EMO_OK;
+  }
+  ++g_map_misses;
+  int rc = make_map_uncached(map, ptr, inner, outer, ld, box_outer);
+  if (rc == EMO_OK) { s.key = MapKey{ptr, inner, outer, ld, box_outer, dev}; s.map = *map; s.used = true; }
+  return rc;
+}
+static int make_map_uncached(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { emo_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return EMO_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};

@@ -621,3 +621,63 @@ def test_sampler_grammar_mask_equals_rejection_sampling_distribution(ops):
     allb = torch.ones_like(banned)
     ops.sample(logits[:4], V, temp, top_p, u[:4], out[:4], st[:4], banned=allb[:4].contiguous())
     assert st[:4].tolist() == [2, 2, 2, 2]
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: tensor-map cache, tcgen05 FAVOR+ forward against the mma.sync formulation
+# ------------------------------------------------------------------------------------------------
+def test_gemm_tensor_map_cache_hits_and_is_transparent(ops):
+    import ctypes
+    from emo_disentanger_b200 import _lib
+    lib = _lib.lib()
+    x = _bf(torch.randn(512, 512, device=DEV))
+    w = _bf(torch.randn(1024, 512, device=DEV))
+    y0, y1, y2 = (torch.empty(512, 1024, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    lib.emo_gemm_map_cache(0)
+    try:
+        ops.linear_fwd(x, w, y0)
+    finally:
+        lib.emo_gemm_map_cache(1)
+    h0, m0, h1, m1 = (ctypes.c_uint64() for _ in range(4))
+    ops.linear_fwd(x, w, y1)
+    lib.emo_gemm_map_cache_stats(ctypes.byref(h0), ctypes.byref(m0))
+    ops.linear_fwd(x, w, y1)                       # same operands again: every descriptor comes from the cache
+    lib.emo_gemm_map_cache_stats(ctypes.byref(h1), ctypes.byref(m1))
+    assert m1.value == m0.value and h1.value >= h0.value + 3
+    ops.linear_fwd(x, w, y2)                       # a new output pointer: one new descriptor, same result
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    # a different view of the same storage (other dims / leading dimension) must not alias a cached descriptor
+    xs = x[:256]
+    ys = torch.empty(256, 1024, device=DEV, dtype=torch.bfloat16)
+    ops.linear_fwd(xs, w, ys)
+    torch.cuda.synchronize()
+    assert torch.equal(ys, y0[:256])
+
+
+@pytest.mark.parametrize("B,T", [(2, 2048), (3, 333), (74, 256)])
+def test_favor_tcgen05_forward_equals_mma_sync_forward(ops, B, T):
+    """the tcgen05 + TMA forward (128-token chunks, normaliser carried as an fp32 vector) against the round-1
+    mma.sync forward (64-token chunks, normaliser as a bf16 ones column): same math, two independent kernels"""
+    from emo_disentanger_b200 import _lib
+    H = 8
+    qkv, omega = _favor_inputs(B, T, H, scale=0.7, seed=31 + T)
+    qkv_d = _bf(qkv.to(DEV))
+    q, k, v = _split(qkv_d, H)
+    res = []
+    for tc in (1, 0):
+        _lib.lib().emo_favor_set_tc(tc)
+        try:
+            out = torch.empty(B, T, H * 64, device=DEV, dtype=torch.bfloat16)
+            den = torch.empty(B, T, H, device=DEV)
+            ws = ops.favor_workspace(B, T, H, torch.bfloat16, DEV)
+            st = torch.empty(B, H, 128, 80, device=DEV)
+            ops.favor_fwd(q, k, v, omega.to(DEV), out, den, st, seg_states=ws)
+            torch.cuda.synchronize()
+            res.append((out.float(), den.clone(), st.clone(), ws[:, :, -1].clone()))
+        finally:
+            _lib.lib().emo_favor_set_tc(1)
+    (o1, d1, s1, w1), (o0, d0, s0, w0) = res
+    assert rms_rel(o1, o0) < 1e-2 and rms_rel(d1, d0) < 1e-2
+    assert rms_rel(s1, s0) < 1e-4 and rms_rel(w1, s1) < 1e-6          # final prefix state: fp32 accumulation in both
+    assert float(s1[:, :, :, 65:].abs().max()) == 0.0
