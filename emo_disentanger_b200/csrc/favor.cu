@@ -31,6 +31,10 @@ int emo_favor_fwd2_launch(const void* q, const void* k, const void* v, int64_t l
 int emo_favor_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, void* out,
                             int64_t ld_out, float* den, const float* state_in, float* state_out, float* seg_states,
                             int nseg, int sc, int B, int T_, int H, cudaStream_t s);     // favor_tc_fwd.cu (tcgen05 + TMA)
+int emo_favor_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, const void* out,
+                            const void* dout, int64_t ld_out, const float* den, const float* seg_states,
+                            const float* seg_rstates, int nseg, int sc, int fwd_nseg, int ratio, void* dq, void* dk, void* dv,
+                            int64_t ld_d, int B, int T_, int H, cudaStream_t s);     // favor_tc_bwd.cu (tcgen05 + TMA)
 int emo_favor_bwd2_launch(const void* q, const void* k, const void* v, int64_t ld, const float* omega, const void* out,
                           const void* dout, int64_t ld_out, const float* den, const float* seg_states,
                           const float* seg_rstates, int nseg, int sc, int fwd_nseg, int ratio, void* dq, void* dk, void* dv,
@@ -49,6 +53,13 @@ static int favor_tc_enabled() {
   return g_favor_tc;
 }
 extern "C" void emo_favor_set_tc(int on) { g_favor_tc = on ? 1 : 0; }   // test / A-B hook
+// EMO_FAVOR_TC_BWD=0: tcgen05 forward with the mma.sync backward (both read the same 128-token-chunk plan)
+static int g_favor_tc_bwd = -1;
+static int favor_tc_bwd_enabled() {
+  if (g_favor_tc_bwd < 0) { const char* e = getenv("EMO_FAVOR_TC_BWD"); g_favor_tc_bwd = e ? atoi(e) : 1; }
+  return g_favor_tc_bwd;
+}
+extern "C" void emo_favor_set_tc_bwd(int on) { g_favor_tc_bwd = on ? 1 : 0; }
 
 struct FavorPlan { int nseg_f, sc_f, nseg_b, sc_b, ratio; };   // sc_* in chunks of FavorCfg<T>::C tokens
 template <typename T> static FavorPlan favor_plan(int B, int T_, int H) {
@@ -152,6 +163,9 @@ static int favor_bwd_launch(const void* q, const void* k, const void* v, int64_t
   }
   static int bwd2 = -1;       // EMO_FAVOR_BWD2=0/1: A/B switch between the block-GEMM and the register-resident backward
   if (bwd2 < 0) { const char* e = getenv("EMO_FAVOR_BWD2"); bwd2 = e ? atoi(e) : FAVOR_BWD2_DEFAULT; }
+  if (sizeof(T) == 2 && favor_tc_enabled() && favor_tc_bwd_enabled())
+    return emo_favor_bwd_tc_launch(q, k, v, ld, omega, out, dout, ld_out, den, seg_states, seg_rstates, nseg, sc / 2, pl.nseg_f, pl.ratio,
+                                   dq, dk, dv, ld_d, B, T_, H, s);
   if (sizeof(T) == 2 && bwd2)
     return emo_favor_bwd2_launch(q, k, v, ld, omega, out, dout, ld_out, den, seg_states, seg_rstates, nseg, sc, pl.nseg_f, pl.ratio,
                                  dq, dk, dv, ld_d, B, T_, H, s);

@@ -42,7 +42,7 @@ struct Params {
   const float* state_in;
   float* state_out;
   float* seg_states;
-  int nseg, seg_chunks, T, H, items;
+  int nseg, seg_chunks, T, H, items, omega_f16;
 };
 
 __global__ void __launch_bounds__(NT, 2)
@@ -65,18 +65,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), T_COLS);
   // Omega * 64^(-1/4) * log2(e) -> bf16 [e][f] (f contiguous): the MN-major B operand of batch 1
-  {
-    const float sc = 0.35355339059327373f * K2;
-    for (int i = tid; i < FE * 8; i += NT) {
-      const int e = i >> 3, c = i & 7;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.omega + e * FE + c * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.omega + e * FE + c * 8 + 4));
-      uint4 t;
-      t.x = pack_bf16x2(w0.x * sc, w0.y * sc); t.y = pack_bf16x2(w0.z * sc, w0.w * sc);
-      t.z = pack_bf16x2(w1.x * sc, w1.y * sc); t.w = pack_bf16x2(w1.z * sc, w1.w * sc);
-      sts128(sOM + sw128(e, c), t);
-    }
-  }
+  stage_omega(p.omega, sOM, tid, NT, p.omega_f16 != 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -84,7 +73,8 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem = *tmem_slot;
   const uint32_t tl = tmem + ((uint32_t)(warp & 3) << 21);   // this warp's lane quadrant: (32 * warp) << 16
 
-  constexpr uint32_t ID_U = make_idesc(64, false, true), ID_S = make_idesc(128, false, false),
+  const uint32_t ID_U = p.omega_f16 ? make_idesc(64, false, true, 128, true, false) : make_idesc(64, false, true);
+  constexpr uint32_t ID_S = make_idesc(128, false, false),
                      ID_O = make_idesc(64, false, true), ID_ST = make_idesc(64, true, true);
   uint32_t ph_qk = 0, ph_v = 0, ph_mma = 0, ph_xf = 0;   // parities of the next completion each role waits for
 
@@ -423,7 +413,7 @@ int emo_favor_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t
   if ((rc = make_map_bt(&mv, v, (int64_t)H * FE, T_, B, ld, C))) return rc;
   Params p;
   p.out = (bf16*)out; p.ld_out = ld_out; p.den_out = den; p.omega = omega; p.state_in = state_in; p.state_out = state_out;
-  p.seg_states = seg_states; p.nseg = nseg; p.seg_chunks = sc; p.T = T_; p.H = H; p.items = B * H * nseg;
+  p.seg_states = seg_states; p.nseg = nseg; p.seg_chunks = sc; p.T = T_; p.H = H; p.items = B * H * nseg; p.omega_f16 = favor_omega_f16();
   const int max_ctas = 2 * emo_num_sms();
   const int grid = p.items < max_ctas ? p.items : max_ctas;
   favor_fwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, p);

@@ -5,6 +5,8 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace tcp {
 
@@ -137,9 +139,38 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m = 128) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+// a_bf16 / b_bf16: operand formats (1 = bf16, 0 = fp16; the two may differ: the descriptor carries one field each)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m = 128, bool a_bf16 = true, bool b_bf16 = true) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// Omega' = Omega * 64^(-1/4) * log2(e) -> 16-bit [e][f] tile (128B swizzle).  fp16 (|Omega'| < 4, 11-bit significand)
+// keeps the feature-map exponents 8x closer to the fp32 oracle than bf16 does; x stays bf16 (mixed-format MMA).
+__device__ __forceinline__ void stage_omega(const float* omega, uint32_t tile, int tid, int nthreads, bool f16) {
+  const float sc = 0.35355339059327373f * 1.4426950408889634f;
+  for (int i = tid; i < 64 * 8; i += nthreads) {
+    const int e = i >> 3, c = i & 7;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(omega + e * 64 + c * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(omega + e * 64 + c * 8 + 4));
+    uint4 t;
+    if (f16) {
+      t.x = pack_f16x2(w0.x * sc, w0.y * sc); t.y = pack_f16x2(w0.z * sc, w0.w * sc);
+      t.z = pack_f16x2(w1.x * sc, w1.y * sc); t.w = pack_f16x2(w1.z * sc, w1.w * sc);
+    } else {
+      t.x = pack_bf16x2(w0.x * sc, w0.y * sc); t.y = pack_bf16x2(w0.z * sc, w0.w * sc);
+      t.z = pack_bf16x2(w1.x * sc, w1.y * sc); t.w = pack_bf16x2(w1.z * sc, w1.w * sc);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)(e * 128 + ((c ^ (e & 7)) << 4))), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+  }
+}
+static inline int favor_omega_f16() {            // EMO_FAVOR_OMEGA_F16=0: bf16 Omega' (A/B)
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EMO_FAVOR_OMEGA_F16"); on = e ? atoi(e) : 1; }
+  return on;
 }
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] tile with the 128B swizzle (TMA / UMMA layout)
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }

@@ -31,11 +31,14 @@ def _model(dtype, seed=11):
     return m, sd, om, tok, seg
 
 
-def _oracle_rows(sd, om, tok, seg, rows):
+def _oracle_rows(sd, om, tok, seg, rows, taps_out=None):
     outs = []
     for r in rows:
+        taps = []
         with torch.no_grad():
-            outs.append(PO.performer_forward(sd, tok[r:r + 1], seg[r:r + 1], [om[l] for l in range(L)], L, H, 512))
+            outs.append(PO.performer_forward(sd, tok[r:r + 1], seg[r:r + 1], [om[l] for l in range(L)], L, H, 512, taps=taps))
+        if taps_out is not None:
+            taps_out.append(taps[-1])            # output of the last layer = the final hidden state
     return torch.cat(outs, 0)
 
 
@@ -58,19 +61,18 @@ def test_fp32_logits_at_bench_config_vs_oracle():
 def test_bf16_hidden_and_logits_at_bench_config_vs_oracle():
     m, sd, om, tok, seg = _model(torch.bfloat16)
     rows = [0, BB - 1]
-    ref = _oracle_rows(sd, om, tok, seg, rows)
+    ref_h = []
+    ref = _oracle_rows(sd, om, tok, seg, rows, ref_h)
     with torch.no_grad():
         hid, _ = m._forward_hidden(tok.cuda(), seg.cuda(), save=False)
         out = m(tok.cuda(), seg_inp=seg.cuda())
     got = torch.stack([out[0], out[BB - 1]]).float().cpu()
     assert torch.isfinite(out.float()).all()
     assert rms_rel(got, ref) < 2e-2
-    # hidden states: the oracle's last hidden state = logits pre-projection; recompute it from the oracle's state dict
-    W, b = sd["dec_out_proj.weight"].double(), sd["dec_out_proj.bias"].double()
     hid = hid.view(BB, T, 512)
-    got_h = torch.stack([hid[0], hid[BB - 1]]).double().cpu()
-    # project our bf16 hidden states with the fp64 oracle weights: the comparison isolates the hidden-state error
-    assert rms_rel((got_h @ W.t() + b).float(), ref) < 1e-2   # north-star tolerance on bf16 hidden states
+    got_h = torch.stack([hid[0], hid[BB - 1]]).float().cpu()
+    e = rms_rel(got_h, torch.cat(ref_h, 0))
+    assert e < 1e-2, "bf16 hidden states after 12 layers: rms rel err %.3e" % e     # north-star tolerance
     # rows that share a sequence share the result, wherever they sit in the batch (multi-wave / multi-segment plan)
     tok2, seg2 = tok.clone(), seg.clone()
     tok2[37], seg2[37] = tok[0], seg[0]
