@@ -1,14 +1,12 @@
 // FAVOR+ backward on the 5th-gen tensor cores (bf16, sm_100a): every product of the reverse pass is a tcgen05.mma with
 // its accumulator in TMEM; q / k / v / out / dout chunks are staged by TMA (128B swizzle).  Same math, interface and
-// workspace layout as favor_bwd2_kernel (mma.sync), which stays as the A/B switch EMO_FAVOR_TC=0.
+// workspace layout as favor_bwd2_kernel (mma.sync), which stays as the A/B switch EMO_FAVOR_TC_BWD=0.
 //
 // Backward of fast_transformers CausalLinearAttention + Favor (causal_dot_product's backward and the feature map's),
 // stage2_accompaniment/model/fast_transformer_decoder.py:28-38.
 //
-// One CTA per SM walks one (batch, head, segment) in REVERSE in chunks of 128 tokens.  8 worker warps in two groups --
-// the query side (warps 0-3, thread = query row i = TMEM lane) and the key side (warps 4-7, thread = key row j) --
-// and one control warp (TMA + MMA issue).  With G = dout / den, gd = -(dout . out) / den (the normaliser's gradient),
-// P = phi(q) phi(k)^T and dP_ij = G_i . v_j + gd_i (both causal), per chunk:
+// One CTA per SM walks one (batch, head, segment) in REVERSE in chunks of 128 tokens.  With G = dout / den,
+// gd = -(dout . out) / den (the normaliser's gradient), P = phi(q) phi(k)^T and dP_ij = G_i . v_j + gd_i (both causal):
 //
 //   d phi(q) = dP phi(k) + G S_prev^T + gd z_prev^T          S_prev, z_prev: prefix state before the chunk
 //   d phi(k) = dP^T phi(q) + V R^T + 1 rz^T                  R = sum_{later} phi(q)^T G, rz = sum_{later} gd phi(q)
@@ -22,6 +20,12 @@
 // bf16 written in place over their fp32 accumulators); d U_q / d U_k are TMEM A operands too.
 // TMEM (512 columns): R [0,64) | -S [64,128) | W1 [128,256) | W0 [256,384) | W2 [384,512); each W holds a 128-column
 // score tile, then its packed copy in the low 64 columns and a 64-column accumulator ("hole") in the high ones.
+//
+// Threads: 8 worker warps + 1 control warp (TMA + MMA issue).  A worker thread is (g, r): r = TMEM lane = row of
+// every tile, g = which HALF of the tile's columns it handles -- both warp groups work on every tile of every phase
+// (the kernel is bound by instruction issue on the element-wise passes, not by the tensor pipe), through one code
+// path.  Four CTA-wide barriers per chunk separate the five MMA batches; inside a phase the workers consume the
+// batch's results in the order the control warp commits them, so tensor-core time hides behind the previous tile.
 #include "tc_ptx.cuh"
 
 namespace favor3b {
@@ -33,24 +37,28 @@ constexpr uint32_t TILE = 16384;
 constexpr uint32_t OFF_XQ = 0, OFF_XK = TILE, OFF_XV = 2 * TILE /* x2 */, OFF_XO = 4 * TILE, OFF_XD = 5 * TILE, OFF_PQ = 6 * TILE /* x2 */,
                    OFF_PK = 8 * TILE /* x2 */, OFF_G = 10 * TILE, OFF_SB = 11 * TILE, OFF_RB = 12 * TILE, OFF_OM = 13 * TILE /* 8 KB */,
                    OFF_VEC = 13 * TILE + 8192;
-// fp32 vectors: z[128] rz[2][128] gd[128] part[8][128]
-constexpr uint32_t V_Z = 0, V_RZ = 512, V_GD = 1536, V_PART = 2048, VEC_BYTES = 2048 + 4096;
+// fp32 vectors: z[128] rz[2][128] gd[128] sp[2][2][128] part[8][128]
+constexpr uint32_t V_Z = 0, V_RZ = 512, V_GD = 1536, V_SP = 2048, V_PART = 4096, VEC_BYTES = 4096 + 4096;
 constexpr uint32_t OFF_BAR = OFF_VEC + VEC_BYTES, SMEM_USED = OFF_BAR + 256;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
 constexpr uint32_t T_R = 0, T_NS = 64, T_W1 = 128, T_W0 = 256, T_W2 = 384, T_COLS = 512;
 
-// barriers (8 bytes each, from OFF_BAR)
-enum { B_XQK = 0, B_OD, B_V0, B_V1, F_X, F_OD, M_U, M_NS, M_C2, M_C13, M_E1, M_E2, M_G, M_DXQ, M_R, M_DXK, N_BARS };
-
+// mbarriers (8 bytes each, from OFF_BAR)
+enum { B_XQK = 0, B_OD, B_V0, B_V1, F_X, F_OD, M_U, M_C1, M_C2, M_C3, M_NS, M_E1, M_E2, M_DXQ, M_G, M_R, M_DXK, N_BARS };
+// named barriers: 1 = whole CTA (phase boundaries), 2 = group 1 only, 3..5 = load/store hand-over of the three masked
+// tiles (group 0 arrives, group 1 waits), 6 = all workers
 struct Params {
   const bf16* q; const bf16* k; int64_t ld;
   const float* omega; const float* den;
   const float* seg_states; const float* seg_rstates;
   bf16* dq; bf16* dk; bf16* dv; int64_t ld_d;
-  int nseg, seg_chunks, fwd_nseg, ratio, T, H, items, omega_f16;
+  int nseg, seg_chunks, fwd_nseg, ratio, T, H, items;
 };
 
+template <int ID> __device__ __forceinline__ void named_bar_arrive(int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
+}
 // 32 fp32 accumulator values -> 4 swizzled 16-byte chunks (chunks c0 .. c0 + 3 of row `row`)
 __device__ __forceinline__ void pack_row32(uint32_t tile, int row, int c0, const uint32_t (&r)[32], float scale) {
 #pragma unroll
@@ -76,7 +84,7 @@ __device__ __forceinline__ float row_sumsq(uint32_t tile, int row) {
 }
 // phi of one row: U (64 fp32 columns at tmem address `tu`) -> bf16 [token][feature] tile (two 16 KB blocks: exp(+u - o) | exp(-u - o))
 __device__ __forceinline__ void phi_row_to_smem(uint32_t tu, uint32_t tile, int row, float o) {
-#pragma unroll
+#pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     uint32_t r[32];
     tmem_ld32_issue(tu + half * 32, r);
@@ -97,15 +105,17 @@ __device__ __forceinline__ void phi_row_to_smem(uint32_t tu, uint32_t tile, int 
     }
   }
 }
-// column sums over the 128 token rows of a [token][128 features] tile, optionally weighted per row: 128 threads,
-// thread t -> 16-byte chunk column (t & 15) of the two blocks, 16 rows (t >> 4); partial sums to part[8][128]
+// column sums over the 128 token rows of a [token][128 features] tile, optionally weighted per row; NTH = 128 or 256
+// threads.  thread t -> 16-byte chunk column (t & 15) of the two blocks, 128 * 16 / NTH rows; partial sums to part[8][128]
+template <int NTH>
 __device__ __forceinline__ void colsum_partial(uint32_t tile, int t, const float* w, float* part) {
+  constexpr int ROWS = 128 * 16 / NTH;
   const int cc = t & 15, blk = cc >> 3, c = cc & 7, rg = t >> 4;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll 4
-  for (int r = rg * 16; r < rg * 16 + 16; ++r) {
+  for (int r = rg * ROWS; r < rg * ROWS + ROWS; ++r) {
     const uint4 a = lds128(tile + blk * TILE + sw128(r, c));
     const float wr = w ? w[r] : 1.f;
     float f0, f1;
@@ -114,7 +124,14 @@ __device__ __forceinline__ void colsum_partial(uint32_t tile, int t, const float
     unpack_bf16x2(a.z, f0, f1); acc[4] += wr * f0; acc[5] += wr * f1;
     unpack_bf16x2(a.w, f0, f1); acc[6] += wr * f0; acc[7] += wr * f1;
   }
-  float4* dst = reinterpret_cast<float4*>(part + rg * 128 + blk * 64 + c * 8);
+  int slot = rg;
+  if (NTH == 256) {                        // lanes l and l ^ 16 hold the same chunk column, adjacent row groups
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    slot = rg >> 1;
+    if (t & 16) return;
+  }
+  float4* dst = reinterpret_cast<float4*>(part + slot * 128 + blk * 64 + c * 8);
   dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
@@ -125,67 +142,101 @@ __device__ __forceinline__ float part_total(const float* part, int f) {
   return s;
 }
 
-// d phi (two 64-column accumulators: features 0..63 at tp, 64..127 at tm) of this thread's row -> du (packed bf16,
-// 32 words) and the coefficient of x:   w = (d phi + coef * vec) * phi ;  du = w+ - w- ;  cx = -sum(w) * s^2
-__device__ __forceinline__ void dphi_row(uint32_t tp, uint32_t tm, uint32_t phi_tile, int row, const float* vec, float coef,
-                                         uint32_t (&du)[32], float& cx) {
-  float s0 = 0.f, s1 = 0.f;
-  const float4* v4 = reinterpret_cast<const float4*>(vec);
+// One masked score tile of the chunk: this thread's two 32-column pieces (2 g, 2 g + 1) of row r -> packed bf16 written
+// in place over the tile's low columns [32 g, 32 g + 32).  MODE 0: keep col >= row (P^T); MODE 1: + gd of the row, keep
+// col <= row (dP); MODE 2: + gd of the column, keep col >= row (dP^T).  Group 1's packed words land on fp32 columns
+// that belong to group 0's pieces, hence the arrive / wait hand-over between load and store.
+template <int MODE, int BAR>
+__device__ __forceinline__ void mask_tile(uint32_t tt, int g, int wq, int r, float gdr, const float* gd) {
+  uint32_t pk[32];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {          // features 32 half .. 32 half + 31 of both signs
-    uint32_t rp[32], rm[32];
-    tmem_ld32_issue(tp + half * 32, rp);
-    tmem_ld32_issue(tm + half * 32, rm);
-    tmem_ld_wait();
+  for (int pp = 0; pp < 2; ++pp) {
+    const int pc = 2 * g + pp;
+    const bool needed = (MODE == 1) ? (pc <= wq) : (pc >= wq);           // warp-uniform
+    if (needed) {
+      uint32_t v[32];
+      tmem_ld32_issue(tt + pc * 32, v);
+      tmem_ld_wait();
+      const bool diag = pc == wq;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const uint4 php = lds128(phi_tile + sw128(row, half * 4 + cc)), phm = lds128(phi_tile + TILE + sw128(row, half * 4 + cc));
-      const float4 vpa = v4[half * 8 + 2 * cc], vpb = v4[half * 8 + 2 * cc + 1];
-      const float4 vma = v4[16 + half * 8 + 2 * cc], vmb = v4[16 + half * 8 + 2 * cc + 1];
-      const uint32_t pw[4] = {php.x, php.y, php.z, php.w}, mw[4] = {phm.x, phm.y, phm.z, phm.w};
-      const float vp[8] = {vpa.x, vpa.y, vpa.z, vpa.w, vpb.x, vpb.y, vpb.z, vpb.w};
-      const float vm[8] = {vma.x, vma.y, vma.z, vma.w, vmb.x, vmb.y, vmb.z, vmb.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float p0, p1, m0, m1;
-        unpack_bf16x2(pw[e], p0, p1);
-        unpack_bf16x2(mw[e], m0, m1);
-        const float wp0 = (__uint_as_float(rp[8 * cc + 2 * e]) + coef * vp[2 * e]) * p0;
-        const float wp1 = (__uint_as_float(rp[8 * cc + 2 * e + 1]) + coef * vp[2 * e + 1]) * p1;
-        const float wm0 = (__uint_as_float(rm[8 * cc + 2 * e]) + coef * vm[2 * e]) * m0;
-        const float wm1 = (__uint_as_float(rm[8 * cc + 2 * e + 1]) + coef * vm[2 * e + 1]) * m1;
-        s0 += wp0 + wm0;
-        s1 += wp1 + wm1;
-        du[half * 16 + cc * 4 + e] = pack_bf16x2(wp0 - wm0, wp1 - wm1);
+      for (int q = 0; q < 16; ++q) {
+        float a0 = __uint_as_float(v[2 * q]), a1 = __uint_as_float(v[2 * q + 1]);
+        const int c0 = pc * 32 + 2 * q;
+        if (MODE == 1) { a0 += gdr; a1 += gdr; }
+        if (MODE == 2) { const float2 gq = *reinterpret_cast<const float2*>(gd + c0); a0 += gq.x; a1 += gq.y; }
+        if (diag) {
+          if (MODE == 1) { a0 = c0 <= r ? a0 : 0.f; a1 = c0 + 1 <= r ? a1 : 0.f; }
+          else { a0 = c0 >= r ? a0 : 0.f; a1 = c0 + 1 >= r ? a1 : 0.f; }
+        }
+        pk[pp * 16 + q] = pack_bf16x2(a0, a1);
       }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pk[pp * 16 + q] = 0u;
     }
   }
-  cx = -(s0 + s1) * F_S2;
+  tc_fence_before();
+  if (g == 0) named_bar_arrive<BAR>(256);
+  else named_bar_sync<BAR>(256);
+  tc_fence_after();
+  tmem_st32(tt + g * 32, pk);
 }
-// dx row = acc(64 columns at `ta`) * ln2 + cx * x  -> global (16-byte stores); x row re-read from global (L2)
-__device__ __forceinline__ void dx_row_out(uint32_t ta, const bf16* xrow, bf16* drow, float cx, bool ok) {
-  uint4 xv[8];
+
+// d phi of this thread's row, features [32 g, 32 g + 32) of both signs (accumulators at tp + 32 g / tm + 32 g):
+//   w = (d phi + coef * vec) * phi ;  du = w+ - w- -> 16 packed words ;  returns sum(w) (partial over the 64 features)
+__device__ __forceinline__ float dphi_half(uint32_t tp, uint32_t tm, uint32_t phi_tile, int row, int g, const float* vec, float coef,
+                                           uint32_t (&du)[16]) {
+  float s0 = 0.f, s1 = 0.f;
+  const float4* v4 = reinterpret_cast<const float4*>(vec);
+  uint32_t rp[32], rm[32];
+  tmem_ld32_issue(tp + g * 32, rp);
+  tmem_ld32_issue(tm + g * 32, rm);
+  tmem_ld_wait();
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const uint4 php = lds128(phi_tile + sw128(row, g * 4 + cc)), phm = lds128(phi_tile + TILE + sw128(row, g * 4 + cc));
+    const float4 vpa = v4[g * 8 + 2 * cc], vpb = v4[g * 8 + 2 * cc + 1];
+    const float4 vma = v4[16 + g * 8 + 2 * cc], vmb = v4[16 + g * 8 + 2 * cc + 1];
+    const uint32_t pw[4] = {php.x, php.y, php.z, php.w}, mw[4] = {phm.x, phm.y, phm.z, phm.w};
+    const float vp[8] = {vpa.x, vpa.y, vpa.z, vpa.w, vpb.x, vpb.y, vpb.z, vpb.w};
+    const float vm[8] = {vma.x, vma.y, vma.z, vma.w, vmb.x, vmb.y, vmb.z, vmb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float p0, p1, m0, m1;
+      unpack_bf16x2(pw[e], p0, p1);
+      unpack_bf16x2(mw[e], m0, m1);
+      const float wp0 = (__uint_as_float(rp[8 * cc + 2 * e]) + coef * vp[2 * e]) * p0;
+      const float wp1 = (__uint_as_float(rp[8 * cc + 2 * e + 1]) + coef * vp[2 * e + 1]) * p1;
+      const float wm0 = (__uint_as_float(rm[8 * cc + 2 * e]) + coef * vm[2 * e]) * m0;
+      const float wm1 = (__uint_as_float(rm[8 * cc + 2 * e + 1]) + coef * vm[2 * e + 1]) * m1;
+      s0 += wp0 + wm0;
+      s1 += wp1 + wm1;
+      du[cc * 4 + e] = pack_bf16x2(wp0 - wm0, wp1 - wm1);
+    }
+  }
+  return s0 + s1;
+}
+// columns [32 g, 32 g + 32) of a dx row = acc * ln2 + cx * x  -> global (16-byte stores); x re-read from global (L2)
+__device__ __forceinline__ void dx_half_out(uint32_t ta, const bf16* xrow, bf16* drow, int g, float cx, bool ok) {
+  uint4 xv[4];
   if (ok) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) xv[c] = __ldg(reinterpret_cast<const uint4*>(xrow) + c);
+    for (int c = 0; c < 4; ++c) xv[c] = __ldg(reinterpret_cast<const uint4*>(xrow) + g * 4 + c);
   }
+  uint32_t r[32];
+  tmem_ld32_issue(ta + g * 32, r);
+  tmem_ld_wait();
+  if (ok) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t r[32];
-    tmem_ld32_issue(ta + half * 32, r);
-    tmem_ld_wait();
-    if (ok) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const uint4 xx = xv[half * 4 + cc];
-        float x0, x1;
-        uint4 t;
-        unpack_bf16x2(xx.x, x0, x1); t.x = pack_bf16x2(__uint_as_float(r[8 * cc + 0]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 1]) * KINV + cx * x1);
-        unpack_bf16x2(xx.y, x0, x1); t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 3]) * KINV + cx * x1);
-        unpack_bf16x2(xx.z, x0, x1); t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 5]) * KINV + cx * x1);
-        unpack_bf16x2(xx.w, x0, x1); t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 7]) * KINV + cx * x1);
-        *(reinterpret_cast<uint4*>(drow) + half * 4 + cc) = t;
-      }
+    for (int cc = 0; cc < 4; ++cc) {
+      const uint4 xx = xv[cc];
+      float x0, x1;
+      uint4 t;
+      unpack_bf16x2(xx.x, x0, x1); t.x = pack_bf16x2(__uint_as_float(r[8 * cc + 0]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 1]) * KINV + cx * x1);
+      unpack_bf16x2(xx.y, x0, x1); t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 3]) * KINV + cx * x1);
+      unpack_bf16x2(xx.z, x0, x1); t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 5]) * KINV + cx * x1);
+      unpack_bf16x2(xx.w, x0, x1); t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 7]) * KINV + cx * x1);
+      *(reinterpret_cast<uint4*>(drow) + g * 4 + cc) = t;
     }
   }
 }
@@ -203,32 +254,31 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   float* z = vec + V_Z / 4;
   float* rzb = vec + V_RZ / 4;        // [2][128]
   float* gd = vec + V_GD / 4;
+  float* sp = vec + V_SP / 4;         // [2 (q / k)][2 (g)][128]: partial sums of d phi * phi
   float* part = vec + V_PART / 4;     // [8][128]
   auto bar = [&](int i) { return sb + OFF_BAR + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * N_BARS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool ctrl = warp == 8, qside = warp < 4;
+  const bool ctrl = warp == 8;
+  const int g = (warp >> 2) & 1, wq = warp & 3;
 
   if (tid == 256) {
     prefetch_map(&tmQ); prefetch_map(&tmK); prefetch_map(&tmV); prefetch_map(&tmO); prefetch_map(&tmD);
-    for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), i == F_X ? 256 : (i == F_OD ? 128 : 1));
+    for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), (i == F_X || i == F_OD) ? 256 : 1);
     mbar_init_fence();
   }
   if (ctrl) tmem_alloc(smem_u32(tmem_slot), T_COLS);
-  stage_omega(p.omega, sOM, tid, NT, p.omega_f16 != 0);
+  stage_omega(p.omega, sOM, tid, NT, false);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tl = tmem + ((uint32_t)(warp & 3) << 21);
-  const int row = tid & 127;                    // token row of the chunk (query side: i, key side: j) / feature row f
+  const uint32_t tl = tmem + ((uint32_t)wq << 21);
+  const int r = tid & 127;                      // TMEM lane: token row of every tile / feature row of the states
 
-  constexpr uint32_t ID_KK128 = make_idesc(128, false, false), ID_ST = make_idesc(64, true, true), ID_MN64 = make_idesc(64, false, true),
-                     ID_KK64 = make_idesc(64, false, false);
-  // products against Omega' (fp16 tile when p.omega_f16): U = X Om' and dx = dU Om'^T
-  const uint32_t ID_U = p.omega_f16 ? make_idesc(64, false, true, 128, true, false) : make_idesc(64, false, true);
-  const uint32_t ID_DX = p.omega_f16 ? make_idesc(64, false, false, 128, true, false) : ID_KK64;
+  constexpr uint32_t ID_U = make_idesc(64, false, true), ID_KK128 = make_idesc(128, false, false), ID_ST = make_idesc(64, true, true),
+                     ID_MN64 = make_idesc(64, false, true), ID_KK64 = make_idesc(64, false, false);
   auto dK = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)(ks >> 2) * TILE + (uint32_t)(ks & 3) * 32, 0, 1024); };   // K-major over 128 features
   auto d64 = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)ks * 32, 0, 1024); };                                  // K-major, K <= 64
   auto dMN = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)ks * 2048, TILE, 1024); };                             // MN-major, K = rows
@@ -259,30 +309,31 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_3d(&tmV, bar(B_V0 + vb), sXV0 + vb * TILE, h * FE, t0, b);
       }
     } else {
-      // ---- states of this segment: R, rz (query side) and -S, z (key side): fp32 -> TMEM, R also bf16 -> smem ----
+      // ---- states of this segment: group 0 loads R, rz (reverse state of the later segments), group 1 loads -S, z
+      //      (the forward's prefix state at the end of the segment): fp32 -> TMEM, R also bf16 -> smem ----
       const float* src;
-      if (qside) src = p.nseg > 1 ? p.seg_rstates + ((int64_t)bh * (p.nseg + 1) + seg) * FM * FV : nullptr;
+      if (g == 0) src = p.nseg > 1 ? p.seg_rstates + ((int64_t)bh * (p.nseg + 1) + seg) * FM * FV : nullptr;
       else {
         int slot = (seg + 1) * p.ratio;
         if (slot > p.fwd_nseg) slot = p.fwd_nseg;
         src = p.seg_states + ((int64_t)bh * (p.fwd_nseg + 1) + slot) * FM * FV;
       }
-      const float* rp = src ? src + row * FV : nullptr;
-      const float sg = qside ? 1.f : -1.f;
-#pragma unroll
+      const float* rp = src ? src + r * FV : nullptr;
+      const float sg = g == 0 ? 1.f : -1.f;
+#pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
+        uint32_t v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 t = rp ? *reinterpret_cast<const float4*>(rp + half * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          r[4 * j] = __float_as_uint(sg * t.x); r[4 * j + 1] = __float_as_uint(sg * t.y);
-          r[4 * j + 2] = __float_as_uint(sg * t.z); r[4 * j + 3] = __float_as_uint(sg * t.w);
+          v[4 * j] = __float_as_uint(sg * t.x); v[4 * j + 1] = __float_as_uint(sg * t.y);
+          v[4 * j + 2] = __float_as_uint(sg * t.z); v[4 * j + 3] = __float_as_uint(sg * t.w);
         }
-        tmem_st32(tl + (qside ? T_R : T_NS) + half * 32, r);
-        if (qside) pack_row32(sRB, row, half * 4, r, 1.f);
+        tmem_st32(tl + (g == 0 ? T_R : T_NS) + half * 32, v);
+        if (g == 0) pack_row32(sRB, r, half * 4, v, 1.f);
       }
-      if (qside) rzb[(nchunks_done & 1) * 128 + row] = rp ? rp[FE] : 0.f;
-      else z[row] = rp ? rp[FE] : 0.f;
+      if (g == 0) rzb[(nchunks_done & 1) * 128 + r] = rp ? rp[FE] : 0.f;
+      else z[r] = rp ? rp[FE] : 0.f;
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
@@ -293,7 +344,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int valid = (p.T - t0 < C) ? (p.T - t0) : C;
       const uint32_t vb = nchunks_done & 1;
       const uint32_t sXV = sXV0 + vb * TILE;
-      float* rz_cur = rzb + vb * 128;              // rz of the later chunks (read by the key side in phase 4)
+      float* rz_cur = rzb + vb * 128;              // rz of the later chunks
       float* rz_nxt = rzb + (vb ^ 1) * 128;
       if (ctrl) {
         // =============================== control warp ===============================
@@ -323,25 +374,26 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         __syncwarp();
-        named_bar_sync<1>(NT);                     // [A] phi(q), phi(k), G in smem; z rolled back
+        named_bar_sync<1>(NT);                     // [A] phi(q), phi(k), G in smem; gd; z rolled back
         if (lane == 0) {
           tc_fence_after();
           mbar_wait(bar(B_V0 + vb), (nchunks_done >> 1) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_NS, dMN(sPK, ks), dMN(sXV, ks), ID_ST, 1u);        // -S += phi(k)^T V
-          umma_commit(bar(M_NS));
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_W0, dK(sPK, ks), dK(sPQ, ks), ID_KK128, ks > 0);    // phi(k) phi(q)^T
+          umma_commit(bar(M_C1));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W1, d64(sG, ks), d64(sXV, ks), ID_KK128, ks > 0);   // G V^T
           umma_commit(bar(M_C2));
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_W0, dK(sPK, ks), dK(sPQ, ks), ID_KK128, ks > 0);    // phi(k) phi(q)^T
-#pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W2, d64(sXV, ks), d64(sG, ks), ID_KK128, ks > 0);   // V G^T
-          umma_commit(bar(M_C13));
+          umma_commit(bar(M_C3));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_NS, dMN(sPK, ks), dMN(sXV, ks), ID_ST, 1u);        // -S += phi(k)^T V
+          umma_commit(bar(M_NS));
         }
         __syncwarp();
-        named_bar_sync<1>(NT);                     // [B] dP, P^T, dP^T packed in TMEM; S_prev bf16 in smem
+        named_bar_sync<1>(NT);                     // [B] P^T, dP, dP^T packed in TMEM; S_prev bf16 in smem
         if (lane == 0) {
           tc_fence_after();
 #pragma unroll
@@ -367,6 +419,9 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) {
           tc_fence_after();
 #pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W2 + 64, tmem + T_W1 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_q Om'^T
+          umma_commit(bar(M_DXQ));
+#pragma unroll
           for (int hf = 0; hf < 2; ++hf) {         // d phi(k)
             const uint32_t d = tmem + (hf == 0 ? T_W1 : T_W0) + 64;
 #pragma unroll
@@ -376,247 +431,158 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           umma_commit(bar(M_G));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W2 + 64, tmem + T_W1 + ks * 8, d64(sOM, ks), ID_DX, ks > 0);   // dU_q Om'^T
-          umma_commit(bar(M_DXQ));
-#pragma unroll
           for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_R, dMN(sPQ, ks), dMN(sG, ks), ID_ST, 1u);          // R += phi(q)^T G
           umma_commit(bar(M_R));
         }
         __syncwarp();
-        named_bar_sync<1>(NT);                     // [D] d phi(k), dx_q consumed; dU_k packed in TMEM (W2 low); R bf16 in smem
+        named_bar_sync<1>(NT);                     // [D] dx_q, d phi(k) consumed; dU_k packed in TMEM (W2 low); R bf16 in smem
         if (lane == 0) {
           tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W0 + 64, tmem + T_W2 + ks * 8, d64(sOM, ks), ID_DX, ks > 0);   // dU_k Om'^T
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W0 + 64, tmem + T_W2 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_k Om'^T
           umma_commit(bar(M_DXK));
         }
         __syncwarp();
-      } else if (qside) {
-        // =============================== query side (row i) ===============================
-        const int i = row;
-        const bool rowok = i < valid;
-        // ---- phase 1: phi(q) -> smem; G, gd ----
+      } else {
+        // =============================== workers: thread (g, r) ===============================
+        const bool rowok = r < valid;
+        const int64_t tok = tokbase + t0 + r;
+        // ---- phase 1: phi of this group's tensor (g = 0: q, g = 1: k) -> smem; G, gd; z rolled back ----
         mbar_wait(bar(M_U), cph);
         tc_fence_after();
-        const float ssq = row_sumsq(sXQ, i);
-        mbar_arrive(bar(F_X));
-        const float oq = rowok ? (0.5f * F_S2 * ssq + F_HALF_LOG_M) * K2 : __int_as_float(0x7f800000);   // +inf -> phi = 0
-        phi_row_to_smem(tl + T_W1, sPQ, i, oq);
-        float gdi;
+        {
+          const float ss = row_sumsq(g ? sXK : sXQ, r);
+          mbar_arrive(bar(F_X));
+          const float o = rowok ? (0.5f * F_S2 * ss + F_HALF_LOG_M) * K2 : __int_as_float(0x7f800000);   // +inf -> phi = 0
+          phi_row_to_smem(tl + T_W1 + 64 * g, g ? sPK : sPQ, r, o);
+        }
         {
           mbar_wait(bar(B_OD), cph);
-          const float dn = rowok ? p.den[(tokbase + t0 + i) * p.H + h] : 1.f;
-          const float inv = rowok ? 1.f / dn : 0.f;
-          float dot = 0.f;
+          const float inv = rowok ? 1.f / p.den[tok * p.H + h] : 0.f;
+          if (g == 0) {                            // the normaliser's gradient: gd = -(dout . out) / den
+            float dot = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint4 od = lds128(sXO + sw128(i, cc)), dd = lds128(sXD + sw128(i, cc));
-            float o0, o1, d0, d1;
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint4 od = lds128(sXO + sw128(r, cc)), dd = lds128(sXD + sw128(r, cc));
+              float o0, o1, d0, d1;
+              unpack_bf16x2(od.x, o0, o1); unpack_bf16x2(dd.x, d0, d1); dot += o0 * d0 + o1 * d1;
+              unpack_bf16x2(od.y, o0, o1); unpack_bf16x2(dd.y, d0, d1); dot += o0 * d0 + o1 * d1;
+              unpack_bf16x2(od.z, o0, o1); unpack_bf16x2(dd.z, d0, d1); dot += o0 * d0 + o1 * d1;
+              unpack_bf16x2(od.w, o0, o1); unpack_bf16x2(dd.w, d0, d1); dot += o0 * d0 + o1 * d1;
+            }
+            gd[r] = -dot * inv;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {         // G = dout / den, columns [32 g, 32 g + 32)
+            const uint4 dd = lds128(sXD + sw128(r, g * 4 + cc));
+            float d0, d1;
             uint4 t;
-            unpack_bf16x2(od.x, o0, o1); unpack_bf16x2(dd.x, d0, d1); dot += o0 * d0 + o1 * d1; t.x = pack_bf16x2(d0 * inv, d1 * inv);
-            unpack_bf16x2(od.y, o0, o1); unpack_bf16x2(dd.y, d0, d1); dot += o0 * d0 + o1 * d1; t.y = pack_bf16x2(d0 * inv, d1 * inv);
-            unpack_bf16x2(od.z, o0, o1); unpack_bf16x2(dd.z, d0, d1); dot += o0 * d0 + o1 * d1; t.z = pack_bf16x2(d0 * inv, d1 * inv);
-            unpack_bf16x2(od.w, o0, o1); unpack_bf16x2(dd.w, d0, d1); dot += o0 * d0 + o1 * d1; t.w = pack_bf16x2(d0 * inv, d1 * inv);
-            sts128(sG + sw128(i, cc), t);
+            unpack_bf16x2(dd.x, d0, d1); t.x = pack_bf16x2(d0 * inv, d1 * inv);
+            unpack_bf16x2(dd.y, d0, d1); t.y = pack_bf16x2(d0 * inv, d1 * inv);
+            unpack_bf16x2(dd.z, d0, d1); t.z = pack_bf16x2(d0 * inv, d1 * inv);
+            unpack_bf16x2(dd.w, d0, d1); t.w = pack_bf16x2(d0 * inv, d1 * inv);
+            sts128(sG + sw128(r, g * 4 + cc), t);
           }
           mbar_arrive(bar(F_OD));
-          gdi = -dot * inv;
-          gd[i] = gdi;
+        }
+        if (g == 1) {
+          named_bar_sync<2>(128);                  // phi(k) tile complete
+          colsum_partial<128>(sPK, r, nullptr, part);
+          named_bar_sync<2>(128);
+          z[r] -= part_total(part, r);
         }
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [A]
-        // ---- phase 2: S_prev -> bf16 smem (feature row f = this thread); dP = tril(G V^T + gd_i) packed in place ----
-        mbar_wait(bar(M_NS), cph);
+        const float gdr = gd[r];
+        // ---- phase 2: the three masked tiles, packed in place; S_prev -> bf16 smem ----
+        mbar_wait(bar(M_C1), cph);
         tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32_issue(tl + T_NS + half * 32, r);
-          tmem_ld_wait();
-          pack_row32(sSB, row, half * 4, r, -1.f);
-        }
+        mask_tile<0, 3>(tl + T_W0, g, wq, r, 0.f, gd);
         mbar_wait(bar(M_C2), cph);
         tc_fence_after();
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          uint32_t pk[16];
-          if (pc <= warp) {                        // key columns 32 pc .. : all in the future of rows < 32 pc
-            uint32_t r[32];
-            tmem_ld32_issue(tl + T_W1 + pc * 32, r);
-            tmem_ld_wait();
-            if (pc < warp) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]) + gdi, __uint_as_float(r[2 * j + 1]) + gdi);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c0 = pc * 32 + 2 * j;
-                pk[j] = pack_bf16x2(c0 <= i ? __uint_as_float(r[2 * j]) + gdi : 0.f, c0 + 1 <= i ? __uint_as_float(r[2 * j + 1]) + gdi : 0.f);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          }
-          tmem_st16(tl + T_W1 + pc * 16, pk);
+        mask_tile<1, 4>(tl + T_W1, g, wq, r, gdr, gd);
+        mbar_wait(bar(M_C3), cph);
+        tc_fence_after();
+        mask_tile<2, 5>(tl + T_W2, g, wq, r, 0.f, gd);
+        mbar_wait(bar(M_NS), cph);
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          tmem_ld32_issue(tl + T_NS + g * 32, v);
+          tmem_ld_wait();
+          pack_row32(sSB, r, g * 4, v, -1.f);      // feature row r of S_prev = -(-S)
         }
         tmem_st_wait();
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [B]
-        // ---- phase 3: d phi(q) -> dU_q (packed, TMEM W1 low 32 columns), coefficient of x_q ----
-        float cxq;
+        // ---- phase 3: rz of the next (earlier) chunk; d phi(q) -> dU_q; dv out ----
+        colsum_partial<256>(sPQ, tid, gd, part);   // sum_i gd_i phi(q_i)
+        named_bar_sync<6>(256);
+        if (g == 0) rz_nxt[r] = rz_cur[r] + part_total(part, r);
         {
-          uint32_t du[32];
+          uint32_t du[16];
           mbar_wait(bar(M_E1), cph);
           tc_fence_after();
-          dphi_row(tl + T_W1 + 64, tl + T_W0 + 64, sPQ, i, z, gdi, du, cxq);
-          tmem_st32(tl + T_W1, du);                // dP (W1 low) is dead: batch E1 has completed
-          tmem_st_wait();
+          sp[g * 128 + r] = dphi_half(tl + T_W1 + 64, tl + T_W0 + 64, sPQ, r, g, z, gdr, du);
+          tmem_st16(tl + T_W1 + g * 16, du);       // dP (W1 low) is dead: batch E1 has completed
         }
-        tc_fence_before();
-        named_bar_sync<1>(NT);                     // [C]
-        // ---- phase 4: dq; R -> bf16 smem ----
-        mbar_wait(bar(M_DXQ), cph);
-        tc_fence_after();
-        dx_row_out(tl + T_W2 + 64, p.q + (tokbase + t0 + i) * p.ld + (int64_t)h * FE, p.dq + (tokbase + t0 + i) * p.ld_d + (int64_t)h * FE, cxq, rowok);
-        mbar_wait(bar(M_R), cph);                  // every MMA of this chunk that reads R bf16 / phi(q) / G has completed
-        tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32_issue(tl + T_R + half * 32, r);
-          tmem_ld_wait();
-          pack_row32(sRB, row, half * 4, r, 1.f);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        named_bar_sync<1>(NT);                     // [D]
-      } else {
-        // =============================== key side (row j) ===============================
-        const int j = row;
-        const bool rowok = j < valid;
-        // ---- phase 1: phi(k) -> smem; z rolled back to the start of the chunk ----
-        mbar_wait(bar(M_U), cph);
-        tc_fence_after();
-        const float ssk = row_sumsq(sXK, j);
-        mbar_arrive(bar(F_X));
-        const float ok = rowok ? (0.5f * F_S2 * ssk + F_HALF_LOG_M) * K2 : __int_as_float(0x7f800000);
-        phi_row_to_smem(tl + T_W1 + 64, sPK, j, ok);
-        named_bar_sync<2>(128);                    // phi(k) tile complete (key side only)
-        colsum_partial(sPK, row, nullptr, part);
-        named_bar_sync<2>(128);
-        z[row] -= part_total(part, row);
-        fence_proxy_async();
-        tc_fence_before();
-        named_bar_sync<1>(NT);                     // [A]
-        // ---- phase 2: P^T = triu(phi(k) phi(q)^T), dP^T = triu(V G^T + gd_i) packed in place ----
-        mbar_wait(bar(M_C13), cph);
-        tc_fence_after();
-        const int kw = warp - 4;
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          uint32_t pk[16];
-          if (pc >= kw) {                          // query columns 32 pc .. : all in the past of rows >= 32 (pc + 1)
-            uint32_t r[32];
-            tmem_ld32_issue(tl + T_W0 + pc * 32, r);
-            tmem_ld_wait();
-            if (pc > kw) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
-            } else {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int c0 = pc * 32 + 2 * q;
-                pk[q] = pack_bf16x2(c0 >= j ? __uint_as_float(r[2 * q]) : 0.f, c0 + 1 >= j ? __uint_as_float(r[2 * q + 1]) : 0.f);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) pk[q] = 0u;
-          }
-          tmem_st16(tl + T_W0 + pc * 16, pk);
-        }
-        {
-          const float4* g4 = reinterpret_cast<const float4*>(gd);
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            uint32_t pk[16];
-            if (pc >= kw) {
-              uint32_t r[32];
-              tmem_ld32_issue(tl + T_W2 + pc * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 gq = g4[pc * 8 + q];
-                const int c0 = pc * 32 + 4 * q;
-                float a0 = __uint_as_float(r[4 * q]) + gq.x, a1 = __uint_as_float(r[4 * q + 1]) + gq.y;
-                float a2 = __uint_as_float(r[4 * q + 2]) + gq.z, a3 = __uint_as_float(r[4 * q + 3]) + gq.w;
-                if (pc == kw) {
-                  a0 = c0 >= j ? a0 : 0.f; a1 = c0 + 1 >= j ? a1 : 0.f; a2 = c0 + 2 >= j ? a2 : 0.f; a3 = c0 + 3 >= j ? a3 : 0.f;
-                }
-                pk[2 * q] = pack_bf16x2(a0, a1);
-                pk[2 * q + 1] = pack_bf16x2(a2, a3);
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) pk[q] = 0u;
-            }
-            tmem_st16(tl + T_W2 + pc * 16, pk);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        named_bar_sync<1>(NT);                     // [B]
-        // ---- phase 3: dv out; rz of the next (earlier) chunk ----
-        colsum_partial(sPQ, row, gd, part);        // sum_i gd_i phi(q_i): phi(q), gd were complete at [A]
-        named_bar_sync<2>(128);
-        rz_nxt[row] = rz_cur[row] + part_total(part, row);
         mbar_wait(bar(M_E2), cph);
         tc_fence_after();
         {
-          bf16* drow = p.dv + (tokbase + t0 + j) * p.ld_d + (int64_t)h * FE;
+          uint32_t v[32];
+          tmem_ld32_issue(tl + T_W2 + 64 + g * 32, v);
+          tmem_ld_wait();
+          if (rowok) {
+            bf16* drow = p.dv + tok * p.ld_d + (int64_t)h * FE;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld32_issue(tl + T_W2 + 64 + half * 32, r);
-            tmem_ld_wait();
-            if (rowok) {
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc) {
-                uint4 t;
-                t.x = pack_bf16x2(__uint_as_float(r[8 * cc]), __uint_as_float(r[8 * cc + 1]));
-                t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
-                t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
-                t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
-                *(reinterpret_cast<uint4*>(drow) + half * 4 + cc) = t;
-              }
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 t;
+              t.x = pack_bf16x2(__uint_as_float(v[8 * cc]), __uint_as_float(v[8 * cc + 1]));
+              t.y = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
+              t.z = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
+              t.w = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
+              *(reinterpret_cast<uint4*>(drow) + g * 4 + cc) = t;
             }
           }
         }
+        tmem_st_wait();
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [C]
-        // ---- phase 4: d phi(k) -> dU_k (packed, TMEM W2 low 32 columns), coefficient of x_k ----
-        float cxk;
+        // ---- phase 4: dq out; d phi(k) -> dU_k; R -> bf16 smem ----
+        mbar_wait(bar(M_DXQ), cph);
+        tc_fence_after();
+        dx_half_out(tl + T_W2 + 64, p.q + tok * p.ld + (int64_t)h * FE, p.dq + tok * p.ld_d + (int64_t)h * FE, g,
+                    -(sp[r] + sp[128 + r]) * F_S2, rowok);
         {
-          uint32_t du[32];
+          uint32_t du[16];
           mbar_wait(bar(M_G), cph);
           tc_fence_after();
-          dphi_row(tl + T_W1 + 64, tl + T_W0 + 64, sPK, j, rz_cur, 1.f, du, cxk);
-          tmem_st32(tl + T_W2, du);                // dP^T (W2 low) is dead: batch G has completed
-          tmem_st_wait();
+          sp[256 + g * 128 + r] = dphi_half(tl + T_W1 + 64, tl + T_W0 + 64, sPK, r, g, rz_cur, 1.f, du);
+          tmem_st16(tl + T_W2 + g * 16, du);       // dP^T (W2 low) is dead: batch G has completed
         }
+        mbar_wait(bar(M_R), cph);                  // every MMA of this chunk that reads R bf16 / phi(q) / G has completed
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          tmem_ld32_issue(tl + T_R + g * 32, v);
+          tmem_ld_wait();
+          pack_row32(sRB, r, g * 4, v, 1.f);
+        }
+        tmem_st_wait();
+        fence_proxy_async();
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [D]
-        // ---- phase 5: dk ----
+        // ---- phase 5: dk out ----
         mbar_wait(bar(M_DXK), cph);
         tc_fence_after();
-        dx_row_out(tl + T_W0 + 64, p.k + (tokbase + t0 + j) * p.ld + (int64_t)h * FE, p.dk + (tokbase + t0 + j) * p.ld_d + (int64_t)h * FE, cxk, rowok);
+        dx_half_out(tl + T_W0 + 64, p.k + tok * p.ld + (int64_t)h * FE, p.dk + tok * p.ld_d + (int64_t)h * FE, g,
+                    -(sp[256 + r] + sp[384 + r]) * F_S2, rowok);
         tc_fence_before();
       }
     }
-    // all three roles meet before the next item rewrites the states (the key side may still be storing dk)
+    // all roles meet before the next item rewrites the states
     tc_fence_before();
     named_bar_sync<1>(NT);
     tc_fence_after();
@@ -652,7 +618,7 @@ int emo_favor_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t
   Params p;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.ld = ld; p.omega = omega; p.den = den; p.seg_states = seg_states;
   p.seg_rstates = seg_rstates; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_d = ld_d;
-  p.nseg = nseg; p.seg_chunks = sc; p.fwd_nseg = fwd_nseg; p.ratio = ratio; p.T = T_; p.H = H; p.items = B * H * nseg; p.omega_f16 = favor_omega_f16();
+  p.nseg = nseg; p.seg_chunks = sc; p.fwd_nseg = fwd_nseg; p.ratio = ratio; p.T = T_; p.H = H; p.items = B * H * nseg;
   const int sms = emo_num_sms();
   const int grid = p.items < sms ? p.items : sms;
   favor_bwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, mo, md, p);

@@ -167,9 +167,11 @@ __device__ __forceinline__ void stage_omega(const float* omega, uint32_t tile, i
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)(e * 128 + ((c ^ (e & 7)) << 4))), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
   }
 }
-static inline int favor_omega_f16() {            // EMO_FAVOR_OMEGA_F16=0: bf16 Omega' (A/B)
+// MEASURED on B200: a kind::f16 MMA with a bf16 A operand and an fp16 B operand raises "illegal instruction" -- the two
+// format fields of the instruction descriptor must agree.  The switch stays off; it documents the experiment.
+static inline int favor_omega_f16() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("EMO_FAVOR_OMEGA_F16"); on = e ? atoi(e) : 1; }
+  if (on < 0) { const char* e = getenv("EMO_FAVOR_OMEGA_F16"); on = e ? atoi(e) : 0; }
   return on;
 }
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][128 B] tile with the 128B swizzle (TMA / UMMA layout)
