@@ -216,13 +216,8 @@ __device__ __forceinline__ float dphi_half(uint32_t tp, uint32_t tm, uint32_t ph
   }
   return s0 + s1;
 }
-// columns [32 g, 32 g + 32) of a dx row = acc * ln2 + cx * x  -> global (16-byte stores); x re-read from global (L2)
-__device__ __forceinline__ void dx_half_out(uint32_t ta, const bf16* xrow, bf16* drow, int g, float cx, bool ok) {
-  uint4 xv[4];
-  if (ok) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) xv[c] = __ldg(reinterpret_cast<const uint4*>(xrow) + g * 4 + c);
-  }
+// columns [32 g, 32 g + 32) of a dx row = acc * ln2 + cx * x  -> global (16-byte stores)
+__device__ __forceinline__ void dx_half_out(uint32_t ta, const uint4 (&xv)[4], bf16* drow, int g, float cx, bool ok) {
   uint32_t r[32];
   tmem_ld32_issue(ta + g * 32, r);
   tmem_ld_wait();
@@ -246,7 +241,9 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) by pointer arithmetic ON the __shared__ array: an integer round trip would
+  // turn every access through z / gd / sp / part into a generic load (ncu: LD.E with long-scoreboard stalls)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(smem);
   const uint32_t sXQ = sb + OFF_XQ, sXK = sb + OFF_XK, sXV0 = sb + OFF_XV, sXO = sb + OFF_XO, sXD = sb + OFF_XD, sPQ = sb + OFF_PQ,
                  sPK = sb + OFF_PK, sG = sb + OFF_G, sSB = sb + OFF_SB, sRB = sb + OFF_RB, sOM = sb + OFF_OM;
@@ -447,6 +444,8 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // =============================== workers: thread (g, r) ===============================
         const bool rowok = r < valid;
         const int64_t tok = tokbase + t0 + r;
+        // 1 / den of this row, requested before anything waits
+        const float den_r = rowok ? __ldg(p.den + tok * p.H + h) : 1.f;
         // ---- phase 1: phi of this group's tensor (g = 0: q, g = 1: k) -> smem; G, gd; z rolled back ----
         mbar_wait(bar(M_U), cph);
         tc_fence_after();
@@ -458,7 +457,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         {
           mbar_wait(bar(B_OD), cph);
-          const float inv = rowok ? 1.f / p.den[tok * p.H + h] : 0.f;
+          const float inv = rowok ? 1.f / den_r : 0.f;
           if (g == 0) {                            // the normaliser's gradient: gd = -(dout . out) / den
             float dot = 0.f;
 #pragma unroll
@@ -518,6 +517,11 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [B]
         // ---- phase 3: rz of the next (earlier) chunk; d phi(q) -> dU_q; dv out ----
+        uint4 xq4[4];                              // requested a phase ahead of its use
+        if (rowok) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) xq4[cc] = __ldg(reinterpret_cast<const uint4*>(p.q + tok * p.ld + (int64_t)h * FE) + g * 4 + cc);
+        }
         colsum_partial<256>(sPQ, tid, gd, part);   // sum_i gd_i phi(q_i)
         named_bar_sync<6>(256);
         if (g == 0) rz_nxt[r] = rz_cur[r] + part_total(part, r);
@@ -551,10 +555,14 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [C]
         // ---- phase 4: dq out; d phi(k) -> dU_k; R -> bf16 smem ----
+        uint4 xk4[4];
+        if (rowok) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) xk4[cc] = __ldg(reinterpret_cast<const uint4*>(p.k + tok * p.ld + (int64_t)h * FE) + g * 4 + cc);
+        }
         mbar_wait(bar(M_DXQ), cph);
         tc_fence_after();
-        dx_half_out(tl + T_W2 + 64, p.q + tok * p.ld + (int64_t)h * FE, p.dq + tok * p.ld_d + (int64_t)h * FE, g,
-                    -(sp[r] + sp[128 + r]) * F_S2, rowok);
+        dx_half_out(tl + T_W2 + 64, xq4, p.dq + tok * p.ld_d + (int64_t)h * FE, g, -(sp[r] + sp[128 + r]) * F_S2, rowok);
         {
           uint32_t du[16];
           mbar_wait(bar(M_G), cph);
@@ -577,8 +585,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- phase 5: dk out ----
         mbar_wait(bar(M_DXK), cph);
         tc_fence_after();
-        dx_half_out(tl + T_W0 + 64, p.k + tok * p.ld + (int64_t)h * FE, p.dk + tok * p.ld_d + (int64_t)h * FE, g,
-                    -(sp[256 + r] + sp[384 + r]) * F_S2, rowok);
+        dx_half_out(tl + T_W0 + 64, xk4, p.dk + tok * p.ld_d + (int64_t)h * FE, g, -(sp[256 + r] + sp[384 + r]) * F_S2, rowok);
         tc_fence_before();
       }
     }

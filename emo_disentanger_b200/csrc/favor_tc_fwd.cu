@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(NT, 2)
 favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps z / zpart accesses LDS / STS, not generic)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(smem);
   const uint32_t sXQ = sb + OFF_XQ, sXK = sb + OFF_XK, sXV = sb + OFF_XV, sPK = sb + OFF_PK, sSB = sb + OFF_SB, sOM = sb + OFF_OM;
   float* z = reinterpret_cast<float*>(smem + OFF_Z);
