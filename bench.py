@@ -124,17 +124,18 @@ def make_batches(n, B, T, V, seed0, pinned):
 
 
 def run_reference(args):
-    """CPU arm: the reference train step (oracle port) on the host cores, bounded sample per step."""
+    """CPU arm: the reference train step (oracle port) on the host cores; each step is a bounded sample of the workload
+    (ONE 2048-token sequence through the same train step), so config.per_gpu_batch says 1."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle.cpu_train import time_cpu_train
-    r = time_cpu_train(V=V_FUNCTIONAL_STAGE2, B=1, T=T_SEQ, steps=args.steps, warmup=max(1, min(args.warmup, 1)))
+    r = time_cpu_train(V=V_FUNCTIONAL_STAGE2, B=1, T=T_SEQ, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "stage2_performer_train_tokens_per_sec", "value": r["value"],
-            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
+            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.batch, 1, "n/a (CPU arm: each step is a bounded sample of the workload -- ONE "
+            "config": workload_config(1, 1, "n/a (CPU arm: each step is a bounded sample of the workload -- ONE "
                                       "2048-token sequence through the same train step, see cpu_baseline.sample)"),
             "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
@@ -178,6 +179,20 @@ def bench_decode(model, V, n_tokens=384, prompt=64, cpu=True):
             dt = time.perf_counter() - t0
         out["batch%d" % B] = {"value": B * n_tokens / dt, "us_per_step": 1e6 * dt / n_tokens}
         del dec
+    # decode is bound by streaming the bf16 weights once per step (75.9 MB / token at batch 1) plus the
+    # fp32 FAVOR+ state (read + write); the batch shares the weight stream
+    pk = peaks()
+    wbytes = 2.0 * (CFG["n_layer"] * (4 * 512 * 512 + 2 * 512 * 2048) + V * 512)
+    sbytes = 2.0 * CFG["n_layer"] * 8 * 128 * 80 * 4
+    for B in (1, 4):
+        d = out["batch%d" % B]
+        byts = wbytes + B * sbytes
+        ach = byts / (d["us_per_step"] * 1e-6) / 1e9
+        d["roofline"] = {"bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
+                         "work_per_step": "bf16 weights %.1f MB + %d x %.1f MB fp32 FAVOR+ state (read + write)" % (wbytes / 1e6, B, sbytes / 1e6),
+                         "peak_source": pk["source"],
+                         "note": "~62 dependent kernels per token: launch / dependency latency, not bandwidth, bounds the step"}
     if cpu:
         # the reference loop (inference.py:252-272) re-runs the model over the WHOLE prefix for every token; timed on
         # the oracle port at one representative prefix length (cost grows linearly with the prefix)
@@ -205,6 +220,187 @@ def bench_decode(model, V, n_tokens=384, prompt=64, cpu=True):
     return out
 
 
+def _time_gpu(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _class_roofline(ops, ms_step, tokens_step, flops_token_attn=None):
+    """roofline entry of the dominant kernel class of the LAST timed step (ops.TIMER enabled by the caller)"""
+    pk = peaks()
+    summ = ops.TIMER.summary()
+    gem = summ.get("gemm", (0, 0.0, 0.0))
+    att_ms = sum(v[1] for k, v in summ.items() if "attn" in k)
+    att_n = sum(v[0] for k, v in summ.items() if "attn" in k)
+    tot = sum(v[1] for v in summ.values()) or 1.0
+    shares = {k: round(v[1] / tot, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1]) if v[0]}
+    if flops_token_attn is not None and att_ms > gem[1]:
+        fl = flops_token_attn * tokens_step
+        ach = fl / (att_ms * 1e-3) / 1e12
+        roof = {"kernel": "attn_fwd / attn_bwd_dkv / attn_bwd_dq (flash-style causal softmax attention, mma.sync)",
+                "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "launches": att_n,
+                "work_per_launch": "causal attention: 4*64*(T+1)/2 MAC-pairs per (token, head) forward, x2.5 for the "
+                                   "backward (recomputed scores)", "peak_source": pk["source"] + ", sustained bf16"}
+    else:
+        ach = gem[2] / (gem[1] * 1e-3) / 1e12 if gem[1] else 0.0
+        roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM)", "bound": "tensor", "achieved": round(ach, 2),
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4), "traffic": None,
+                "launches": gem[0], "work_per_launch": "2*M*N*K flops of each launch, summed",
+                "peak_source": pk["source"] + ", sustained bf16"}
+    roof["share_of_step"] = round((att_ms if "attn" in roof["kernel"] else gem[1]) / ms_step, 4)
+    return roof, shares
+
+
+def bench_gpt2_train(cpu=True, B=16, steps=6, warmup=3):
+    """BASELINE.json configs[2]: stage-2 GPT-2 backbone, REMI representation (V = 372), seq 2048, bf16, 1 GPU."""
+    import contextlib
+    import torch
+    from emo_disentanger_b200 import ops
+    from emo_disentanger_b200.stage2 import MusicGPT2
+    from emo_disentanger_b200.optim import FusedAdam
+    from emo_disentanger_b200.synth import synthetic_batch
+    V, T = 372, T_SEQ
+    with contextlib.redirect_stdout(sys.stderr):
+        m = MusicGPT2(V, CFG["n_layer"], 8, 512, 2048, 512, dropout=0.1, use_segment_emb=True, n_segment_types=2)
+    m = m.cuda().train()
+    opt = FusedAdam(m, lr=1e-4, max_grad_norm=0.5)
+    tok, seg, tgt = (t.cuda() for t in synthetic_batch(V, B, T, 0))
+    step = lambda: (m.train_step(tok, seg, tgt), opt.step())
+    ms = _time_gpu(step, steps, warmup)
+    ops.TIMER.enable(["gemm", "emo_attn_fwd", "emo_attn_bwd", "emo_ln_fwd", "emo_ln_bwd"])
+    step()
+    torch.cuda.synchronize()
+    # causal attention work per token (SURVEY 8d): fwd 12*8*2*2*64*(T+1)/2 flops, bwd 2.5x (dq, dk, dv + recomputed scores)
+    attn_flops_token = CFG["n_layer"] * 8 * 2 * 2 * 64 * (T + 1) / 2 * 3.5
+    roof, shares = _class_roofline(ops, ms, B * T, attn_flops_token)
+    ops.TIMER.disable()
+    out = {"metric": "stage2_gpt2_train_tokens_per_sec", "value": B * T / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "stage2 GPT-2 train step: 12 HF-GPT2 blocks d512 8h ff2048 gelu_new, REMI repr V=%d, seq=%d, "
+                                  "batch %d, dropout 0.1 (incl. attention-prob dropout), clip 0.5 + Adam" % (V, T, B)},
+           "steps": steps, "warmup": warmup, "roofline": roof, "kernel_time_shares": shares}
+    del m, opt
+    torch.cuda.empty_cache()
+    if cpu:
+        from oracle.cpu_train import time_cpu_train_gpt2
+        r = time_cpu_train_gpt2(V=V, B=1, T=T, steps=1, warmup=1)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    return out
+
+
+def bench_stage1_train(cpu=True, steps=8, warmup=3):
+    """BASELINE.json configs[0] (the reference's own CPU-runnable case): stage-1 lead-sheet model, functional
+    representation (V = 216), seq 512, batch 1, one train.py step -- on the GPU at batch 1 (the same config) and at
+    batch 64, next to the CPU twin."""
+    import contextlib
+    import torch
+    from emo_disentanger_b200 import ops
+    from emo_disentanger_b200.stage1 import PlainTransformer
+    from emo_disentanger_b200.optim import FusedAdam
+    V, T = 216, 512
+    with contextlib.redirect_stdout(sys.stderr):
+        m = PlainTransformer(512, V, CFG["n_layer"], 8, 512, 2048, 0, T, dec_dropout=0.1, pre_lnorm=True)
+    m = m.cuda().train()
+    opt = FusedAdam(m, lr=1e-4, max_grad_norm=0.5)
+    out = {"metric": "stage1_train_tokens_per_sec", "unit": "tokens/s", "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "stage1 PlainTransformer train step: 12 Transformer-XL layers (rel-pos attention, mem_len 0), "
+                                  "d512 8h ff2048, functional lead-sheet V=%d, seq=%d, dropout 0.1, clip 0.5 + Adam" % (V, T)},
+           "steps": steps, "warmup": warmup}
+    for B in (1, 64):
+        g = torch.Generator().manual_seed(B)
+        tok = torch.randint(0, V - 1, (T, B), generator=g).cuda()
+        tgt = torch.roll(tok, -1, 0)
+        step = lambda: (m.train_step(tok, tgt), opt.step())
+        ms = _time_gpu(step, steps, warmup)
+        out["batch%d" % B] = {"value": B * T / ms * 1e3, "ms_per_step": ms}
+        if B == 64:
+            ops.TIMER.enable(["gemm", "emo_relattn_fwd", "emo_relattn_bwd", "emo_ln_fwd", "emo_ln_bwd"])
+            step()
+            torch.cuda.synchronize()
+            attn_flops_token = CFG["n_layer"] * 8 * 2 * 2 * 64 * (T + 1) / 2 * 2 * 3.5       # content + position scores
+            roof, shares = _class_roofline(ops, ms, B * T, attn_flops_token)
+            ops.TIMER.disable()
+            out["roofline"], out["kernel_time_shares"] = roof, shares
+    out["value"] = out["batch1"]["value"]
+    del m, opt
+    torch.cuda.empty_cache()
+    if cpu:
+        from oracle.cpu_train import time_cpu_train_stage1
+        r = time_cpu_train_stage1(V=V, B=1, T=T, steps=3, warmup=1)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    return out
+
+
+def bench_two_stage_generate(n_bars=8, max_events_s1=400, max_events_s2=700):
+    """BASELINE.json configs[4]: stage-1 lead sheet (generate_plain_xl, <= 512 events) -> stage-2 accompaniment for the
+    four emotion quadrants (generate_conditional), random-init weights, fixed seeds, grammar checks ON, temperature /
+    top-p on the device; tokens/s = accepted events / wall time.  Positive lead sheet -> Q1, Q4; Negative -> Q2, Q3
+    (stage2_accompaniment/inference.py:433-450)."""
+    import contextlib
+    import numpy as np
+    import torch
+    from emo_disentanger_b200.stage1 import PlainTransformer
+    from emo_disentanger_b200.stage2 import MusicPerformer
+    from emo_disentanger_b200.generate import generate_plain_xl, generate_conditional
+    from emo_disentanger_b200.synth import synthetic_vocab, synthetic_lead_sheet
+    V1, V2 = 216, V_FUNCTIONAL_STAGE2
+    e1, i1 = synthetic_vocab(V1, 1)
+    e2, i2 = synthetic_vocab(V2, 2)
+    torch.manual_seed(7)
+    with contextlib.redirect_stdout(sys.stderr):
+        m1 = PlainTransformer(512, V1, CFG["n_layer"], 8, 512, 2048, 512, 512, dec_dropout=0.1, pre_lnorm=True).cuda().eval()
+        m2 = MusicPerformer(V2, CFG["n_layer"], 8, 512, 2048, 512, use_segment_emb=True, n_segment_types=2,
+                            favor_feature_dims=128).cuda().eval()
+    out = {"metric": "two_stage_generate_tokens_per_sec", "unit": "accepted events/s", "top_p": 0.9, "dtype": "bf16",
+           "config": {"workload": "stage1 lead sheet (%d bars, temperature 1.2) -> stage2 Performer accompaniment for Q1..Q4 "
+                                  "(temperature 1.1 / 1.2 as inference.py:455-462), grammar checks on, random-init weights" % n_bars}}
+    rng = np.random.RandomState(0)
+    np.random.seed(0)
+    devnull = open(os.devnull, "w")
+    n1 = n2 = 0
+    t1 = t2 = 0.0
+    sheets = {}
+    for emo in ("Positive", "Negative"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(devnull):
+            gen, _ = generate_plain_xl(m1, e1, i1, max_bars=n_bars, max_events=max_events_s1, primer=["Emotion_" + emo],
+                                       temp=1.2, top_p=0.9, rng=rng, verbose=False)
+        torch.cuda.synchronize()
+        t1 += time.perf_counter() - t0
+        n1 += len(gen) if gen else 0
+        # the lead sheet handed to stage 2 (ids of the stage-2 vocabulary): a synthetic one of the same bar count when the
+        # random-init stage-1 model gets stuck on the grammar (it emits no usable bars)
+        sheets[emo] = synthetic_lead_sheet(e2, n_bars, seed=len(sheets))
+    out["stage1"] = {"value": n1 / t1 if t1 else 0.0, "events": n1, "seconds": t1}
+    for q, emo, temp in (("Q1", "Positive", 1.1), ("Q2", "Negative", 1.2), ("Q3", "Negative", 1.2), ("Q4", "Positive", 1.1)):
+        primer = [e2["Emotion_" + q], e2["Key_C"], e2["Tempo_110"]]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(devnull):
+            toks = generate_conditional(m2, e2, i2, sheets[emo], primer, max_events=max_events_s2, temp=temp, top_p=0.9)
+        torch.cuda.synchronize()
+        t2 += time.perf_counter() - t0
+        n2 += len(toks) if toks else 0
+    out["stage2_4q_batch1"] = {"value": n2 / t2 if t2 else 0.0, "events": n2, "seconds": t2,
+                               "note": "the four quadrants are decoded one after the other (batch 1 each); a batched "
+                                       "(ragged) 4-quadrant decode is not implemented"}
+    out["value"] = (n1 + n2) / (t1 + t2) if (t1 + t2) else 0.0
+    del m1, m2
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(B, world, l2note):
     return {"workload": "stage2 Performer train step: 12L d512 8h ff2048 FAVOR+ M=128, functional repr V=%d, "
                         "seq=%d, per-GPU batch %d, dropout 0.1, clip 0.5 + Adam, Omega redrawn per forward"
@@ -220,14 +416,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--batch", type=int, default=74,
                     help="per-GPU batch (sequences of 2048 tokens); 74 = 2 per SM pair: every GEMM and FAVOR+ launch is a "
-                         "whole number of waves on 148 SMs (swept 4..74 in profiles/)")
+                         "whole number of waves on 148 SMs; the line also carries the B = 4 point (reference batch_size)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (B = 4 point, GPT-2 / stage-1 train, two-stage generation)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the 1-GPU autoregressive decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps or 3
-        args.warmup = args.warmup or 1
+        args.warmup = 1 if args.warmup is None else max(1, args.warmup)
         return run_reference(args)
     args.steps = args.steps or 20
     args.warmup = max(3, args.warmup if args.warmup is not None else 5)
@@ -315,7 +513,10 @@ def main():
     ms = float(tms[0])
     ksum = ops.TIMER.summary()
     ops.TIMER.disable()
-    loss_last = float(acc[1] / acc[0]) if world == 1 else None
+    acc_g = acc.clone()
+    if world > 1:                                   # acc[0] (non-pad count) is already global; loss sum / hits are local
+        dist.all_reduce(acc_g[1:], op=dist.ReduceOp.SUM)
+    loss_last = float(acc_g[1] / acc_g[0])         # mean CE of the last timed step over the GLOBAL batch
     value = B * T * world * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel class -----------------------------------------------------
@@ -380,13 +581,39 @@ def main():
             "config": workload_config(B, world, "per-step working set (bf16 weights 76 MB + ~%.1f GB saved activations) "
                                       "exceeds the 126 MB L2; no explicit flush" % (B * T * 148e3 / 1e9)),
             "e2e": e2e, "gpu_launches": launches, "roofline": roof, "kernel_time_shares": shares,
-            "clocks": ck, "loss_last_step": loss_last, "impl": "b200"}
+            "clocks": ck, "loss_last_step": loss_last, "impl": "b200",
+            "timing_note": "the `value` loop carries two cudaEventRecords around every launch of the dominant kernel class "
+                           "(the live roofline timer); the `e2e` loop does not, which is why e2e can read slightly above value"}
 
+    if rank == 0 and world == 1 and not args.no_extras:
+        # the reference's own batch_size (emopia_finetune.yaml: 4): 8 192 tokens per step, where host-side launch cost
+        # (tensor-map encodes are cached, emo_gemm) rather than the GPU bounds the step
+        hb = make_batches(2, 4, T, V, 77, pinned=False)
+        db = [tuple(t.to(dev) for t in b) for b in hb]
+        def step_b4(i=[0]):
+            tok, seg, tgt = db[i[0] % 2]
+            i[0] += 1
+            model.train_step(tok, seg, tgt)
+            opt.step()
+        ms4 = _time_gpu(step_b4, 10, 4)
+        line["train_b4"] = {"value": 4 * T / ms4 * 1e3, "unit": "tokens/s", "ms_per_step": ms4, "per_gpu_batch": 4,
+                            "note": "reference batch_size (config YAML); same step, 8 192 tokens"}
+        del db
     if rank == 0 and world == 1 and not args.no_decode:
         del devb, opt, sync
         model.zero_grad()
         torch.cuda.empty_cache()
         line["decode"] = bench_decode(model, V, cpu=not args.no_cpu_baseline)
+    if rank == 0 and world == 1 and not args.no_extras:
+        model = None
+        torch.cuda.empty_cache()
+        for key, fn in (("gpt2_train", lambda: bench_gpt2_train(cpu=not args.no_cpu_baseline)),
+                        ("stage1_train", lambda: bench_stage1_train(cpu=not args.no_cpu_baseline)),
+                        ("two_stage_generate", bench_two_stage_generate)):
+            try:
+                line[key] = fn()
+            except Exception as e:                 # an extra leg must never cost the headline line
+                line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_train import time_cpu_train
         r = time_cpu_train(V=V, B=1, T=T, steps=3, warmup=1)

@@ -69,3 +69,70 @@ def time_cpu_train(V=329, B=1, T=2048, steps=3, warmup=1, threads=None, n_layer=
     return {"value": B * T * steps / tot, "ms_per_step": 1e3 * tot / steps, "cores": cores,
             "sample": "%d step(s) of B=%d x T=%d (V=%d, %d layers, fp32 torch on host, dropout 0.1, Omega redrawn "
                       "per forward); %d warm-up" % (steps, B, T, V, n_layer, warmup)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU twins of the other two train steps (BASELINE.json configs[2] and configs[0]); eval-mode math of the oracle
+# (no dropout: dropout is a negligible share of a CPU step) + CE + backward + clip_grad_norm_(0.5) + Adam
+# ------------------------------------------------------------------------------------------------
+def _time_steps(step, units, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    tot = time.perf_counter() - t0
+    return units * steps / tot, 1e3 * tot / steps
+
+
+def time_cpu_train_gpt2(V=372, B=1, T=2048, steps=1, warmup=1, threads=None, n_layer=12):
+    """stage2_accompaniment/train.py:58-81 with -m gpt2 (music_gpt2.py + HF GPT2Block) over oracle/gpt2_oracle.py"""
+    import os
+    from . import gpt2_oracle as GO
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = PO.seeded_state(GO.gpt2_state_shapes(V, n_layer), 0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    full = dict(params)
+    full["pe.pe"] = PO.sinusoid_pe(12000, 512)
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    tok, seg, tgt = synthetic_batch(V, B, T, 0)
+
+    def step():
+        logits = GO.gpt2_forward(full, tok, seg, n_layer, 8, 512)
+        loss = PO.ce_loss(logits, tgt, V - 1)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 0.5)
+        opt.step()
+    v, ms = _time_steps(step, B * T, steps, warmup)
+    return {"value": v, "ms_per_step": ms, "cores": cores,
+            "sample": "%d step(s) of B=%d x T=%d (REMI V=%d, %d GPT-2 blocks, fp32 torch on host, O(T^2) attention); %d warm-up"
+                      % (steps, B, T, V, n_layer, warmup)}
+
+
+def time_cpu_train_stage1(V=216, B=1, T=512, steps=2, warmup=1, threads=None, n_layer=12):
+    """stage1_compose/train.py:48-65 (PlainTransformer, mem_len 0 in training) over oracle/txl_oracle.py, which is
+    pinned against the unmodified reference model (oracle/validate_against_reference.py)"""
+    import os
+    from . import txl_oracle as TO
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = PO.seeded_state(TO.txl_state_shapes(V, n_layer), 0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, V - 1, (T, B), generator=g)
+    tgt = torch.roll(tok, -1, 0)
+
+    def step():
+        logits, _ = TO.txl_forward(params, tok, None, n_layer, 8, 512, 0)
+        loss = F.cross_entropy(logits.view(-1, V), tgt.view(-1), ignore_index=V - 1)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 0.5)
+        opt.step()
+    v, ms = _time_steps(step, B * T, steps, warmup)
+    return {"value": v, "ms_per_step": ms, "cores": cores,
+            "sample": "%d step(s) of T=%d x B=%d (functional lead-sheet V=%d, %d Transformer-XL layers, fp32 torch on host); "
+                      "%d warm-up" % (steps, T, B, V, n_layer, warmup)}

@@ -213,8 +213,9 @@ def test_stage1_token_store_batches_equal_reference_golden():
 
 @pytest.mark.parametrize("stage", [1, 2])
 def test_token_store_loader_shards_an_epoch_across_ranks(stage, monkeypatch):
-    """data parallel (SURVEY 8e): with the `random` module seeded alike, rank r of `world` takes batches r::world of
-    the same shuffled order -- disjoint, and together one full epoch.  Host logic only (batch() is stubbed)."""
+    """data parallel (SURVEY 8e): rank r of `world` takes batches r::world of ONE shuffled order drawn from
+    Random(seed + epoch) -- never the process-global `random` state, which differs per rank -- disjoint, the same number
+    of batches on every rank.  Host logic only (batch() is stubbed)."""
     from emo_disentanger_b200.data import Stage1TokenStore, Stage2TokenStore
     if stage == 1:
         g = golden("stage1_dataset.npz")
@@ -225,11 +226,12 @@ def test_token_store_loader_shards_an_epoch_across_ranks(stage, monkeypatch):
     monkeypatch.setattr(type(st), "batch", lambda self, idx, *a: list(idx))
     per_rank = []
     for r in range(2):
-        random.seed(123)
-        per_rank.append(list(st.loader(batch_size=2, shuffle=True, rank=r, world=2)))
-    random.seed(123)
-    whole = list(st.loader(batch_size=2, shuffle=True))
-    assert whole[0::2] == per_rank[0] and whole[1::2] == per_rank[1]
+        random.seed(1000 + r)                  # ranks do NOT share the global RNG state
+        per_rank.append(list(st.loader(batch_size=2, shuffle=True, rank=r, world=2, seed=9, epoch=1)))
+    whole = list(st.loader(batch_size=2, shuffle=True, seed=9, epoch=1))
+    n_even = len(whole) // 2 * 2
+    assert whole[0:n_even:2] == per_rank[0] and whole[1:n_even:2] == per_rank[1]
+    assert len(per_rank[0]) == len(per_rank[1])
     flat = [p for b in whole for p in b]
     assert sorted(flat) == list(range(len(st))) and all(len(b) <= 2 for b in whole)
     random.seed(123)
