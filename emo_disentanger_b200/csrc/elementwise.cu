@@ -223,8 +223,12 @@ template <typename T> struct RowRegs {
   }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+// RES: the row is x + res, summed in fp32 (x = the projection's output WITHOUT its residual, res = the sub-layer's
+// input).  The pre-LN sum then never exists as a rounded 16-bit tensor on the forward path -- at 12 layers that
+// rounding is a quarter of the bf16 hidden-state error -- and sum_out (optional) keeps a copy for the backward.
+template <typename T, bool RES>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                     T* __restrict__ sum_out, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, T* __restrict__ y,
                                                      float* __restrict__ mean, float* __restrict__ rstd,
                                                      int64_t rows, float eps) {
@@ -248,31 +252,48 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
       g_[j * R::N + i] = g4.x; g_[j * R::N + i + 1] = g4.y; g_[j * R::N + i + 2] = g4.z; g_[j * R::N + i + 3] = g4.w;
       b_[j * R::N + i] = b4.x; b_[j * R::N + i + 1] = b4.y; b_[j * R::N + i + 2] = b4.z; b_[j * R::N + i + 3] = b4.w;
     }
-  uint4 q[DEPTH][R::NV];                  // ring of raw rows: q[k] = row + k * wstride
-  auto fetch = [&](uint4 (&dst)[R::NV], int64_t r) {
+  constexpr int NS = RES ? 2 : 1;
+  uint4 q[DEPTH][NS][R::NV];              // ring of raw rows: q[k] = row + k * wstride
+  auto fetch = [&](uint4 (&dst)[NS][R::NV], int64_t r) {
     if (r < rows) {
 #pragma unroll
-      for (int j = 0; j < R::NV; ++j) dst[j] = *reinterpret_cast<const uint4*>(x + r * LN_D + R::col(j, lane));
+      for (int j = 0; j < R::NV; ++j) dst[0][j] = *reinterpret_cast<const uint4*>(x + r * LN_D + R::col(j, lane));
+      if constexpr (RES) {
+#pragma unroll
+        for (int j = 0; j < R::NV; ++j) dst[1][j] = *reinterpret_cast<const uint4*>(res + r * LN_D + R::col(j, lane));
+      }
+    }
+  };
+  auto unpack = [&](const uint4 (&src)[R::NV], R& r) {
+#pragma unroll
+    for (int j = 0; j < R::NV; ++j) {
+      if constexpr (sizeof(T) == 2) {
+        unpack_bf16x2(src[j].x, r.v[j * 8], r.v[j * 8 + 1]); unpack_bf16x2(src[j].y, r.v[j * 8 + 2], r.v[j * 8 + 3]);
+        unpack_bf16x2(src[j].z, r.v[j * 8 + 4], r.v[j * 8 + 5]); unpack_bf16x2(src[j].w, r.v[j * 8 + 6], r.v[j * 8 + 7]);
+      } else {
+        r.v[j * 4] = __uint_as_float(src[j].x); r.v[j * 4 + 1] = __uint_as_float(src[j].y);
+        r.v[j * 4 + 2] = __uint_as_float(src[j].z); r.v[j * 4 + 3] = __uint_as_float(src[j].w);
+      }
     }
   };
 #pragma unroll
   for (int k = 0; k < DEPTH; ++k) fetch(q[k], row + k * wstride);
   for (; row < rows; row += wstride) {
     R r;
+    unpack(q[0][0], r);
+    if constexpr (RES) {
+      R r2;
+      unpack(q[0][1], r2);
 #pragma unroll
-    for (int j = 0; j < R::NV; ++j) {
-      if constexpr (sizeof(T) == 2) {
-        unpack_bf16x2(q[0][j].x, r.v[j * 8], r.v[j * 8 + 1]); unpack_bf16x2(q[0][j].y, r.v[j * 8 + 2], r.v[j * 8 + 3]);
-        unpack_bf16x2(q[0][j].z, r.v[j * 8 + 4], r.v[j * 8 + 5]); unpack_bf16x2(q[0][j].w, r.v[j * 8 + 6], r.v[j * 8 + 7]);
-      } else {
-        r.v[j * 4] = __uint_as_float(q[0][j].x); r.v[j * 4 + 1] = __uint_as_float(q[0][j].y);
-        r.v[j * 4 + 2] = __uint_as_float(q[0][j].z); r.v[j * 4 + 3] = __uint_as_float(q[0][j].w);
-      }
+      for (int i = 0; i < E; ++i) r.v[i] += r2.v[i];
+      if (sum_out) r.store(sum_out + row * LN_D, lane);
     }
 #pragma unroll
     for (int k = 0; k + 1 < DEPTH; ++k)
 #pragma unroll
-      for (int j = 0; j < R::NV; ++j) q[k][j] = q[k + 1][j];
+      for (int s_ = 0; s_ < NS; ++s_)
+#pragma unroll
+        for (int j = 0; j < R::NV; ++j) q[k][s_][j] = q[k + 1][s_][j];
     fetch(q[DEPTH - 1], row + DEPTH * wstride);
     float s = 0.f;
 #pragma unroll
@@ -292,19 +313,35 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   }
 }
 
+static int ln_fwd_launch(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y,
+                         float* mean, float* rstd, int64_t rows, float eps, int dtype, cudaStream_t s) {
+  int64_t want = (rows + 7) / 8;
+  int blocks = (int)(want < (int64_t)emo_num_sms() * 8 ? want : (int64_t)emo_num_sms() * 8);
+  if (dtype == EMO_BF16) {
+    if (res) ln_fwd_kernel<bf16, true><<<blocks, 256, 0, s>>>((const bf16*)x, (const bf16*)res, (bf16*)sum_out, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+    else ln_fwd_kernel<bf16, false><<<blocks, 256, 0, s>>>((const bf16*)x, nullptr, nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+  } else {
+    if (res) ln_fwd_kernel<float, true><<<blocks, 256, 0, s>>>((const float*)x, (const float*)res, (float*)sum_out, gamma, beta, (float*)y, mean, rstd, rows, eps);
+    else ln_fwd_kernel<float, false><<<blocks, 256, 0, s>>>((const float*)x, nullptr, nullptr, gamma, beta, (float*)y, mean, rstd, rows, eps);
+  }
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+
 extern "C" int emo_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                           float* rstd, int64_t rows, int d, float eps, int dtype, void* stream) {
   EMO_REQUIRE(d == LN_D, "emo_ln_fwd: d must be 512 (got %d)", d);
   if (rows == 0) return EMO_OK;
-  int64_t want = (rows + 7) / 8;
-  int blocks = (int)(want < (int64_t)emo_num_sms() * 8 ? want : (int64_t)emo_num_sms() * 8);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == EMO_BF16)
-    ln_fwd_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
-  else
-    ln_fwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, gamma, beta, (float*)y, mean, rstd, rows, eps);
-  EMO_LAUNCH_CHECK();
-  return EMO_OK;
+  return ln_fwd_launch(x, nullptr, nullptr, gamma, beta, y, mean, rstd, rows, eps, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int emo_ln_res_fwd(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta,
+                              void* y, float* mean, float* rstd, int64_t rows, int d, float eps, int dtype,
+                              void* stream) {
+  EMO_REQUIRE(d == LN_D, "emo_ln_res_fwd: d must be 512 (got %d)", d);
+  EMO_REQUIRE(res != nullptr, "emo_ln_res_fwd: res is required (use emo_ln_fwd without a residual)");
+  if (rows == 0) return EMO_OK;
+  return ln_fwd_launch(x, res, sum_out, gamma, beta, y, mean, rstd, rows, eps, dtype, (cudaStream_t)stream);
 }
 
 template <typename T>

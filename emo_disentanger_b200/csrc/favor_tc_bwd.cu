@@ -451,7 +451,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         {
           const float ss = row_sumsq(g ? sXK : sXQ, r);
-          mbar_arrive(bar(F_X));
+          mbar_arrive_after_reads(bar(F_X), ss);
           const float o = rowok ? (0.5f * F_S2 * ss + F_HALF_LOG_M) * K2 : __int_as_float(0x7f800000);   // +inf -> phi = 0
           phi_row_to_smem(tl + T_W1 + 64 * g, g ? sPK : sPQ, r, o);
         }

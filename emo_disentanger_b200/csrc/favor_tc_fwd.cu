@@ -198,7 +198,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           unpack_bf16x2(bq.x, f0, f1); ssk += f0 * f0 + f1 * f1; unpack_bf16x2(bq.y, f0, f1); ssk += f0 * f0 + f1 * f1;
           unpack_bf16x2(bq.z, f0, f1); ssk += f0 * f0 + f1 * f1; unpack_bf16x2(bq.w, f0, f1); ssk += f0 * f0 + f1 * f1;
         }
-        mbar_arrive(bar_xf);
+        mbar_arrive_after_reads(bar_xf, ssq + ssk);
         const float oq = (0.5f * F_S2 * ssq + F_HALF_LOG_M) * K2, ok = (0.5f * F_S2 * ssk + F_HALF_LOG_M) * K2;
         // ---- phi(k) -> smem (rows past the end of the sequence are zero: they must not enter the state) ----
 #pragma unroll

@@ -21,6 +21,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that releases shared memory this thread has READ (a "buffer free" signal to a TMA producer).  An mbarrier
+// arrive does not wait for earlier ld.shared instructions whose results it does not use: MEASURED on B200, a plain
+// arrive right after the loads let the next chunk's TMA overwrite rows that were still being read (a few rows per
+// ~1000 CTAs got a wrong |q|^2).  `dep` must be computed from every loaded value; the barrier address is made to
+// depend on it (the compared pattern is a NaN no arithmetic produces, so the offset is always 0).
+__device__ __forceinline__ void mbar_arrive_after_reads(uint32_t bar, float dep) {
+  const uint32_t off = (__float_as_uint(dep) == 0xFFFFFFFFu) ? 8u : 0u;
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar + off) : "memory");
+}
 // parity wait; try_wait suspends in hardware up to the hint, the spin counter is a watchdog (a protocol bug traps
 // after a few seconds instead of hanging the GPU)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

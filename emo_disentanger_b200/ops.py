@@ -119,6 +119,14 @@ def ln_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
+def ln_res_fwd(x, res, gamma, beta, y, mean=None, rstd=None, sum_out=None, eps=1e-5):
+    """y = LN(x + res), the sum formed in fp32 in the kernel; sum_out (optional) = x + res for ln_bwd"""
+    rows = x.numel() // x.shape[-1]
+    _call("emo_ln_res_fwd", _p(x), _p(res), _p(sum_out), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows,
+          x.shape[-1], eps, _dt(x), _stream())
+    return y
+
+
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0, dxsum=None):
     """dxsum (fp32 [d]) += column sums of dx_drop (or dx): the bias gradient of the projection below."""
     rows = x.numel() // x.shape[-1]

@@ -109,20 +109,24 @@ class MusicPerformer(Stage2Base):
             den = new(B, T, H, dtype=torch.float32) if save else None
             state = ops.favor_workspace(B, T, H, dt, dev)      # segment-state sums (kept for backward when save)
             ops.favor_fwd(q, k, v, omegas[l], att.view(B, T, d), den, seg_states=state)
-            s1 = new(R, d)
-            ops.linear_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"), s1,
+            # the residual joins inside the LN kernel, in fp32: x + dropout(attn) is never rounded to bf16 on the
+            # way into norm1 / norm2 (s1 / s2 below are the copies the backward re-normalises)
+            b1 = new(R, d)
+            ops.linear_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"), b1,
                            bias=self._wv(Wf, nm + "attention.out_projection.bias"),
-                           drop_p=p, seed=site_seed(seed, 4 * l + 1), residual=h_in, ld_res=d)
+                           drop_p=p, seed=site_seed(seed, 4 * l + 1))
             y1, m1, r1 = new(R, d), new(R, dtype=torch.float32), new(R, dtype=torch.float32)
-            ops.ln_fwd(s1, self._wv(Wf, nm + "norm1.weight"), self._wv(Wf, nm + "norm1.bias"), y1, m1, r1)
+            s1 = b1 if save else None            # in place: each lane rewrites exactly the elements it has read
+            ops.ln_res_fwd(b1, h_in, self._wv(Wf, nm + "norm1.weight"), self._wv(Wf, nm + "norm1.bias"), y1, m1, r1, sum_out=s1)
             hh = new(R, f)
             ops.linear_fwd(y1, self._wv(Wc, nm + "linear1.weight"), hh, bias=self._wv(Wf, nm + "linear1.bias"),
                            act=ops.ACT_RELU, drop_p=p, seed=site_seed(seed, 4 * l + 2))
-            s2 = new(R, d)
-            ops.linear_fwd(hh, self._wv(Wc, nm + "linear2.weight"), s2, bias=self._wv(Wf, nm + "linear2.bias"),
-                           drop_p=p, seed=site_seed(seed, 4 * l + 3), residual=y1, ld_res=d)
+            b2 = new(R, d)
+            ops.linear_fwd(hh, self._wv(Wc, nm + "linear2.weight"), b2, bias=self._wv(Wf, nm + "linear2.bias"),
+                           drop_p=p, seed=site_seed(seed, 4 * l + 3))
             out, m2, r2 = new(R, d), new(R, dtype=torch.float32), new(R, dtype=torch.float32)
-            ops.ln_fwd(s2, self._wv(Wf, nm + "norm2.weight"), self._wv(Wf, nm + "norm2.bias"), out, m2, r2)
+            s2 = b2 if save else None
+            ops.ln_res_fwd(b2, y1, self._wv(Wf, nm + "norm2.weight"), self._wv(Wf, nm + "norm2.bias"), out, m2, r2, sum_out=s2)
             if save:
                 layers.append((h_in, qkv, att, den, state, s1, m1, r1, y1, hh, s2, m2, r2))
             h_in = out

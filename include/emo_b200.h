@@ -107,6 +107,13 @@ int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int6
  * optimus_txl_decoder.py:52,318.  Saves mean/rstd (fp32 [rows]) for backward. */
 int emo_ln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                float* rstd, int64_t rows, int d, float eps, int dtype, void* stream);
+/* y = LN(x + res) with the sum formed in fp32 inside the kernel: x is a projection's output WITHOUT its residual
+ * (out_projection / linear2 after dropout), res the sub-layer's input (TransformerEncoderLayer.forward:
+ * `x = norm1(x + dropout(attn))`, `norm2(x + y)`).  sum_out (may be NULL) receives x + res rounded to the
+ * compute dtype: the tensor emo_ln_bwd re-normalises. */
+int emo_ln_res_fwd(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta,
+                   void* y, float* mean, float* rstd, int64_t rows, int d, float eps, int dtype,
+                   void* stream);
 /* dx = LNgrad(dy) (+ add_in if non-NULL).  If dx_drop != NULL also writes
  * dx_drop = dx * dropmask(seed)/(1-p) (gradient entering a `x + dropout(proj)` branch).
  * dgamma/dbeta (fp32 [d]) are ACCUMULATED (atomics).  dxsum (fp32 [d], may be NULL) += column sums of

@@ -303,6 +303,30 @@ def test_layernorm_fwd_bwd(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("R", [1, 37, 5000])
+def test_layernorm_with_fp32_residual_sum(ops, dtype, R):
+    """emo_ln_res_fwd: y = LN(x + res) with the sum in fp32 (never rounded to the compute dtype); sum_out may alias x"""
+    torch.manual_seed(8)
+    x = (torch.randn(R, 512, device=DEV) * 0.3).to(dtype)
+    res = (torch.randn(R, 512, device=DEV) * 2 + 0.5).to(dtype)
+    gamma, beta = 1 + 0.1 * torch.randn(512, device=DEV), 0.1 * torch.randn(512, device=DEV)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(R, device=DEV), torch.empty(R, device=DEV)
+    s = x.float() + res.float()
+    yr = torch.nn.functional.layer_norm(s, (512,), gamma, beta, 1e-5)
+    ops.ln_res_fwd(x, res, gamma, beta, y, mean, rstd)
+    # bf16: the only rounding left is the output's (half an ulp of each element)
+    assert rel_err(y.float(), yr) < (1e-5 if dtype == torch.float32 else 4e-3)
+    assert torch.equal(y, yr.to(dtype)) or dtype == torch.float32 or (y.float() - yr).abs().max() <= yr.abs().max() * 2 ** -8
+    assert rel_err(mean, s.mean(-1)) < 1e-5 and rel_err(rstd, (s.var(-1, unbiased=False) + 1e-5).rsqrt()) < 1e-5
+    # sum_out in place of x: same y, x now holds the rounded sum
+    y2, xs = torch.empty_like(x), x.clone()
+    ops.ln_res_fwd(xs, res, gamma, beta, y2, mean, rstd, sum_out=xs)
+    assert torch.equal(y2, y)
+    assert torch.equal(xs, s.to(dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,ld", [(5000, 512, 512), (777, 329, 336), (64, 1536, 4608), (100, 331, 331)])
 def test_colsum(ops, dtype, M, N, ld):
     torch.manual_seed(M)
@@ -681,3 +705,31 @@ def test_favor_tcgen05_forward_equals_mma_sync_forward(ops, B, T):
     assert rms_rel(o1, o0) < 1e-2 and rms_rel(d1, d0) < 1e-2
     assert rms_rel(s1, s0) < 1e-4 and rms_rel(w1, s1) < 1e-6          # final prefix state: fp32 accumulation in both
     assert float(s1[:, :, :, 65:].abs().max()) == 0.0
+
+
+def test_favor_tcgen05_is_bit_reproducible_at_bench_shape(ops):
+    """The tcgen05 forward / backward at the bench shape (592 (batch, head) items, 2 CTAs per SM, 16 chunks each), run
+    repeatedly on the same inputs, must give the same bits (normaliser included).  Guards the shared-memory hand-over
+    between the worker warps' row reads and the next chunk's TMA (an mbarrier arrive does not wait for earlier
+    ld.shared: tc_ptx.cuh, mbar_arrive_after_reads)."""
+    B, T, H = 74, 2048, 8
+    qkv, omega = _favor_inputs(B, T, H, scale=0.7, seed=77)
+    qkv_d = _bf(qkv.to(DEV))
+    q, k, v = _split(qkv_d, H)
+    om = omega.to(DEV)
+    dout = _bf(torch.randn(B, T, H * 64, device=DEV))
+    ws = ops.favor_workspace(B, T, H, torch.bfloat16, DEV)
+    ref = None
+    for it in range(12):
+        out = torch.empty(B, T, H * 64, device=DEV, dtype=torch.bfloat16)
+        den = torch.empty(B, T, H, device=DEV)
+        ops.favor_fwd(q, k, v, om, out, den, seg_states=ws)
+        dqkv = torch.empty_like(qkv_d)
+        dq, dk, dv = _split(dqkv, H)
+        ops.favor_bwd(q, k, v, om, out, dout, den, ws, dq, dk, dv)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (out, den, dqkv)
+        else:
+            assert torch.equal(out, ref[0]) and torch.equal(den, ref[1]), "forward differs on repeat %d" % it
+            assert torch.equal(dqkv, ref[2]), "backward differs on repeat %d" % it
