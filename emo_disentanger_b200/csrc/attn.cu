@@ -389,6 +389,16 @@ __global__ void __launch_bounds__(BG_THREADS) attn_bwd_dq_kernel(const AttnArgs 
 // ---------------------------------------------------------------------------------------------
 static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// attn_tc.cu: the tcgen05 + TMA kernels (bf16, no relative positions); EMO_ATTN_TC=0 / emo_attn_set_tc(0) switch back
+int emo_attn_tc_enabled();
+int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
+                           float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s);
+int emo_attn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* out,
+                           const void* dout, int64_t ld_o, const float* lse, void* dq, void* dk, void* dv, int64_t ld_dq,
+                           int64_t ld_dkv, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s);
+// a 128-row query tile per CTA: below this many queries (decode steps) the 64-row mma.sync tiles waste less
+constexpr int ATTN_TC_MIN_TQ = 64;
+
 template <typename T, bool REL> static int attn_fwd_launch(const AttnArgs& a, cudaStream_t s) {
   constexpr int BQ = AttnCfg<T>::BQ;
   size_t smem = sizeof(AttnSmemFwd<T, REL>);
@@ -440,6 +450,8 @@ extern "C" int emo_attn_fwd(const void* q, const void* k, const void* v, int64_t
   if (rc) return rc;
   EMO_REQUIRE(al16(out), "emo_attn_fwd: out must be 16-byte aligned");
   if (B * H == 0 || Tq == 0) return EMO_OK;
+  if (dtype == EMO_BF16 && emo_attn_tc_enabled() && Tq >= ATTN_TC_MIN_TQ && scale > 0.f)
+    return emo_attn_fwd_tc_launch(q, k, v, ld_q, ld_kv, out, ld_out, lse, B, Tq, Tk, H, scale, drop_p, seed, (cudaStream_t)stream);
   if (dtype == EMO_BF16) return attn_fwd_launch<bf16, false>(a, (cudaStream_t)stream);
   return attn_fwd_launch<float, false>(a, (cudaStream_t)stream);
 }
@@ -457,6 +469,9 @@ extern "C" int emo_attn_bwd(const void* q, const void* k, const void* v, int64_t
               "emo_attn_bwd: gradient pointers / strides must be 16-byte aligned");
   EMO_REQUIRE(lse != nullptr, "emo_attn_bwd: lse is required");
   if (B * H == 0 || Tq == 0) return EMO_OK;
+  if (dtype == EMO_BF16 && emo_attn_tc_enabled() && Tq >= ATTN_TC_MIN_TQ && scale > 0.f)
+    return emo_attn_bwd_tc_launch(q, k, v, ld_q, ld_kv, out, dout, ld_out, lse, dq, dk, dv, ld_dq, ld_dkv, B, Tq, Tk, H, scale, drop_p, seed,
+                                  (cudaStream_t)stream);
   if (dtype == EMO_BF16) return attn_bwd_launch<bf16, false>(a, (cudaStream_t)stream);
   return attn_bwd_launch<float, false>(a, (cudaStream_t)stream);
 }

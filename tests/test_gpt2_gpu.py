@@ -23,7 +23,10 @@ def _ref_attn(q, k, v, scale):
 
 
 @pytest.mark.parametrize("dtype,Tq,Tk", [(torch.float32, 70, 70), (torch.float32, 33, 97), (torch.bfloat16, 200, 200),
-                                          (torch.bfloat16, 64, 64), (torch.bfloat16, 1, 130), (torch.bfloat16, 1, 1)])
+                                          (torch.bfloat16, 64, 64), (torch.bfloat16, 1, 130), (torch.bfloat16, 1, 1),
+                                          # tcgen05 path (Tq >= 64): ragged tiles, Tq < Tk with an offset that is not a tile multiple
+                                          (torch.bfloat16, 128, 128), (torch.bfloat16, 333, 333), (torch.bfloat16, 130, 300),
+                                          (torch.bfloat16, 640, 1000), (torch.bfloat16, 1024, 1024)])
 def test_attention_fwd_bwd_vs_torch(dtype, Tq, Tk):
     from emo_disentanger_b200 import ops
     B, H = 2, 8
@@ -90,6 +93,39 @@ def test_attention_dropout_mask_consistent_fwd_bwd():
     out0 = torch.empty_like(out)
     ops.attn_fwd(q, k, v, out0, lse, 0.125)
     assert rel_err(out, out0) > 1e-2
+
+
+@pytest.mark.parametrize("B,T,p", [(2, 2048, 0.0), (2, 2048, 0.1), (3, 700, 0.25)])
+def test_attention_tcgen05_equals_mma_sync(B, T, p):
+    """the tcgen05 + TMA attention (128 x 128 tiles, P / P^T as tensor-memory operands, fp32 dQ reductions) against the
+    round-1 mma.sync kernels (64 x 64 tiles): two independent implementations of the same math and the SAME dropout
+    mask (with p > 0 a different mask would show as O(1) differences)"""
+    from emo_disentanger_b200 import ops, _lib
+    H, d = 8, 512
+    g = torch.Generator().manual_seed(100 + T)
+    x = torch.randn(B, T, 3 * d, generator=g).to(DEV).to(torch.bfloat16)
+    dout = torch.randn(B, T, d, generator=g).to(DEV).to(torch.bfloat16)
+    q, k, v = (x[:, :, i * d:(i + 1) * d].unflatten(-1, (H, 64)) for i in range(3))
+    res = []
+    for tc in (1, 0):
+        _lib.lib().emo_attn_set_tc(tc)
+        try:
+            out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+            lse = torch.empty(B, H, T, device=DEV)
+            ops.attn_fwd(q, k, v, out, lse, 0.125, p, 4242)
+            dx = torch.empty_like(x)
+            dq, dk, dv = (dx[:, :, i * d:(i + 1) * d].unflatten(-1, (H, 64)) for i in range(3))
+            ops.attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, 0.125, p, 4242)
+            torch.cuda.synchronize()
+            res.append((out.float(), lse, dx.float()))
+        finally:
+            _lib.lib().emo_attn_set_tc(1)
+    (o1, l1, g1), (o0, l0, g0) = res
+    assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
+    assert rms_rel(o1, o0) < 6e-3
+    assert float((l1 - l0).abs().max()) < 2e-3
+    for i, nm in enumerate("qkv"):
+        assert rms_rel(g1[:, :, i * d:(i + 1) * d], g0[:, :, i * d:(i + 1) * d]) < 1.5e-2, "d" + nm
 
 
 def test_attention_causal_prefix_invariance_full_size():
