@@ -246,42 +246,87 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // backward
 // ------------------------------------------------------------------------------------------------------------------
 namespace bwd {
-constexpr int NT = 288, NST = 3;
+constexpr int NW = 16, NT = 32 * (NW + 1), NST = 3;      // 16 worker warps (4 per TMEM lane quadrant) + 1 control warp
 constexpr uint32_t OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE /* x3 */, OFF_DO = 5 * TILE /* x3 */, OFF_DS = 8 * TILE /* x2 */,
-                   OFF_L = 10 * TILE /* lse2[3][128] */, OFF_D = OFF_L + NST * 512, OFF_BAR = OFF_D + NST * 512, SMEM_USED = OFF_BAR + 128;
+                   OFF_DQ = 10 * TILE /* 16 warps x [32 rows][16 fp32] */, OFF_L = 12 * TILE /* lse2[3][128] */, OFF_D = OFF_L + NST * 512,
+                   OFF_BAR = OFF_D + NST * 512, SMEM_USED = OFF_BAR + 128;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "one CTA per SM");
 constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384, T_P = 448, T_COLS = 512;
 constexpr uint32_t LD_BYTES = 2 * TILE + 2 * 512;
 
 struct Params {
-  const float* lse2; const float* dsum;        // [B*H][Tq_pad]: lse * log2(e) (+inf past Tq), rowsum(dO * O)
-  float* dqacc;                                // fp32 [B][Tq][H*64], zeroed
+  const float* lse2; const float* dsum;        // [B*H][Tq_pad]: lse * log2(e) (+inf past Tq), scale * rowsum(dO * O)
   bf16* dk; bf16* dv; int64_t ld_dkv;
   int Tq, Tk, Tq_pad, H, nqt;
   float scale, sl2, keep_scale;
   uint32_t drop_thr; uint64_t seed;
-  int dbg_skip_dq;
-  long long* dbg_clk;                          // optional [2][16] clock64 stamps of tile 3 of CTA (0, 0): control / worker 0
+  int drop_fast;                               // Tk even and fewer than 2^32 element pairs: one 32-bit hash per (query, key pair)
+  long long* dbg_clk;                          // optional: clock64 stamps of worker thread 0, tiles 3 and 4 of CTA (0, 0)
 };
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+
+// Element-wise pass of one thread: 32 query columns of key row j.  s = raw S^T, dp = raw dP^T (fp32 bits);
+// P = exp2(s * sl2 - lse2), dS = P * (dP_dropped - D) * scale  (aD holds D * scale).  DROP == 1: the fast mask (the two
+// lanes of a key pair share one hash per query column: each computes every other column and they swap);
+// DROP == 2: the general per-element mask.
+template <bool DIAG, int DROP>
+__device__ __forceinline__ void ew_pass(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint32_t aL, uint32_t aD, int cmin,
+                                        const Params& p, uint32_t pbase, uint32_t key, int lane, uint64_t e_base,
+                                        uint32_t (&pk)[16], uint32_t (&dsk)[16]) {
+  const float kss = p.keep_scale * p.scale;
+  const uint32_t odd = lane & 1, sel = odd ? 0x4432u : 0x4410u, pstep = (uint32_t)p.Tk >> 1;
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {                           // 4 query columns at a time
+    const uint4 l4 = lds128(aL + 16 * c4), d4 = lds128(aD + 16 * c4);
+    const float lv[4] = {__uint_as_float(l4.x), __uint_as_float(l4.y), __uint_as_float(l4.z), __uint_as_float(l4.w)};
+    const float dv_[4] = {__uint_as_float(d4.x), __uint_as_float(d4.y), __uint_as_float(d4.z), __uint_as_float(d4.w)};
+    bool keep[4] = {true, true, true, true};
+    if (DROP == 1) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const uint32_t hm = emo_drop_mix(pbase + (uint32_t)(4 * c4 + 2 * m + odd) * pstep, key);
+        const uint32_t ho = __shfl_xor_sync(0xffffffffu, hm, 1);
+        keep[2 * m] = __byte_perm(odd ? ho : hm, 0, sel) >= p.drop_thr;
+        keep[2 * m + 1] = __byte_perm(odd ? hm : ho, 0, sel) >= p.drop_thr;
+      }
+    } else if (DROP == 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) keep[e] = emo_drop_keep(p.seed, e_base + (uint64_t)(4 * c4 + e) * (uint64_t)p.Tk, p.drop_thr);
+    }
+    float pd[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * c4 + e;
+      float pv = ex2(fmaf(__uint_as_float(s[c]), p.sl2, -lv[e]));
+      if (DIAG) pv = (c >= cmin) ? pv : 0.f;
+      const float dpv = __uint_as_float(dp[c]);
+      if (DROP) {
+        pd[e] = keep[e] ? pv * p.keep_scale : 0.f;
+        ds[e] = pv * (keep[e] ? fmaf(dpv, kss, -dv_[e]) : -dv_[e]);
+      } else {
+        pd[e] = pv;
+        ds[e] = pv * fmaf(dpv, p.scale, -dv_[e]);
+      }
+    }
+    pk[2 * c4] = pack_bf16x2(pd[0], pd[1]); pk[2 * c4 + 1] = pack_bf16x2(pd[2], pd[3]);
+    dsk[2 * c4] = pack_bf16x2(ds[0], ds[1]); dsk[2 * c4 + 1] = pack_bf16x2(ds[2], ds[3]);
+  }
 }
 
-#define WAIT(bar, par) do { if (p.dbg_skip_dq & 8) mbar_wait_poll(bar, par); else mbar_wait(bar, par); } while (0)
 __global__ void __launch_bounds__(NT, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ Params p) {
+                   const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(smem);
-  const uint32_t sK = sb + OFF_K, sV = sb + OFF_V, sQ = sb + OFF_Q, sDO = sb + OFF_DO, sDS = sb + OFF_DS, sL = sb + OFF_L, sD = sb + OFF_D;
+  const uint32_t sK = sb + OFF_K, sV = sb + OFF_V, sQ = sb + OFF_Q, sDO = sb + OFF_DO, sDS = sb + OFF_DS, sDQ = sb + OFF_DQ, sL = sb + OFF_L,
+                 sD = sb + OFF_D;
   const uint32_t bar_kv = sb + OFF_BAR, bar_ld = bar_kv + 8 /* x3 */, bar_s = bar_kv + 32, bar_sfree = bar_kv + 40, bar_p = bar_kv + 48,
                  bar_acc = bar_kv + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
@@ -290,114 +335,117 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
   const int j0 = kt * BN, off = p.Tk - p.Tq;
   const int qt0 = (j0 - off > 0) ? (j0 - off) / BM : 0;        // first query tile with a row that sees key j0
-  const int n = p.nqt - qt0;
+  const int n = p.nqt - qt0;                                   // >= 1 (Tk >= Tq)
 
-  if (tid == 256) {
-    prefetch_map(&tmQ); prefetch_map(&tmK); prefetch_map(&tmV); prefetch_map(&tmDO);
+  if (tid == 32 * NW) {
+    prefetch_map(&tmQ); prefetch_map(&tmK); prefetch_map(&tmV); prefetch_map(&tmDO); prefetch_map(&tmDQ);
     mbar_init(bar_kv, 1);
     for (int s_ = 0; s_ < NST; ++s_) mbar_init(bar_ld + 8 * s_, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_sfree, 256); mbar_init(bar_p, 256); mbar_init(bar_acc, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_sfree, 32 * NW); mbar_init(bar_p, 32 * NW); mbar_init(bar_acc, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), T_COLS);
+  if (warp == NW) tmem_alloc(smem_u32(tmem_slot), T_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (n <= 0) {                                                // (cannot happen for Tk >= Tq; keeps the barriers balanced)
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, T_COLS);
-    return;
-  }
 
   constexpr uint32_t ID_T = make_idesc(128, false, false),     // S^T, dP^T: both operands K-major
                      ID_KM = make_idesc(64, false, true),      // dV, dK: A K-major (TMEM / smem), B MN-major
                      ID_MM = make_idesc(64, true, true);       // dQ: A = dS^T tile read MN-major, B MN-major
 
-  if (warp == 8) {
-    // ================================ control: TMA + MMA issue ================================
-    if (lane == 0) {
-      auto load_tile = [&](int t) {
-        const uint32_t st = t % NST, bar = bar_ld + 8 * st;
-        const int i0 = (qt0 + t) * BM;
+  if (warp == NW) {
+    // ================================ control warp: all lanes walk the loop, one elected lane issues ================================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const DescLH dK_k = make_desc_lh(sK, 0, 1024), dV_k = make_desc_lh(sV, 0, 1024), dK_mn = make_desc_lh(sK, 16384, 1024),
+                 dDS_k0 = make_desc_lh(sDS, 0, 1024), dDS_k1 = make_desc_lh(sDS + TILE, 0, 1024), dDS_mn = make_desc_lh(sDS, 16384, 1024);
+    auto load_tile = [&](int t) {
+      const uint32_t st = t % NST, bar = bar_ld + 8 * st;
+      const int i0 = (qt0 + t) * BM;
+      if (elect_one()) {
         mbar_expect_tx(bar, LD_BYTES);
         tma_load_3d(&tmQ, bar, sQ + st * TILE, h * HD, i0, b);
         tma_load_3d(&tmDO, bar, sDO + st * TILE, h * HD, i0, b);
         bulk_load(sL + st * 512, p.lse2 + (int64_t)bh * p.Tq_pad + i0, 512, bar);
         bulk_load(sD + st * 512, p.dsum + (int64_t)bh * p.Tq_pad + i0, 512, bar);
-      };
-      auto issue_scores = [&](int t) {
-        const uint32_t st = t % NST;
+      }
+      __syncwarp();
+    };
+    auto issue_scores = [&](int t) {
+      const uint32_t st = t % NST;
+      const DescLH dQ_k = make_desc_lh(sQ + st * TILE, 0, 1024), dDO_k = make_desc_lh(sDO + st * TILE, 0, 1024);
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem + T_S, make_desc(sK + ks * 32, 0, 1024), make_desc(sQ + st * TILE + ks * 32, 0, 1024), ID_T, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_S, desc_at(dK_k, ks * 32), desc_at(dQ_k, ks * 32), ID_T, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem + T_DP, make_desc(sV + ks * 32, 0, 1024), make_desc(sDO + st * TILE + ks * 32, 0, 1024), ID_T, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_DP, desc_at(dV_k, ks * 32), desc_at(dDO_k, ks * 32), ID_T, ks > 0);
         umma_commit(bar_s);
-      };
+      }
+      __syncwarp();
+    };
+    if (elect_one()) {
       mbar_expect_tx(bar_kv, 2 * TILE);
       tma_load_3d(&tmK, bar_kv, sK, h * HD, j0, b);
       tma_load_3d(&tmV, bar_kv, sV, h * HD, j0, b);
-      load_tile(0);
-      if (n > 1) load_tile(1);
-      WAIT(bar_kv, 0);
-      WAIT(bar_ld, 0);
-      tc_fence_after();
-      issue_scores(0);
-      int ck = 0;
-#define CSTAMP() do { if (p.dbg_clk && blockIdx.x == 0 && blockIdx.y == 0 && (it == 3 || it == 4) && ck < 16) p.dbg_clk[ck++] = clock64(); } while (0)
-      for (int it = 0; it < n; ++it) {
-        const uint32_t st = it % NST;
-        CSTAMP();
-        if (it + 1 < n) {                       // the workers hold S^T / dP^T (it) in registers: the next pair may overwrite them
-          WAIT(bar_sfree, it & 1);
-          WAIT(bar_ld + 8 * ((it + 1) % NST), ((it + 1) / NST) & 1);
-          tc_fence_after();
-          CSTAMP();
-          issue_scores(it + 1);
-          CSTAMP();
-        }
-        WAIT(bar_p, it & 1);
-        CSTAMP();               // P^T (it) in tensor memory, dS^T (it) in shared memory, dQ (it - 1) read out
-        if (it >= 1 && it + 2 < n) WAIT(bar_acc, (it - 1) & 1);    // stage of tile it - 1 is free (waited before this tile's commit)
-        tc_fence_after();
-        const uint32_t acc = it > 0 ? 1u : 0u;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem + T_DV, tmem + T_P + ks * 8, make_desc(sDO + st * TILE + ks * 2048, 16384, 1024), ID_KM, (ks > 0) ? 1u : acc);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ss(tmem + T_DK, make_desc(sDS + (ks >> 2) * TILE + (ks & 3) * 32, 0, 1024), make_desc(sQ + st * TILE + ks * 2048, 16384, 1024),
-                  ID_KM, (ks > 0) ? 1u : acc);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ss(tmem + T_DQ, make_desc(sDS + ks * 2048, 16384, 1024), make_desc(sK + ks * 2048, 16384, 1024), ID_MM, ks > 0);
-        umma_commit(bar_acc);
-        CSTAMP();
-        if (it + 2 < n) load_tile(it + 2);
-        CSTAMP();
-      }
     }
     __syncwarp();
+    load_tile(0);
+    if (n > 1) load_tile(1);
+    mbar_wait(bar_kv, 0);
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    issue_scores(0);
+    for (int it = 0; it < n; ++it) {
+      const uint32_t st = it % NST;
+      if (it + 1 < n) {                         // the workers hold S^T / dP^T (it) in registers: the next pair may overwrite them
+        mbar_wait(bar_sfree, it & 1);
+        mbar_wait(bar_ld + 8 * ((it + 1) % NST), ((it + 1) / NST) & 1);
+        tc_fence_after();
+        issue_scores(it + 1);
+      }
+      mbar_wait(bar_p, it & 1);                 // P^T (it) in tensor memory, dS^T (it) in shared memory, dQ (it - 1) read out
+      if (it >= 1 && it + 2 < n) mbar_wait(bar_acc, (it - 1) & 1);    // stage of tile it - 1 is free (waited before this tile's commit)
+      tc_fence_after();
+      const uint32_t acc = it > 0 ? 1u : 0u;
+      const DescLH dDO_mn = make_desc_lh(sDO + st * TILE, 16384, 1024), dQ_mn = make_desc_lh(sQ + st * TILE, 16384, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_ts(tm + T_DV, tm + T_P + ks * 8, desc_at(dDO_mn, ks * 2048), ID_KM, (ks > 0) ? 1u : acc);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ss(tm + T_DK, desc_at((ks >> 2) ? dDS_k1 : dDS_k0, (ks & 3) * 32), desc_at(dQ_mn, ks * 2048), ID_KM, (ks > 0) ? 1u : acc);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_DQ, desc_at(dDS_mn, ks * 2048), desc_at(dK_mn, ks * 2048), ID_MM, ks > 0);
+        umma_commit(bar_acc);
+      }
+      __syncwarp();
+      if (it + 2 < n) load_tile(it + 2);
+    }
   } else {
-    // ================================ workers: thread = (key row r, column half ch) ================================
+    // ================================ workers: thread = (key row r, column quarter ch) ================================
     const int quad = warp & 3, ch = warp >> 2;
     const int r = quad * 32 + lane;
     const int j = j0 + r;
     const uint32_t tl = tmem + ((uint32_t)quad << 21);
-    // dQ tile (lanes = queries, 32 of the 64 head columns) -> fp32 workspace
+    const uint32_t sDQw = sDQ + warp * 2048;                 // this warp's [32 queries][16 head columns] fp32 staging tile (64B swizzle)
+    const uint32_t key = emo_drop_key(p.seed, 0);
+    const int drop_mode = p.drop_thr ? (p.drop_fast ? 1 : 2) : 0;
+    // dQ tile (lanes = queries, 16 of the 64 head columns) += into the fp32 workspace: TMEM -> smem -> TMA reduce
     auto dq_out = [&](int t) {
-      const int iq = (qt0 + t) * BM + r;
-      uint32_t d[32];
-      tmem_ld32_issue(tl + T_DQ + 32 * ch, d);
+      if (lane == 0) tma_store_wait_read<0>();               // the previous reduction has read the staging tile
+      __syncwarp();
+      uint32_t d[16];
+      tmem_ld16_issue(tl + T_DQ + 16 * ch, d);
       tmem_ld_wait();
-      if (iq < p.Tq && !(p.dbg_skip_dq & 1)) {
-        float* dst = p.dqacc + (((int64_t)b * p.Tq + iq) * p.H + h) * HD + 32 * ch;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          red_add_v4(dst + 4 * c, __uint_as_float(d[4 * c]), __uint_as_float(d[4 * c + 1]), __uint_as_float(d[4 * c + 2]), __uint_as_float(d[4 * c + 3]));
+      for (int cc = 0; cc < 4; ++cc) {
+        uint4 t4;
+        t4.x = d[4 * cc]; t4.y = d[4 * cc + 1]; t4.z = d[4 * cc + 2]; t4.w = d[4 * cc + 3];
+        sts128(sDQw + (uint32_t)(lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4)), t4);
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_reduce_add_3d(&tmDQ, sDQw, h * HD + 16 * ch, (qt0 + t) * BM + 32 * quad, b);
     };
     int wk = 0;
 #define WSTAMP() do { if (p.dbg_clk && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && (it == 3 || it == 4) && wk < 16) p.dbg_clk[16 + wk++] = clock64(); } while (0)
@@ -405,66 +453,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t st = it % NST;
       const int i0 = (qt0 + it) * BM;
       WSTAMP();
-      WAIT(bar_s, it & 1);
+      mbar_wait(bar_s, it & 1);
       WSTAMP();
       tc_fence_after();
-      WAIT(bar_ld + 8 * st, (it / NST) & 1);          // lse2 / dsum of this tile (TMA writes) are visible to this thread
-      uint32_t s[64], dp[64];
-      tmem_ld32_issue(tl + T_S + 64 * ch, s);
-      tmem_ld32_issue(tl + T_S + 64 * ch + 32, s + 32);
-      tmem_ld32_issue(tl + T_DP + 64 * ch, dp);
-      tmem_ld32_issue(tl + T_DP + 64 * ch + 32, dp + 32);
+      mbar_wait(bar_ld + 8 * st, (it / NST) & 1);          // lse2 / dsum of this tile (TMA writes) are visible to this thread
+      uint32_t s[32], dp[32];
+      tmem_ld32_issue(tl + T_S + 32 * ch, s);
+      tmem_ld32_issue(tl + T_DP + 32 * ch, dp);
       tmem_ld_wait();
       WSTAMP();
       tc_fence_before();
       mbar_arrive(bar_sfree);
-      const uint32_t aL = sL + st * 512 + ch * 256, aD = sD + st * 512 + ch * 256;
+      const uint32_t aL = sL + st * 512 + ch * 128, aD = sD + st * 512 + ch * 128;
       const bool diag = i0 + off < j0 + BN - 1;              // CTA-uniform: some (query, key) pair of the tile is masked
-      const int cmin = j - off - i0 - 64 * ch;               // column c (query i0 + 64 ch + c) sees key j iff c >= cmin
-      uint32_t pk[32], dsk[32];
-      if (p.dbg_skip_dq & 4) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { pk[c] = s[2 * c] & 0x3f803f80u; dsk[c] = dp[2 * c + 1] & 0x3f803f80u; }
-      } else
-#pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {                      // 4 query columns at a time
-        const uint4 l4 = lds128(aL + 16 * c4), d4 = lds128(aD + 16 * c4);
-        const float lv[4] = {__uint_as_float(l4.x), __uint_as_float(l4.y), __uint_as_float(l4.z), __uint_as_float(l4.w)};
-        const float dv_[4] = {__uint_as_float(d4.x), __uint_as_float(d4.y), __uint_as_float(d4.z), __uint_as_float(d4.w)};
-        float pd[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * c4 + e;
-          float pv = ex2(fmaf(__uint_as_float(s[c]), p.sl2, -lv[e]));
-          if (diag) pv = (c >= cmin) ? pv : 0.f;
-          float dpv = __uint_as_float(dp[c]);
-          float pdv = pv;
-          if (p.drop_thr) {
-            const uint64_t eidx = ((uint64_t)bh * p.Tq + (uint64_t)(i0 + 64 * ch + c)) * (uint64_t)p.Tk + (uint64_t)j;
-            const bool keep = emo_drop_keep(p.seed, eidx, p.drop_thr);
-            pdv = keep ? pv * p.keep_scale : 0.f;
-            dpv = keep ? dpv * p.keep_scale : 0.f;
-          }
-          pd[e] = pdv;
-          ds[e] = pv * (dpv - dv_[e]) * p.scale;
-        }
-        pk[2 * c4] = pack_bf16x2(pd[0], pd[1]); pk[2 * c4 + 1] = pack_bf16x2(pd[2], pd[3]);
-        dsk[2 * c4] = pack_bf16x2(ds[0], ds[1]); dsk[2 * c4 + 1] = pack_bf16x2(ds[2], ds[3]);
+      const int cmin = j - off - i0 - 32 * ch;               // column c (query i0 + 32 ch + c) sees key j iff c >= cmin
+      const uint64_t e_base = ((uint64_t)bh * p.Tq + (uint64_t)(i0 + 32 * ch)) * (uint64_t)p.Tk + (uint64_t)j;   // mask index of column 0
+      const uint32_t pbase = (uint32_t)(e_base >> 1);
+      uint32_t pk[16], dsk[16];
+      if (drop_mode == 0) {
+        if (diag) ew_pass<true, 0>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+        else ew_pass<false, 0>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+      } else if (drop_mode == 1) {
+        if (diag) ew_pass<true, 1>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+        else ew_pass<false, 1>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+      } else {
+        ew_pass<true, 2>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
       }
       WSTAMP();
       if (it > 0) {                                          // products of tile it - 1 are complete: P^T / dS^T / dQ may be reused
-        WAIT(bar_acc, (it - 1) & 1);
+        mbar_wait(bar_acc, (it - 1) & 1);
         WSTAMP();
         tc_fence_after();
-        if (!(p.dbg_skip_dq & 2)) dq_out(it - 1);
+        dq_out(it - 1);
       }
       WSTAMP();
-      tmem_st32(tl + T_P + 32 * ch, pk);
+      tmem_st16(tl + T_P + 16 * ch, pk);
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
+      for (int cc = 0; cc < 4; ++cc) {
         uint4 t;
         t.x = dsk[4 * cc]; t.y = dsk[4 * cc + 1]; t.z = dsk[4 * cc + 2]; t.w = dsk[4 * cc + 3];
-        sts128(sDS + ch * TILE + sw128(r, cc), t);
+        sts128(sDS + (ch >> 1) * TILE + sw128(r, (ch & 1) * 4 + cc), t);
       }
       tmem_st_wait();
       fence_proxy_async();
@@ -472,19 +500,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(bar_p);
       WSTAMP();
     }
-    WAIT(bar_acc, (n - 1) & 1);
+    mbar_wait(bar_acc, (n - 1) & 1);
     tc_fence_after();
     dq_out(n - 1);
     // ---- dK, dV rows of this key tile ----
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      uint32_t d[32];
-      tmem_ld32_issue(tl + (which ? T_DK : T_DV) + 32 * ch, d);
+      uint32_t d[16];
+      tmem_ld16_issue(tl + (which ? T_DK : T_DV) + 16 * ch, d);
       tmem_ld_wait();
       if (j < p.Tk) {
-        bf16* dst = (which ? p.dk : p.dv) + ((int64_t)b * p.Tk + j) * p.ld_dkv + (int64_t)h * HD + 32 * ch;
+        bf16* dst = (which ? p.dk : p.dv) + ((int64_t)b * p.Tk + j) * p.ld_dkv + (int64_t)h * HD + 16 * ch;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           uint4 t;
           t.x = pack_bf16x2(__uint_as_float(d[8 * cc]), __uint_as_float(d[8 * cc + 1]));
           t.y = pack_bf16x2(__uint_as_float(d[8 * cc + 2]), __uint_as_float(d[8 * cc + 3]));
@@ -494,19 +522,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();                     // the last reduction has left shared memory before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NW) {
     tc_fence_after();
     tmem_dealloc(tmem, T_COLS);
   }
 }
 
-// lse2 = lse * log2(e) (+inf on the padding rows: P = 0 there), dsum = rowsum(dO * O); one warp per 4 rows
+// lse2 = lse * log2(e) (+inf on the padding rows: P = 0 there), dsum = scale * rowsum(dO * O); 8 threads per row
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, int64_t ld_o,
                                      const float* __restrict__ lse, float* __restrict__ lse2, float* __restrict__ dsum,
-                                     int Tq, int Tq_pad, int H, int64_t rows_pad) {
+                                     int Tq, int Tq_pad, int H, int64_t rows_pad, float scale) {
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // 8 threads per row
   const int part = threadIdx.x & 7;
   if (gw >= rows_pad) return;
@@ -527,7 +556,7 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* _
   dot += __shfl_xor_sync(0xffffffffu, dot, 2);
   dot += __shfl_xor_sync(0xffffffffu, dot, 4);
   if (part == 0) {
-    dsum[gw] = dot;
+    dsum[gw] = dot * scale;
     lse2[gw] = (i < Tq) ? lse[bh * Tq + i] * LOG2E : INFINITY;
   }
 }
@@ -606,20 +635,21 @@ int emo_attn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t 
   int rc = EMO_OK;
   do {
     if (cudaMemsetAsync(dqacc, 0, (size_t)n_acc * sizeof(float), s) != cudaSuccess) { rc = EMO_ERR_CUDA; break; }
-    attn_bwd_prep_kernel<<<(unsigned)((n_vec * 8 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, ld_o, lse, lse2, dsum, Tq, Tq_pad, H, n_vec);
-    CUtensorMap mq, mk, mv, mdo;
+    attn_bwd_prep_kernel<<<(unsigned)((n_vec * 8 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, ld_o, lse, lse2, dsum, Tq, Tq_pad, H, n_vec, scale);
+    CUtensorMap mq, mk, mv, mdo, mdq;
     if ((rc = tcp::make_map_bt(&mq, q, (int64_t)H * HD, Tq, B, ld_q, BM))) break;
     if ((rc = tcp::make_map_bt(&mk, k, (int64_t)H * HD, Tk, B, ld_kv, BN))) break;
     if ((rc = tcp::make_map_bt(&mv, v, (int64_t)H * HD, Tk, B, ld_kv, BN))) break;
     if ((rc = tcp::make_map_bt(&mdo, dout, (int64_t)H * HD, Tq, B, ld_o, BM))) break;
+    if ((rc = tcp::make_map_f32_bt(&mdq, dqacc, (int64_t)H * HD, Tq, B, 32, 16))) break;
     Params p;
-    p.lse2 = lse2; p.dsum = dsum; p.dqacc = dqacc; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_dkv = ld_dkv;
+    p.lse2 = lse2; p.dsum = dsum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_dkv = ld_dkv;
     p.Tq = Tq; p.Tk = Tk; p.Tq_pad = Tq_pad; p.H = H; p.nqt = nqt; p.scale = scale; p.sl2 = scale * LOG2E;
     p.keep_scale = 1.f / (1.f - drop_p); p.drop_thr = emo_drop_thr(drop_p); p.seed = seed;
-    { const char* e = getenv("EMO_ATTN_DBG_SKIP_DQ"); p.dbg_skip_dq = e ? atoi(e) : 0; }
+    p.drop_fast = ((Tk & 1) == 0) && ((uint64_t)B * H * (uint64_t)Tq * (uint64_t)Tk < (1ull << 33));
     { const char* e = getenv("EMO_ATTN_DBG_CLK"); p.dbg_clk = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
     dim3 grid(nkt, B * H);
-    attn_bwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, mdo, p);
+    attn_bwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, mdo, mdq, p);
     const int64_t nconv = (int64_t)B * Tq * (H * HD / 8);
     attn_bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, s>>>(dqacc, (bf16*)dq, ld_dq, (int64_t)B * Tq, H * HD);
   } while (0);

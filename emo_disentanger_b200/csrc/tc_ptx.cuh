@@ -83,6 +83,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// global[tile] += shared[tile] (element type and add come from the tensor map: fp32); rows outside the tensor are clipped
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
@@ -105,6 +112,13 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -168,6 +182,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m = 128, bool a_bf16 = true, bool b_bf16 = true) {
   return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// ---- warp-uniform issue path ------------------------------------------------------------------------------------
+// The control warp runs its loop with ALL lanes (waits included) and only the instruction itself is given to one
+// elected lane.  MEASURED on B200: with the whole loop under `if (lane == 0)` every descriptor lives in vector
+// registers of a divergent region and each tcgen05.mma costs ~17 SASS instructions (R2UR moves plus an ELECT /
+// BRA.U.ANY loop), ~72 clocks per MMA -- more than an N = 64, K = 16 MMA takes on the tensor pipe (32 clocks).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: adding (bytes >> 4) to `lo` moves the start address (no carry out of the 14-bit field for any
+// shared-memory address)
+struct DescLH { uint32_t lo, hi; };
+__device__ __forceinline__ DescLH make_desc_lh(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  DescLH d;
+  d.lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+  d.hi = (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_at(const DescLH& d, uint32_t byte_off) {
+  return ((uint64_t)d.hi << 32) | (uint64_t)(d.lo + (byte_off >> 4));
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
@@ -250,6 +286,25 @@ static inline int make_map_bt(CUtensorMap* map, const void* ptr, int64_t inner, 
   if (r != CUDA_SUCCESS) {
     emo_set_error("cuTensorMapEncodeTiled (3d) failed: %d (inner=%lld T=%lld B=%lld ld=%lld)", (int)r, (long long)inner, (long long)T,
                   (long long)B, (long long)ld);
+    return EMO_ERR_CUDA;
+  }
+  return EMO_OK;
+}
+
+// fp32 [B][T][row of `inner` elements], dense rows: box = {32 floats = 128 B, box_rows, 1}, 128B swizzle (the dQ
+// accumulation target of the attention backward: cp.reduce.async.bulk.tensor adds tiles into it)
+static inline int make_map_f32_bt(CUtensorMap* map, const void* ptr, int64_t inner, int64_t T, int64_t B, int box_rows, int box_cols = 32) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { emo_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return EMO_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 4, (cuuint64_t)T * (cuuint64_t)inner * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};       // 32 floats: 128B swizzle; 16 floats: 64B swizzle
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    emo_set_error("cuTensorMapEncodeTiled (3d, fp32) failed: %d (inner=%lld T=%lld B=%lld)", (int)r, (long long)inner, (long long)T, (long long)B);
     return EMO_ERR_CUDA;
   }
   return EMO_OK;
