@@ -246,11 +246,15 @@ def _class_roofline(ops, ms_step, tokens_step, flops_token_attn=None):
     if flops_token_attn is not None and att_ms > gem[1]:
         fl = flops_token_attn * tokens_step
         ach = fl / (att_ms * 1e-3) / 1e12
-        roof = {"kernel": "attn_fwd / attn_bwd_dkv / attn_bwd_dq (flash-style causal softmax attention, mma.sync)",
+        rel = any("relattn" in k for k, v in summ.items() if v[0])
+        kname = ("attn_fwd / attn_bwd_dkv / attn_bwd_dq <REL> (flash-style relative-position attention, mma.sync)" if rel else
+                 "attn_fwd_tc_kernel / attn_bwd_tc_kernel (flash-style causal softmax attention, tcgen05 + TMA, attn_tc.cu)")
+        roof = {"kernel": kname,
                 "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "launches": att_n,
                 "work_per_launch": "causal attention: 4*64*(T+1)/2 MAC-pairs per (token, head) forward, x2.5 for the "
-                                   "backward (recomputed scores)", "peak_source": pk["source"] + ", sustained bf16"}
+                                   "backward (recomputed scores); the time includes the backward's prep / dQ-convert passes",
+                "peak_source": pk["source"] + ", sustained bf16"}
     else:
         ach = gem[2] / (gem[1] * 1e-3) / 1e12 if gem[1] else 0.0
         roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM)", "bound": "tensor", "achieved": round(ach, 2),

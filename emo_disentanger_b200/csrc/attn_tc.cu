@@ -89,41 +89,50 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t ID_S = make_idesc(128, false, false), ID_O = make_idesc(64, false, true);
 
   if (warp == 4) {
-    // ================================ control: TMA + MMA issue ================================
-    if (lane == 0) {
+    // ================================ control warp: all lanes walk the loop, one elected lane issues ================================
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const DescLH dQ = make_desc_lh(sQ, 0, 1024);
+    if (elect_one()) {
       mbar_expect_tx(bar_q, TILE);
       tma_load_3d(&tmQ, bar_q, sQ, h * HD, i0, b);
       mbar_expect_tx(bar_k, TILE);
       tma_load_3d(&tmK, bar_k, sK, h * HD, 0, b);
       mbar_expect_tx(bar_v, TILE);
       tma_load_3d(&tmV, bar_v, sV, h * HD, 0, b);
-      for (int it = 0; it < n; ++it) {
-        const uint32_t st = it & 1, par = (it >> 1) & 1;
-        if (it == 0) mbar_wait(bar_q, 0);
-        mbar_wait(bar_k + 8 * st, par);
-        tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(bar_q, 0);
+    for (int it = 0; it < n; ++it) {
+      const uint32_t st = it & 1, par = (it >> 1) & 1;
+      const DescLH dK = make_desc_lh(sK + st * TILE, 0, 1024), dV = make_desc_lh(sV + st * TILE, 16384, 1024);
+      mbar_wait(bar_k + 8 * st, par);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem + T_S, make_desc(sQ + ks * 32, 0, 1024), make_desc(sK + st * TILE + ks * 32, 0, 1024), ID_S, ks > 0);
+        for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_S, desc_at(dQ, ks * 32), desc_at(dK, ks * 32), ID_S, ks > 0);
         umma_commit(bar_s);
         if (it + 1 < n) {                       // S(it - 1), the last reader of that stage, was seen complete by the workers
           mbar_expect_tx(bar_k + 8 * (st ^ 1), TILE);
           tma_load_3d(&tmK, bar_k + 8 * (st ^ 1), sK + (st ^ 1) * TILE, h * HD, (it + 1) * BN, b);
         }
-        mbar_wait(bar_p, it & 1);               // P(it) is in tensor memory (and O rescaled if it had to be)
-        tc_fence_after();
-        if (it + 1 < n) {                       // P V(it - 1) completed before S(it) did
-          mbar_expect_tx(bar_v + 8 * (st ^ 1), TILE);
-          tma_load_3d(&tmV, bar_v + 8 * (st ^ 1), sV + (st ^ 1) * TILE, h * HD, (it + 1) * BN, b);
-        }
-        mbar_wait(bar_v + 8 * st, par);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, it & 1);                 // P(it) is in tensor memory (and O rescaled if it had to be)
+      if (it + 1 < n && elect_one()) {          // P V(it - 1) completed before S(it) did
+        mbar_expect_tx(bar_v + 8 * (st ^ 1), TILE);
+        tma_load_3d(&tmV, bar_v + 8 * (st ^ 1), sV + (st ^ 1) * TILE, h * HD, (it + 1) * BN, b);
+      }
+      __syncwarp();
+      mbar_wait(bar_v + 8 * st, par);
+      tc_fence_after();
+      const uint32_t acc = it > 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem + T_O, tmem + T_S + ks * 8, make_desc(sV + st * TILE + ks * 2048, 16384, 1024), ID_O, (it > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) umma_ts(tm + T_O, tm + T_S + ks * 8, desc_at(dV, ks * 2048), ID_O, (ks > 0) ? 1u : acc);
         umma_commit(bar_o);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ================================ softmax warps: thread = query row ================================
     const int i = i0 + tid;

@@ -276,9 +276,12 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   constexpr uint32_t ID_U = make_idesc(64, false, true), ID_KK128 = make_idesc(128, false, false), ID_ST = make_idesc(64, true, true),
                      ID_MN64 = make_idesc(64, false, true), ID_KK64 = make_idesc(64, false, false);
-  auto dK = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)(ks >> 2) * TILE + (uint32_t)(ks & 3) * 32, 0, 1024); };   // K-major over 128 features
-  auto d64 = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)ks * 32, 0, 1024); };                                  // K-major, K <= 64
-  auto dMN = [](uint32_t tile, int ks) { return make_desc(tile + (uint32_t)ks * 2048, TILE, 1024); };                             // MN-major, K = rows
+  // Operand descriptors as (lo, hi) halves built from warp-uniform values OUTSIDE the elected-lane regions (they stay in
+  // uniform registers; inside, a descriptor is one add of a constant): tc_ptx.cuh, elect_one.
+  auto dK = [](uint32_t tile, int ks) { return desc_at(make_desc_lh(tile, 0, 1024), (uint32_t)(ks >> 2) * TILE + (uint32_t)(ks & 3) * 32); };   // K-major over 128 features
+  auto d64 = [](uint32_t tile, int ks) { return desc_at(make_desc_lh(tile, 0, 1024), (uint32_t)ks * 32); };                                  // K-major, K <= 64
+  auto dMN = [](uint32_t tile, int ks) { return desc_at(make_desc_lh(tile, TILE, 1024), (uint32_t)ks * 2048); };                             // MN-major, K = rows
+  const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);      // the control warp's copy of the TMEM base, warp-uniform
 
   uint32_t cph = 0;            // parity of this chunk's once-per-chunk barriers
   uint32_t nchunks_done = 0;   // chunks processed by this CTA so far (V double buffer / rz double buffer index)
@@ -293,7 +296,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int64_t tokbase = (int64_t)b * p.T;
 
     if (ctrl) {
-      if (lane == 0) {
+      if (elect_one()) {
         const int t0 = (c_end - 1) * C;
         mbar_expect_tx(bar(B_XQK), 2 * TILE);
         tma_load_3d(&tmQ, bar(B_XQK), sXQ, h * FE, t0, b);
@@ -305,6 +308,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_expect_tx(bar(B_V0 + vb), TILE);
         tma_load_3d(&tmV, bar(B_V0 + vb), sXV0 + vb * TILE, h * FE, t0, b);
       }
+      __syncwarp();
     } else {
       // ---- states of this segment: group 0 loads R, rz (reverse state of the later segments), group 1 loads -S, z
       //      (the forward's prefix state at the end of the segment): fp32 -> TMEM, R also bf16 -> smem ----
@@ -345,67 +349,69 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float* rz_nxt = rzb + (vb ^ 1) * 128;
       if (ctrl) {
         // =============================== control warp ===============================
-        if (lane == 0) {
-          mbar_wait(bar(B_XQK), cph);
-          tc_fence_after();
+        // all 32 lanes walk the protocol (waits, fences); one elected lane issues MMAs / TMA
+        mbar_wait(bar(B_XQK), cph);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W1, d64(sXQ, ks), dMN(sOM, ks), ID_U, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_W1, d64(sXQ, ks), dMN(sOM, ks), ID_U, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W1 + 64, d64(sXK, ks), dMN(sOM, ks), ID_U, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_W1 + 64, d64(sXK, ks), dMN(sOM, ks), ID_U, ks > 0);
           umma_commit(bar(M_U));
           if (c > c_begin) {                       // prefetch the previous chunk (reverse order)
-            const int tn = t0 - C;
             mbar_expect_tx(bar(B_V0 + (vb ^ 1)), TILE);
-            tma_load_3d(&tmV, bar(B_V0 + (vb ^ 1)), sXV0 + (vb ^ 1) * TILE, h * FE, tn, b);
-            mbar_wait(bar(F_X), cph);
-            mbar_expect_tx(bar(B_XQK), 2 * TILE);
-            tma_load_3d(&tmQ, bar(B_XQK), sXQ, h * FE, tn, b);
-            tma_load_3d(&tmK, bar(B_XQK), sXK, h * FE, tn, b);
-            mbar_wait(bar(F_OD), cph);
-            mbar_expect_tx(bar(B_OD), 2 * TILE);
-            tma_load_3d(&tmO, bar(B_OD), sXO, h * FE, tn, b);
-            tma_load_3d(&tmD, bar(B_OD), sXD, h * FE, tn, b);
-          } else {
-            mbar_wait(bar(F_X), cph);
-            mbar_wait(bar(F_OD), cph);
+            tma_load_3d(&tmV, bar(B_V0 + (vb ^ 1)), sXV0 + (vb ^ 1) * TILE, h * FE, t0 - C, b);
           }
         }
         __syncwarp();
+        mbar_wait(bar(F_X), cph);
+        if (c > c_begin && elect_one()) {
+          mbar_expect_tx(bar(B_XQK), 2 * TILE);
+          tma_load_3d(&tmQ, bar(B_XQK), sXQ, h * FE, t0 - C, b);
+          tma_load_3d(&tmK, bar(B_XQK), sXK, h * FE, t0 - C, b);
+        }
+        __syncwarp();
+        mbar_wait(bar(F_OD), cph);
+        if (c > c_begin && elect_one()) {
+          mbar_expect_tx(bar(B_OD), 2 * TILE);
+          tma_load_3d(&tmO, bar(B_OD), sXO, h * FE, t0 - C, b);
+          tma_load_3d(&tmD, bar(B_OD), sXD, h * FE, t0 - C, b);
+        }
+        __syncwarp();
         named_bar_sync<1>(NT);                     // [A] phi(q), phi(k), G in smem; gd; z rolled back
-        if (lane == 0) {
-          tc_fence_after();
-          mbar_wait(bar(B_V0 + vb), (nchunks_done >> 1) & 1);
-          tc_fence_after();
+        mbar_wait(bar(B_V0 + vb), (nchunks_done >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_W0, dK(sPK, ks), dK(sPQ, ks), ID_KK128, ks > 0);    // phi(k) phi(q)^T
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_W0, dK(sPK, ks), dK(sPQ, ks), ID_KK128, ks > 0);    // phi(k) phi(q)^T
           umma_commit(bar(M_C1));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W1, d64(sG, ks), d64(sXV, ks), ID_KK128, ks > 0);   // G V^T
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_W1, d64(sG, ks), d64(sXV, ks), ID_KK128, ks > 0);   // G V^T
           umma_commit(bar(M_C2));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss(tmem + T_W2, d64(sXV, ks), d64(sG, ks), ID_KK128, ks > 0);   // V G^T
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_W2, d64(sXV, ks), d64(sG, ks), ID_KK128, ks > 0);   // V G^T
           umma_commit(bar(M_C3));
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_NS, dMN(sPK, ks), dMN(sXV, ks), ID_ST, 1u);        // -S += phi(k)^T V
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_NS, dMN(sPK, ks), dMN(sXV, ks), ID_ST, 1u);        // -S += phi(k)^T V
           umma_commit(bar(M_NS));
         }
         __syncwarp();
         named_bar_sync<1>(NT);                     // [B] P^T, dP, dP^T packed in TMEM; S_prev bf16 in smem
-        if (lane == 0) {
-          tc_fence_after();
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {         // d phi(q): features 64 hf .. -> hole of W1 / W0
             const uint32_t d = tmem + (hf == 0 ? T_W1 : T_W0) + 64;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tmem + T_W1 + ks * 8, dMN(sPK + hf * TILE, ks), ID_MN64, ks > 0);
+            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tm + T_W1 + ks * 8, dMN(sPK + hf * TILE, ks), ID_MN64, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_ss(d, d64(sG, ks), d64(sSB + hf * 8192, ks), ID_KK64, 1u);
           }
           umma_commit(bar(M_E1));
           {                                        // dv = P^T G + phi(k) R -> hole of W2
-            const uint32_t d = tmem + T_W2 + 64;
+            const uint32_t d = tm + T_W2 + 64;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tmem + T_W0 + ks * 8, dMN(sG, ks), ID_MN64, ks > 0);
+            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tm + T_W0 + ks * 8, dMN(sG, ks), ID_MN64, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) umma_ss(d, dK(sPK, ks), dMN(sRB, ks), ID_MN64, 1u);
           }
@@ -413,30 +419,30 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
         named_bar_sync<1>(NT);                     // [C] d phi(q) and dv consumed; dU_q packed in TMEM (W1 low)
-        if (lane == 0) {
-          tc_fence_after();
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W2 + 64, tmem + T_W1 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_q Om'^T
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tm + T_W2 + 64, tm + T_W1 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_q Om'^T
           umma_commit(bar(M_DXQ));
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {         // d phi(k)
             const uint32_t d = tmem + (hf == 0 ? T_W1 : T_W0) + 64;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tmem + T_W2 + ks * 8, dMN(sPQ + hf * TILE, ks), ID_MN64, ks > 0);
+            for (int ks = 0; ks < 8; ++ks) umma_ts(d, tm + T_W2 + ks * 8, dMN(sPQ + hf * TILE, ks), ID_MN64, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_ss(d, d64(sXV, ks), d64(sRB + hf * 8192, ks), ID_KK64, 1u);
           }
           umma_commit(bar(M_G));
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + T_R, dMN(sPQ, ks), dMN(sG, ks), ID_ST, 1u);          // R += phi(q)^T G
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_R, dMN(sPQ, ks), dMN(sG, ks), ID_ST, 1u);          // R += phi(q)^T G
           umma_commit(bar(M_R));
         }
         __syncwarp();
         named_bar_sync<1>(NT);                     // [D] dx_q, d phi(k) consumed; dU_k packed in TMEM (W2 low); R bf16 in smem
-        if (lane == 0) {
-          tc_fence_after();
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ts(tmem + T_W0 + 64, tmem + T_W2 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_k Om'^T
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tm + T_W0 + 64, tm + T_W2 + ks * 8, d64(sOM, ks), ID_KK64, ks > 0);   // dU_k Om'^T
           umma_commit(bar(M_DXK));
         }
         __syncwarp();

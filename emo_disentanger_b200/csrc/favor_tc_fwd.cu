@@ -78,6 +78,11 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t ID_S = make_idesc(128, false, false),
                      ID_O = make_idesc(64, false, true), ID_ST = make_idesc(64, true, true);
   uint32_t ph_qk = 0, ph_v = 0, ph_mma = 0, ph_xf = 0;   // parities of the next completion each role waits for
+  // control warp: the tensor-memory base as a warp-uniform value, operand descriptors built once
+  const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+  const DescLH dXQ = make_desc_lh(sXQ, 0, 1024), dXK = make_desc_lh(sXK, 0, 1024), dOM = make_desc_lh(sOM, 8192, 1024),
+               dPK0 = make_desc_lh(sPK, 0, 1024), dPK1 = make_desc_lh(sPK + 16384, 0, 1024), dSBmn = make_desc_lh(sSB, 16384, 1024),
+               dXVmn = make_desc_lh(sXV, 16384, 1024), dPKmn = make_desc_lh(sPK, 16384, 1024);
 
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int bh = item / p.nseg, seg = item % p.nseg;
@@ -86,13 +91,14 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int t_end = (t_begin + p.seg_chunks * C < p.T) ? t_begin + p.seg_chunks * C : p.T;
 
     if (warp == 4) {
-      if (lane == 0 && t_begin < t_end) {
+      if (t_begin < t_end && elect_one()) {
         mbar_expect_tx(bar_qk, 2 * C * FE * 2);
         tma_load_3d(&tmQ, bar_qk, sXQ, h * FE, t_begin, b);
         tma_load_3d(&tmK, bar_qk, sXK, h * FE, t_begin, b);
         mbar_expect_tx(bar_v, C * FE * 2);
         tma_load_3d(&tmV, bar_v, sXV, h * FE, t_begin, b);
       }
+      __syncwarp();
     } else {
       // ---- prefix state of this item: fp32 -> TMEM, bf16 -> smem, z ----
       const float* sin = nullptr;
@@ -130,55 +136,54 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int valid = (p.T - t0 < C) ? (p.T - t0) : C;
       if (warp == 4) {
         // ============================ control warp: TMA + MMA issue ============================
-        if (lane == 0) {
-          mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
-          tc_fence_after();
+        // all 32 lanes walk the protocol (waits, phase bits, descriptors: warp-uniform, so they live in uniform
+        // registers); one elected lane issues -- see tc_ptx.cuh, elect_one
+        mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + T_PQ, make_desc(sXQ + ks * 32, 0, 1024), make_desc(sOM + ks * 2048, 8192, 1024), ID_U, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_PQ, desc_at(dXQ, ks * 32), desc_at(dOM, ks * 2048), ID_U, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + T_SC, make_desc(sXK + ks * 32, 0, 1024), make_desc(sOM + ks * 2048, 8192, 1024), ID_U, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_SC, desc_at(dXK, ks * 32), desc_at(dOM, ks * 2048), ID_U, ks > 0);
           umma_commit(bar_mma);
-          // the next chunk's q, k once every worker has read its x rows (the row norms) and batch 1 is done with them
-          mbar_wait(bar_xf, ph_xf); ph_xf ^= 1;
-          if (t0 + C < t_end) {
-            mbar_expect_tx(bar_qk, 2 * C * FE * 2);
-            tma_load_3d(&tmQ, bar_qk, sXQ, h * FE, t0 + C, b);
-            tma_load_3d(&tmK, bar_qk, sXK, h * FE, t0 + C, b);
-          }
+        }
+        __syncwarp();
+        // the next chunk's q, k once every worker has read its x rows (the row norms) and batch 1 is done with them
+        mbar_wait(bar_xf, ph_xf); ph_xf ^= 1;
+        if (t0 + C < t_end && elect_one()) {
+          mbar_expect_tx(bar_qk, 2 * C * FE * 2);
+          tma_load_3d(&tmQ, bar_qk, sXQ, h * FE, t0 + C, b);
+          tma_load_3d(&tmK, bar_qk, sXK, h * FE, t0 + C, b);
         }
         ph_mma ^= 1;                           // batch 1 (the workers wait for it; this warp only keeps count)
         __syncwarp();
         named_bar_sync<1>(NT);                 // [B1] phi(k) in smem, phi(q) in TMEM
-        if (lane == 0) {
-          tc_fence_after();
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_ts(tmem + T_SC, tmem + T_PQ + ks * 8, make_desc(sPK + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024), ID_S, ks > 0);
+            umma_ts(tm + T_SC, tm + T_PQ + ks * 8, desc_at((ks >> 2) ? dPK1 : dPK0, (ks & 3) * 32), ID_S, ks > 0);
           umma_commit(bar_mma);
         }
         ph_mma ^= 1;                           // batch 2
         __syncwarp();
         named_bar_sync<1>(NT);                 // [B2] P in TMEM (and, from the previous chunk, S'_bf16 in smem)
-        if (lane == 0) {
-          mbar_wait(bar_v, ph_v); ph_v ^= 1;
-          tc_fence_after();
+        mbar_wait(bar_v, ph_v); ph_v ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ts(tmem + T_O, tmem + T_PQ + ks * 8, make_desc(sSB + ks * 2048, 16384, 1024), ID_O, ks > 0);
+          for (int ks = 0; ks < 8; ++ks) umma_ts(tm + T_O, tm + T_PQ + ks * 8, desc_at(dSBmn, ks * 2048), ID_O, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ts(tmem + T_O, tmem + T_SC + ks * 8, make_desc(sXV + ks * 2048, 16384, 1024), ID_O, 1u);
+          for (int ks = 0; ks < 8; ++ks) umma_ts(tm + T_O, tm + T_SC + ks * 8, desc_at(dXVmn, ks * 2048), ID_O, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ss(tmem + T_ST, make_desc(sPK + ks * 2048, 16384, 1024), make_desc(sXV + ks * 2048, 16384, 1024), ID_ST, 1u);
+          for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_ST, desc_at(dPKmn, ks * 2048), desc_at(dXVmn, ks * 2048), ID_ST, 1u);
           umma_commit(bar_mma);
-          mbar_wait(bar_mma, ph_mma);          // batch 3 done: v, phi(k) and the TMEM operands are free
-          if (t0 + C < t_end) {
-            mbar_expect_tx(bar_v, C * FE * 2);
-            tma_load_3d(&tmV, bar_v, sXV, h * FE, t0 + C, b);
-          }
+        }
+        __syncwarp();
+        mbar_wait(bar_mma, ph_mma);            // batch 3 done: v, phi(k) and the TMEM operands are free
+        if (t0 + C < t_end && elect_one()) {
+          mbar_expect_tx(bar_v, C * FE * 2);
+          tma_load_3d(&tmV, bar_v, sXV, h * FE, t0 + C, b);
         }
         ph_mma ^= 1;
         __syncwarp();
