@@ -4,7 +4,7 @@
 # profiles/ by scripts/ncu_traffic.py / scripts/ncu_summary.py.  Numbers printed under ncu are never bench values.
 set -u
 TAG=${1:-r01}
-PARTS=${PARTS:-launches gemm favor}       # which passes to run
+PARTS=${PARTS:-launches gemm favor attn}       # which passes to run
 mkdir -p gpurun_out
 if [[ " $PARTS " == *" launches "* ]]; then
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
@@ -33,8 +33,13 @@ rm -f gpurun_out/${TAG}_gemm_all.ncu-rep
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 1 -s 2 -o gpurun_out/${TAG}_gemm_ffn1 python scripts/gemm_shapes.py > /dev/null 2>&1
 fi
 if [[ " $PARTS " == *" favor "* ]]; then
-B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd2?_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
-B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd2?_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_fwd_tc_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_fwd python scripts/favor_perf.py > /dev/null 2>&1
+B=74 timeout 600 ncu --set full --clock-control none --import-source on -k regex:favor_bwd_tc_kernel -c 1 -s 3 -o gpurun_out/${TAG}_favor_bwd python scripts/favor_perf.py > /dev/null 2>&1
+fi
+if [[ " $PARTS " == *" attn "* ]]; then
+# GPT-2 causal attention (tcgen05 + TMA) at B=16 T=2048: the p = 0.1 launches (the training configuration)
+AB=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_tc_kernel -c 1 -s 16 -o gpurun_out/${TAG}_attn_fwd python scripts/attn_perf.py > /dev/null 2>&1
+AB=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_tc_kernel -c 1 -s 16 -o gpurun_out/${TAG}_attn_bwd python scripts/attn_perf.py > /dev/null 2>&1
 fi
 rm -f gpurun_out/${TAG}_launches_all.csv
 du -sh gpurun_out
