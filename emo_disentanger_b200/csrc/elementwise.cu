@@ -696,7 +696,11 @@ extern "C" int emo_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* tg
 // ---------------------------------------------------------------------------------------------
 // K12 grad-norm + Adam on flat buffers
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+// Deterministic: block partials are written to a workspace and the LAST block to finish adds them up in block order,
+// so every data-parallel replica gets bit-identical clip factors from bit-identical (all-reduced) gradients.  (A float
+// atomicAdd per block gave last-bit differences between ranks: the replicas drifted apart by ulps per step.)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out,
+                                                    float* __restrict__ partial, unsigned int* __restrict__ ticket) {
   float acc = 0.f;
   int64_t n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -708,20 +712,49 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     for (int64_t i = n4 << 2; i < n; ++i) acc += g[i] * g[i];
   acc = warp_sum(acc);
   __shared__ float s[8];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += s[i];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) t += __ldcg(partial + i);      // fixed assignment, fixed order
+    t = warp_sum(t);
+    if (threadIdx.x == 0) { *out += t; *ticket = 0u; }
+  }
+}
+static int sumsq_workspace(float** partial, unsigned int** ticket, int blocks) {
+  constexpr int MAX_DEV = 64, MAX_BLOCKS = 4096;
+  static float* ws[MAX_DEV] = {nullptr};
+  int dev = 0;
+  EMO_CHECK_CUDA(cudaGetDevice(&dev));
+  EMO_REQUIRE(dev < MAX_DEV && blocks <= MAX_BLOCKS, "emo_sumsq: device index / grid out of range");
+  if (!ws[dev]) {
+    EMO_CHECK_CUDA(cudaMalloc(&ws[dev], (MAX_BLOCKS + 1) * sizeof(float)));
+    EMO_CHECK_CUDA(cudaMemset(ws[dev], 0, (MAX_BLOCKS + 1) * sizeof(float)));
+  }
+  *partial = ws[dev];
+  *ticket = reinterpret_cast<unsigned int*>(ws[dev] + MAX_BLOCKS);
+  return EMO_OK;
 }
 extern "C" int emo_sumsq(const float* g, int64_t n, float* out, void* stream) {
   if (n == 0) return EMO_OK;
   EMO_REQUIRE(((uintptr_t)g & 15) == 0, "emo_sumsq: buffer must be 16-byte aligned");
   int64_t want = (n / 4 + 255) / 256;
   int blocks = (int)(want < (int64_t)emo_num_sms() * 8 ? (want > 0 ? want : 1) : (int64_t)emo_num_sms() * 8);
-  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  float* partial;
+  unsigned int* ticket;
+  int rc = sumsq_workspace(&partial, &ticket, blocks);      // one workspace per device: calls on one device must be stream-ordered
+  if (rc) return rc;
+  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out, partial, ticket);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -121,6 +121,24 @@ class FlatModule(nn.Module):
             self._flat_grad.zero_()
         self._attach_grads()
 
+    def grad_range(self, prefix):
+        """[lo, hi) of the flat gradient buffer that holds every parameter whose name starts with `prefix`
+        (registration keeps a layer's parameters contiguous): the unit of the bucketed gradient all-reduce"""
+        sel = [(off, off + n) for name, shape, off, n, _ in self._specs if name.startswith(prefix)]
+        if not sel:
+            raise KeyError(prefix)
+        lo, hi = min(a for a, _ in sel), max(b for _, b in sel)
+        inside = sum(1 for name, shape, off, n, _ in self._specs if lo <= off < hi)
+        if inside != len(sel):
+            raise RuntimeError("parameters of %r are not contiguous in the flat buffer" % prefix)
+        return lo, hi
+
+    def _layer_done(self, l):
+        """called by the backward of each model after the last kernel that writes layer l's gradients was launched"""
+        hook = self.__dict__.get("grad_hook")
+        if hook is not None:
+            hook(l)
+
     def grad_view(self, p_name):
         for name, shape, off, n, _ in self._specs:
             if name == p_name:

@@ -141,6 +141,7 @@ def main(argv=None):
         for batch in common.rank_strided(dloader, rank, world):
             x, tgt, seg = (batch[k].cuda(gpuid, non_blocking=True) for k in ('dec_input', 'dec_target', 'track_mask'))
             steps += 1
+            sync.begin_step(last_micro_batch=(steps % accum == 0))    # per-layer gradient buckets leave from the last backward only
             acc = model.train_step(x, seg, tgt, gscale=1.0 / accum, count_allreduce=sync.count_allreduce)
             if steps % accum == 0:
                 opt.step()                               # all-reduce -> clip(0.5) -> Adam -> zero grads

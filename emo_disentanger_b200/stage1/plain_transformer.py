@@ -115,6 +115,9 @@ class PlainTransformer(FlatModule):
         return dec_mems if len(dec_mems) > 0 else None
 
     # ---- reference-facing API ----------------------------------------------------------------
+    def layer_grad_range(self, l):
+        return self.grad_range("decoder.layers.%d." % l)
+
     def forward(self, dec_input, dec_mems, dec_seg_len=None, return_avg_attn=False):
         if return_avg_attn:
             raise NotImplementedError("return_avg_attn materialises the T x T attention matrix; not on the hot path")
@@ -325,6 +328,7 @@ class PlainTransformer(FlatModule):
             ops.ln_bwd(da, h, m1, r1, self._wv(Wf, nm + "dec_attn.layer_norm.weight"), dx, self._gv(nm + "dec_attn.layer_norm.weight"),
                        self._gv(nm + "dec_attn.layer_norm.bias"), add_in=dh1)
             dh = dx
+            self._layer_done(l)
         if p > 0:
             ops.dropout_apply(dh, dh, p, site_seed(seed, 1))
         ops.embed_bwd(saved["tokens"], None, dh, self._gv("word_emb.emb_lookup.weight"), None, d ** 0.5, p,

@@ -144,4 +144,8 @@ class MusicGPT2(Stage2Base):
             ops.ln_bwd(da, h_in, m1, r1, self._wv(Wf, nm + "ln_1.weight"), dx, self._gv(nm + "ln_1.weight"),
                        self._gv(nm + "ln_1.bias"), add_in=dh)
             dout = dx
+            self._layer_done(l)
         return dout
+
+    def layer_grad_range(self, l):
+        return self.grad_range("transformer_decoder.%d." % l)

@@ -181,4 +181,8 @@ class MusicPerformer(Stage2Base):
             dx = new(R, d)
             ops.linear_dgrad(dqkv, self._qkv_w(Wc, l), dx, residual=ds1, ld_res=d)
             dout = dx
+            self._layer_done(l)
         return dout
+
+    def layer_grad_range(self, l):
+        return self.grad_range(self._layer_names(l))

@@ -86,6 +86,22 @@ def _worker_body(rank, world, port, q):
     # single-process result over the WHOLE batch
     g_ref, lsum_ref = grads(tok, seg, tgt, (tgt != V - 1).sum().float())
     err = float((model._flat_grad - g_ref).abs().max() / g_ref.abs().max())
+    # bucketed path: "layers" reduced early from the backward's call-backs (reverse order, async), the rest at the end
+    reduced = model._flat_grad.clone()
+    cuts = [n // 7, n // 3, n // 2, (3 * n) // 4]           # three layer buckets in the middle; head and tail are "the rest"
+    model.layer_grad_range = lambda l: (cuts[l], cuts[l + 1])
+    model._flat_grad.copy_(g)
+    sync.begin_step(last_micro_batch=False)                   # accumulating micro-batch: the call-backs must not reduce
+    for l in (2, 1, 0):
+        model.grad_hook(l)
+    assert torch.equal(model._flat_grad, g) and not sync._work
+    sync.begin_step(last_micro_batch=True)
+    for l in (2, 1, 0):
+        model.grad_hook(l)
+    assert len(sync._work) == 3
+    sync.allreduce_grads()
+    assert not sync._work and not sync._ranges
+    err = max(err, float((model._flat_grad - reduced).abs().max()))     # same sums, bucket by bucket
     q.put((rank, err, abs(float(acc[1]) - lsum_ref) / lsum_ref))
     dist.destroy_process_group()
 
