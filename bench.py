@@ -293,6 +293,29 @@ def bench_gpt2_train(cpu=True, B=16, steps=6, warmup=3):
            "config": {"workload": "stage2 GPT-2 train step: 12 HF-GPT2 blocks d512 8h ff2048 gelu_new, REMI repr V=%d, seq=%d, "
                                   "batch %d, dropout 0.1 (incl. attention-prob dropout), clip 0.5 + Adam" % (V, T, B)},
            "steps": steps, "warmup": warmup, "roofline": roof, "kernel_time_shares": shares}
+    # GPT-2 autoregressive decode through the same engine as the Performer: K|V cache, the ragged batch in one
+    # static-shaped launch sequence (csrc/attn_decode.cu), model step + sampler in one CUDA graph
+    import numpy as np
+    from emo_disentanger_b200.decode import Stage2Decoder
+    m.eval()
+    dd = {"api": "Stage2Decoder.step_sample (K|V cache, ragged-batch attention step, step + sampler in one CUDA graph)",
+          "temperature": 1.2, "top_p": 0.9, "prompt_tokens": 64, "generated_tokens_per_sequence": 256}
+    for Bd in (1, 4):
+        dec = Stage2Decoder(m, batch=Bd, max_len=2048)
+        rng = np.random.RandomState(Bd)
+        for b in range(Bd):
+            dec.append(b, rng.randint(0, V - 1, size=64).tolist(), [0] * 64)
+        toks = [5] * Bd
+        for n in (16, 256):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                toks, _st = dec.step_sample(toks, [1] * Bd, rng.random_sample(Bd), 1.2, 0.9)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        dd["batch%d" % Bd] = {"value": Bd * 256 / dt, "unit": "tokens/s", "us_per_step": 1e6 * dt / 256}
+        del dec
+    out["decode"] = dd
     del m, opt
     torch.cuda.empty_cache()
     if cpu:

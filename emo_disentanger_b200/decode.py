@@ -46,12 +46,13 @@ class Stage2Decoder:
             self.state = torch.zeros(L, batch, H, 128, 80, dtype=torch.float32, device=dev)
         else:
             self.kv = torch.zeros(L, batch, max_len, 2 * d, dtype=self.dt, device=dev)
+            self.pos_tok = torch.zeros(batch, dtype=torch.int64, device=dev)   # position of the token a step is processing
             # HF Conv1D stores weights [in, out]; decode keeps [out, in] copies (weights are frozen while
             # generating) so that the one-row-per-sequence step runs the weight-streaming NT kernel
             self.wT = {}
         # static step buffers (graph inputs / outputs)
         self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=dev)
-        self.use_graph = bool(use_graph) and self.is_performer
+        self.use_graph = bool(use_graph)
         self.use_pdl = bool(use_pdl)      # step kernels overlap their prologue with the predecessor's tail (graph only)
         # the whole step as ONE kernel, a 16-CTA cluster per sequence (bf16 Performer; csrc/decode_step.cu).  Opt-in:
         # bit-identical to the kernel chain, sequences scale almost for free (one cluster each), but at batch 1-4 it
@@ -248,6 +249,48 @@ class Stage2Decoder:
         if not m.use_pe:
             self.pos.add_(1)
 
+    def _gpt2_step_body(self):
+        """one new token for EVERY sequence of the ragged batch in static-shaped launches (graph-capturable): the
+        projections see B rows, the attention reads each sequence's own cache length from the device"""
+        m = self.m
+        B, d, f, H = self.B, m.d_model, m.d_ff, m.n_head
+        Wf = m._flat
+        new = lambda *shape, dtype=self.dt: torch.empty(*shape, dtype=dtype, device=self.dev)
+        self.pos_tok.copy_(self.pos)
+        h = new(B, d)
+        ops.embed_rows(self.tok_in, self.seg_in if m.use_segment_emb else None, self.pos if m.use_pe else None,
+                       m._wv(Wf, "token_emb.emb_lookup.weight"),
+                       m._wv(Wf, "segemb.emb_lookup.weight") if m.use_segment_emb else None,
+                       m.pe.pe if m.use_pe else None, h, d ** 0.5, advance_pos=self.pos if m.use_pe else None)
+        if not m.use_pe:
+            self.pos.add_(1)
+        scale = 1.0 / (E ** 0.5)
+        for l in range(m.n_layer):
+            nm = "transformer_decoder.%d." % l
+            a = new(B, d)
+            ops.ln_fwd(h, m._wv(Wf, nm + "ln_1.weight"), m._wv(Wf, nm + "ln_1.bias"), a)
+            qkv = new(B, 3 * d)
+            ops.linear_fwd(a, self.wT[nm + "attn.c_attn.weight"], qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"))
+            att = new(B, d)
+            ops.attn_decode_step(qkv, self.kv[l], self.pos_tok, att, scale)
+            hx = new(B, d)
+            ops.linear_fwd(att, self.wT[nm + "attn.c_proj.weight"], hx, bias=m._wv(Wf, nm + "attn.c_proj.bias"),
+                           residual=h, ld_res=d)
+            c = new(B, d)
+            ops.ln_fwd(hx, m._wv(Wf, nm + "ln_2.weight"), m._wv(Wf, nm + "ln_2.bias"), c)
+            g = new(B, f)
+            ops.linear_fwd(c, self.wT[nm + "mlp.c_fc.weight"], g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"), act=ops.ACT_GELU_NEW)
+            h = new(B, d)
+            ops.linear_fwd(g, self.wT[nm + "mlp.c_proj.weight"], h, bias=m._wv(Wf, nm + "mlp.c_proj.bias"),
+                           residual=hx, ld_res=d)
+        self._logits_into(h, self.logits, None)
+
+    def _step_body(self):
+        if self.is_performer:
+            self._performer_step_body()
+        else:
+            self._gpt2_step_body()
+
     @torch.no_grad()
     def step(self, tokens, segs):
         """tokens / segs: python lists of length B (one new token per sequence). Returns logits [B, V] (fp32,
@@ -256,19 +299,15 @@ class Stage2Decoder:
         m = self.m
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
-        if self.is_performer:
-            self._stage_inputs(tokens, segs, None)
-            if self.use_graph:
-                if self.graph is None:
-                    self._capture()
-                self.graph.replay()
-            else:
-                self._performer_step_body()
-            for b in range(self.B):
-                self.pos_host[b] += 1
+        self._stage_inputs(tokens, segs, None)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
         else:
-            for b in range(self.B):
-                self.append(b, [tokens[b]], [segs[b]])
+            self._step_body()
+        for b in range(self.B):
+            self.pos_host[b] += 1
         return self.logits[:, :m.n_token]
 
     def _stage_inputs(self, tokens, segs, us):
@@ -295,8 +334,8 @@ class Stage2Decoder:
         """step() fused with the device sampler in ONE CUDA graph: tokens / segs / uniforms in by one H2D copy, the
         sampled ids (and the sampler's status words) back by one D2H copy.  Returns (ids, status) python lists;
         self.logits still holds the step's logits (a rejected draw is re-drawn from them by DeviceSampler)."""
-        if not (self.is_performer and self.use_graph):
-            raise RuntimeError("step_sample needs the Performer graph path")
+        if not self.use_graph:
+            raise RuntimeError("step_sample needs the graph path (use_graph=True)")
         self._sync_weights()
         if max(self.pos_host) + 1 > self.max_len:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
@@ -320,19 +359,23 @@ class Stage2Decoder:
     def _capture(self, with_sampler=False):
         m = self.m
         m.weights()                                   # make sure the bf16 shadow exists before capture
-        state0, pos0 = self.state.clone(), self.pos.clone()
+        # the warm-up / capture-time launches advance the state: Performer prefix sums are restored below; the GPT-2
+        # cache rows they write lie at or beyond `pos` and are rewritten when a real token reaches them
+        state0, pos0 = (self.state.clone() if self.is_performer else None), self.pos.clone()
+        if not self.is_performer and int(pos0.max()) + 3 > self.max_len:
+            raise RuntimeError("capturing the GPT-2 step needs 3 free cache rows below max_len")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):                        # warm-up outside capture (lazy module / attribute init)
-                self._performer_step_body()
+                self._step_body()
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         from . import _lib
         _lib.lib().emo_set_pdl(1 if self.use_pdl else 0)    # programmatic dependent launches inside the step graph
         try:
             with torch.cuda.graph(g):
-                self._performer_step_body()
+                self._step_body()
                 if with_sampler:
                     t, p, greedy, _ = self.sample_cfg
                     ops.sample(self.logits, m.n_token, t, p, self.u_in,
@@ -340,7 +383,8 @@ class Stage2Decoder:
                                banned=self._banned)
         finally:
             _lib.lib().emo_set_pdl(0)
-        self.state.copy_(state0)                      # undo the warm-up / capture-time state advance
+        if state0 is not None:
+            self.state.copy_(state0)                  # undo the warm-up / capture-time state advance
         self.pos.copy_(pos0)
         if with_sampler:
             self.graph_sample = g

@@ -124,7 +124,7 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
         if len(generated) < MAX_DEC_INP_LEN:
             if fed < len(generated):          # fold the not-yet-seen suffix (primer, new token, lead-sheet bar)
                 n_new = len(generated) - fed
-                if n_new == 1 and fed > 0 and dec.is_performer and dec.use_graph:
+                if n_new == 1 and fed > 0 and dec.use_graph:
                     # the common case: one new token -> model step and draw fused in one CUDA graph
                     u = 0.0 if greedy else (np.random if rng is None else rng).random_sample()
                     ids, st = dec.step_sample([generated[-1]], [seg_inp[-1]], [u], temp, top_p, greedy=greedy, banned=banned)

@@ -303,6 +303,16 @@ def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale, drop_p=0.0, seed=0):
           drop_p, int(seed), _dt(q), _stream())
 
 
+def attn_decode_step(qkv, kv_cache, pos, out, scale):
+    """qkv [B, 3*H*64] (the new token's q | k | v), kv_cache [B, max_len, 2*H*64], pos int64 [B] (device): appends k | v
+    at pos[b], attends over keys 0..pos[b]; out [B, H*64]"""
+    B, max_len = kv_cache.shape[0], kv_cache.shape[1]
+    H = kv_cache.shape[2] // 128
+    _call("emo_attn_decode_step", _p(qkv), qkv.stride(0), _p(kv_cache), max_len, _p(pos), _p(out), out.stride(0), B, H,
+          float(scale), _dt(qkv), _stream())
+    return out
+
+
 def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale, drop_p=0.0, seed=0):
     """r [Tk,H,64] (row p = distance Tk-1-p); biases [H,64] fp32."""
     B, Tq, H, E = q.shape

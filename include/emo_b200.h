@@ -218,6 +218,13 @@ int emo_attn_bwd(const void* q, const void* k, const void* v, int64_t ld_q, int6
                  void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, int B, int Tq, int Tk, int H,
                  float scale, float drop_p, uint64_t seed, int dtype, void* stream);
 
+/* Decode step of the GPT-2 attention for a ragged batch (one new token per sequence): appends this token's k | v row
+ * (qkv row b = [q | k | v], 3*H*64 values) to sequence b's cache [max_len][2*H*64] at pos[b] (int64, device) and attends
+ * over keys 0..pos[b].  Replaces the full-prefix re-run of HF GPT2Attention per sampled token
+ * (stage2_accompaniment/inference.py:252-272).  Static shapes: capturable in a CUDA graph. */
+int emo_attn_decode_step(const void* qkv, int64_t ld_qkv, void* kv_cache, int64_t max_len, const int64_t* pos,
+                         void* out, int64_t ld_out, int B, int H, float scale, int dtype, void* stream);
+
 /* ---- A9: stage-1 relative-position attention ----------------------------------------------
  * optimus_txl_decoder.py:305-387: score(i,j) = ((q_i+r_w_bias).k_j + (q_i+r_r_bias).r_{dist})/8,
  * dist = i + mlen - j (>= 0 visible), softmax, dropatt(drop_p, seed), renormalise /(sum+1e-8), . v

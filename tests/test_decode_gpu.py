@@ -64,6 +64,38 @@ def test_incremental_state_equals_full_prefix_forward(kind):
         assert rel_err(lb, full[0, 24]) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gpt2_ragged_batch_step_equals_per_sequence_decode(dtype):
+    """the batched GPT-2 step (projections over B rows, one ragged attention launch reading each sequence's own cache
+    length from the device, captured in a CUDA graph) against the per-sequence chunked path (append of one token)"""
+    from emo_disentanger_b200.decode import Stage2Decoder
+    from emo_disentanger_b200 import ops
+    V, L, B = 96, 2, 4
+    m = _stage2("gpt2", V, L, 9, dtype)
+    gen = torch.Generator().manual_seed(3)
+    T = 40
+    tok = torch.randint(0, V - 1, (B, T), generator=gen)
+    seg = torch.randint(0, 2, (B, T), generator=gen)
+    primers = [3, 11, 1, 7]                                   # ragged cache lengths
+    ref = Stage2Decoder(m, batch=B, max_len=64, use_graph=False)
+    dec = Stage2Decoder(m, batch=B, max_len=64, use_graph=True)
+    for d_ in (ref, dec):
+        for b in range(B):
+            d_.append(b, tok[b, :primers[b]].tolist(), seg[b, :primers[b]].tolist())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for s in range(10):
+        toks = [int(tok[b, primers[b] + s]) for b in range(B)]
+        segs = [int(seg[b, primers[b] + s]) for b in range(B)]
+        want = torch.stack([ref.append(b, [toks[b]], [segs[b]]).clone() for b in range(B)])
+        got = dec.step(toks, segs)
+        assert rel_err(got, want) < tol, (s, rel_err(got, want))
+    assert dec.pos_host == ref.pos_host and torch.equal(dec.pos, ref.pos)
+    # the caches hold the same rows
+    for b in range(B):
+        n = dec.pos_host[b]
+        assert rel_err(dec.kv[:, b, :n].float(), ref.kv[:, b, :n].float()) < tol
+
+
 @pytest.mark.parametrize("kind", ["performer", "gpt2"])
 def test_generate_conditional_greedy_tokens_identical_to_reference_loop(kind):
     from emo_disentanger_b200.generate import generate_conditional
