@@ -396,6 +396,15 @@ int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t 
 int emo_attn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* out,
                            const void* dout, int64_t ld_o, const float* lse, void* dq, void* dk, void* dv, int64_t ld_dq,
                            int64_t ld_dkv, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s);
+// relattn_tc.cu: the stage-1 relative-position attention on the same tcgen05 kernels (position scores through HBM)
+bool emo_relattn_tc_ok(int B, int Tq, int Tk, int H);
+int emo_relattn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* r, int64_t ld_r,
+                              const float* r_w_bias, const float* r_r_bias, void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk,
+                              int H, float scale, float drop_p, uint64_t seed, cudaStream_t s);
+int emo_relattn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* r, int64_t ld_r,
+                              const float* r_w_bias, const float* r_r_bias, const void* out, const void* dout, int64_t ld_out,
+                              const float* lse, void* dq, void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, float* dr, float* d_rw,
+                              float* d_rr, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s);
 // a 128-row query tile per CTA: below this many queries (decode steps) the 64-row mma.sync tiles waste less
 constexpr int ATTN_TC_MIN_TQ = 64;
 
@@ -486,6 +495,9 @@ extern "C" int emo_relattn_fwd(const void* q, const void* k, const void* v, int6
   if (rc) return rc;
   EMO_REQUIRE(r && r_w_bias && r_r_bias && al16(out), "emo_relattn_fwd: r / biases required, out 16-byte aligned");
   if (B * H == 0 || Tq == 0) return EMO_OK;
+  if (dtype == EMO_BF16 && emo_attn_tc_enabled() && scale > 0.f && emo_relattn_tc_ok(B, Tq, Tk, H) && ld_out == (int64_t)H * AE)
+    return emo_relattn_fwd_tc_launch(q, k, v, ld_q, ld_kv, r, ld_r, r_w_bias, r_r_bias, out, ld_out, lse, B, Tq, Tk, H, scale, drop_p, seed,
+                                     (cudaStream_t)stream);
   if (dtype == EMO_BF16) return attn_fwd_launch<bf16, true>(a, (cudaStream_t)stream);
   return attn_fwd_launch<float, true>(a, (cudaStream_t)stream);
 }
@@ -505,6 +517,9 @@ extern "C" int emo_relattn_bwd(const void* q, const void* k, const void* v, int6
               "emo_relattn_bwd: gradient pointers / strides must be 16-byte aligned");
   EMO_REQUIRE(r && r_w_bias && r_r_bias && lse && dr && d_r_w_bias && d_r_r_bias, "emo_relattn_bwd: null argument");
   if (B * H == 0 || Tq == 0) return EMO_OK;
+  if (dtype == EMO_BF16 && emo_attn_tc_enabled() && scale > 0.f && emo_relattn_tc_ok(B, Tq, Tk, H) && ld_out == (int64_t)H * AE)
+    return emo_relattn_bwd_tc_launch(q, k, v, ld_q, ld_kv, r, ld_r, r_w_bias, r_r_bias, out, dout, ld_out, lse, dq, dk, dv, ld_dq, ld_dkv, dr,
+                                     d_r_w_bias, d_r_r_bias, B, Tq, Tk, H, scale, drop_p, seed, (cudaStream_t)stream);
   if (dtype == EMO_BF16) return attn_bwd_launch<bf16, true>(a, (cudaStream_t)stream);
   return attn_bwd_launch<float, true>(a, (cudaStream_t)stream);
 }

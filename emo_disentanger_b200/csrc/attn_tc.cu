@@ -55,6 +55,11 @@ struct Params {
   int Tq, Tk, H, nqt;
   float sl2, keep_scale;                       // scale * log2(e); 1 / (1 - p)
   uint32_t drop_thr; uint64_t seed;
+  // stage-1 relative-position mode (relattn_tc.cu): bias [B*H][Tq][Tk] bf16 = the shifted position scores, added to
+  // Q K^T before the scale; rel != 0 also switches dropout to "drop keys, then renormalise" (a softmax over the kept
+  // keys: the mask joins the causal mask) and the 1e-8 of optimus_txl_decoder.py:362-363
+  const bf16* bias;
+  int rel;
 };
 
 __global__ void __launch_bounds__(NT, 2)
@@ -147,6 +152,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32_issue(tl + T_S + 32 * c, s + 32 * c);
       tmem_ld_wait();
+      if (p.bias) {                             // + position scores of this row (256 contiguous bytes), 32 columns at a time
+        const int ib = i < p.Tq ? i : p.Tq - 1;
+        const uint4* brow = reinterpret_cast<const uint4*>(p.bias + ((int64_t)bh * p.Tq + ib) * p.Tk + j0);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint4 bb[4];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) bb[k4] = __ldg(brow + 4 * c4 + k4);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t w[4] = {bb[k4].x, bb[k4].y, bb[k4].z, bb[k4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float b0, b1;
+              unpack_bf16x2(w[e], b0, b1);
+              const int c = 32 * c4 + 8 * k4 + 2 * e;
+              s[c] = __float_as_uint(__uint_as_float(s[c]) + b0);
+              s[c + 1] = __float_as_uint(__uint_as_float(s[c + 1]) + b1);
+            }
+          }
+        }
+      }
+      if (p.rel && p.drop_thr) {                // dropped keys leave the softmax
+        const uint64_t e0 = ((uint64_t)bh * p.Tq + i) * (uint64_t)p.Tk + j0;
+        const DropRow dr = drop_row(p.seed, e0, BN);
+        if (dr.fast) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const uint32_t hsh = emo_drop_mix(dr.lo0 + c, dr.key);
+            if ((hsh & 0xffffu) < p.drop_thr) s[2 * c] = 0xff800000u;
+            if ((hsh >> 16) < p.drop_thr) s[2 * c + 1] = 0xff800000u;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (!emo_drop_keep(p.seed, e0 + c, p.drop_thr)) s[c] = 0xff800000u;
+        }
+      }
       float mx = -INFINITY;
       if (j0 + BN - 1 > i0 + off) {             // CTA-uniform: the tile crosses the diagonal
         const int lim = lim_base - j0;
@@ -178,10 +221,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_st32(tl + T_O + 32, o + 32);
         }
       }
-      const float nm = -m_used;
+      const float nm = (m_used == -INFINITY) ? 0.f : -m_used;     // every key so far masked / dropped: exp2(-inf + 0) = 0, not NaN
       uint32_t pk[64];
       float sum0 = 0.f, sum1 = 0.f;
-      if (p.drop_thr == 0) {
+      if (p.drop_thr == 0 || p.rel) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
           const float p0 = ex2(fmaf(__uint_as_float(s[2 * c]), p.sl2, nm)), p1 = ex2(fmaf(__uint_as_float(s[2 * c + 1]), p.sl2, nm));
@@ -220,7 +263,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bar_o, (n - 1) & 1);
     tc_fence_after();
     {
-      const float inv = 1.f / l;
+      // stage 1: P / (sum P + 1e-8) with sum P = 1, or 0 when every key of the row was dropped
+      const float inv = p.rel ? (l > 0.f ? 1.f / (l * (1.f + 1e-8f)) : 0.f) : 1.f / l;
       bf16* orow = p.out + ((int64_t)b * p.Tq + i) * p.ld_o + (int64_t)h * HD;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -239,7 +283,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      if (p.lse && i < p.Tq) p.lse[(int64_t)bh * p.Tq + i] = m_used * LN2 + logf(l);
+      if (p.lse && i < p.Tq) p.lse[(int64_t)bh * p.Tq + i] = l > 0.f ? m_used * LN2 + logf(l) : INFINITY;
     }
   }
   tc_fence_before();
@@ -271,6 +315,10 @@ struct Params {
   float scale, sl2, keep_scale;
   uint32_t drop_thr; uint64_t seed;
   int drop_fast;                               // Tk even and fewer than 2^32 element pairs: one 32-bit hash per (query, key pair)
+  // stage-1 relative-position mode (relattn_tc.cu): biasT [B*H][Tk][Tq] bf16 = the TRANSPOSED shifted position scores,
+  // added to K Q^T; dbiasT (same layout) receives dS^T; rel != 0: dropout = drop keys and renormalise (no 1/(1-p))
+  const bf16* biasT; bf16* dbiasT;
+  int rel;
   long long* dbg_clk;                          // optional: clock64 stamps of worker thread 0, tiles 3 and 4 of CTA (0, 0)
 };
 
@@ -283,7 +331,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 // P = exp2(s * sl2 - lse2), dS = P * (dP_dropped - D) * scale  (aD holds D * scale).  DROP == 1: the fast mask (the two
 // lanes of a key pair share one hash per query column: each computes every other column and they swap);
 // DROP == 2: the general per-element mask.
-template <bool DIAG, int DROP>
+template <bool DIAG, int DROP, bool REL = false>
 __device__ __forceinline__ void ew_pass(const uint32_t (&s)[32], const uint32_t (&dp)[32], uint32_t aL, uint32_t aD, int cmin,
                                         const Params& p, uint32_t pbase, uint32_t key, int lane, uint64_t e_base,
                                         uint32_t (&pk)[16], uint32_t (&dsk)[16]) {
@@ -314,7 +362,11 @@ __device__ __forceinline__ void ew_pass(const uint32_t (&s)[32], const uint32_t 
       float pv = ex2(fmaf(__uint_as_float(s[c]), p.sl2, -lv[e]));
       if (DIAG) pv = (c >= cmin) ? pv : 0.f;
       const float dpv = __uint_as_float(dp[c]);
-      if (DROP) {
+      if (DROP && REL) {                     // a dropped key is outside the softmax: P = 0 there
+        pv = keep[e] ? pv : 0.f;
+        pd[e] = pv;
+        ds[e] = pv * fmaf(dpv, p.scale, -dv_[e]);
+      } else if (DROP) {
         pd[e] = keep[e] ? pv * p.keep_scale : 0.f;
         ds[e] = pv * (keep[e] ? fmaf(dpv, kss, -dv_[e]) : -dv_[e]);
       } else {
@@ -478,8 +530,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int cmin = j - off - i0 - 32 * ch;               // column c (query i0 + 32 ch + c) sees key j iff c >= cmin
       const uint64_t e_base = ((uint64_t)bh * p.Tq + (uint64_t)(i0 + 32 * ch)) * (uint64_t)p.Tk + (uint64_t)j;   // mask index of column 0
       const uint32_t pbase = (uint32_t)(e_base >> 1);
+      const int64_t boff = ((int64_t)bh * p.Tk + (j < p.Tk ? j : p.Tk - 1)) * p.Tq + i0 + 32 * ch;   // biasT / dbiasT: 32 queries of key row j
+      if (p.biasT) {
+        const uint4* brow = reinterpret_cast<const uint4*>(p.biasT + boff);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint4 bb = __ldg(brow + k4);
+          const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float b0, b1;
+            unpack_bf16x2(w[e], b0, b1);
+            s[8 * k4 + 2 * e] = __float_as_uint(__uint_as_float(s[8 * k4 + 2 * e]) + b0);
+            s[8 * k4 + 2 * e + 1] = __float_as_uint(__uint_as_float(s[8 * k4 + 2 * e + 1]) + b1);
+          }
+        }
+      }
       uint32_t pk[16], dsk[16];
-      if (drop_mode == 0) {
+      if (p.rel) {                                           // stage 1 (short sequences): one variant per dropout mode
+        if (drop_mode == 0) ew_pass<true, 0, true>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+        else if (drop_mode == 1) ew_pass<true, 1, true>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+        else ew_pass<true, 2, true>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
+      } else if (drop_mode == 0) {
         if (diag) ew_pass<true, 0>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
         else ew_pass<false, 0>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
       } else if (drop_mode == 1) {
@@ -488,7 +560,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       } else {
         ew_pass<true, 2>(s, dp, aL, aD, cmin, p, pbase, key, lane, e_base, pk, dsk);
       }
-      WSTAMP();
+      if (p.dbiasT && j < p.Tk && i0 + 32 * ch < p.Tq) {     // d(position scores)^T = dS^T: 64 contiguous bytes per thread (Tq % 32 == 0)
+        uint4* drow = reinterpret_cast<uint4*>(p.dbiasT + boff);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) drow[k4] = make_uint4(dsk[4 * k4], dsk[4 * k4 + 1], dsk[4 * k4 + 2], dsk[4 * k4 + 3]);
+      }
       if (it > 0) {                                          // products of tile it - 1 are complete: P^T / dS^T / dQ may be reused
         mbar_wait(bar_acc, (it - 1) & 1);
         WSTAMP();
@@ -570,14 +646,23 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* _
   }
 }
 
-// fp32 dQ workspace [B][Tq][H*64] -> bf16 dq (row stride ld_dq)
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t ld_dq, int64_t rows, int HD_all) {
+// fp32 dQ workspace [B][Tq][H*64] (+ optional bf16 addend of the same dense shape) -> bf16 dq (row stride ld_dq)
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, const bf16* __restrict__ add, bf16* __restrict__ dq, int64_t ld_dq,
+                                           int64_t rows, int HD_all) {
   const int vpr = HD_all / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * vpr) return;
   const int64_t row = idx / vpr;
   const int c = (int)(idx % vpr) * 8;
-  const float4 a = *reinterpret_cast<const float4*>(acc + row * HD_all + c), b = *reinterpret_cast<const float4*>(acc + row * HD_all + c + 4);
+  float4 a = *reinterpret_cast<const float4*>(acc + row * HD_all + c), b = *reinterpret_cast<const float4*>(acc + row * HD_all + c + 4);
+  if (add) {
+    const uint4 t = *reinterpret_cast<const uint4*>(add + row * HD_all + c);
+    float x0, x1;
+    unpack_bf16x2(t.x, x0, x1); a.x += x0; a.y += x1;
+    unpack_bf16x2(t.y, x0, x1); a.z += x0; a.w += x1;
+    unpack_bf16x2(t.z, x0, x1); b.x += x0; b.y += x1;
+    unpack_bf16x2(t.w, x0, x1); b.z += x0; b.w += x1;
+  }
   uint4 t;
   t.x = pack_bf16x2(a.x, a.y); t.y = pack_bf16x2(a.z, a.w); t.z = pack_bf16x2(b.x, b.y); t.w = pack_bf16x2(b.z, b.w);
   *reinterpret_cast<uint4*>(dq + row * ld_dq + c) = t;
@@ -595,8 +680,17 @@ int emo_attn_tc_enabled() {
 }
 extern "C" void emo_attn_set_tc(int on) { g_attn_tc = on ? 1 : 0; }   // test / A-B hook
 
-int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
-                           float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s) {
+// extras of the stage-1 relative-position mode (relattn_tc.cu); all NULL / 0 for the GPT-2 attention
+struct AttnTcRel {
+  const void* bias;      // forward: [B*H][Tq][Tk] bf16 shifted position scores
+  const void* biasT;     // backward: [B*H][Tk][Tq] bf16, transposed
+  void* dbiasT;          // backward: receives dS^T in the same layout
+  int rel;               // dropout = drop keys and renormalise; 1e-8 in the normaliser
+};
+
+int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
+                              float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, const AttnTcRel* rel,
+                              cudaStream_t s) {
   using namespace attn3;
   using namespace attn3::fwd;
   static bool configured = false;
@@ -612,8 +706,81 @@ int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t 
   Params p;
   p.out = (bf16*)out; p.ld_o = ld_o; p.lse = lse; p.Tq = Tq; p.Tk = Tk; p.H = H; p.nqt = (Tq + BM - 1) / BM;
   p.sl2 = scale * LOG2E; p.keep_scale = 1.f / (1.f - drop_p); p.drop_thr = emo_drop_thr(drop_p); p.seed = seed;
+  p.bias = rel ? (const bf16*)rel->bias : nullptr;
+  p.rel = rel ? rel->rel : 0;
   dim3 grid(p.nqt, B * H);
   attn_fwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
+                           float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s) {
+  return emo_attn_fwd_tc_launch_ex(q, k, v, ld_q, ld_kv, out, ld_o, lse, B, Tq, Tk, H, scale, drop_p, seed, nullptr, s);
+}
+
+// fp32 floats of workspace the backward core needs: dQ accumulator [B][Tq][H*64] + lse2 / dsum [B*H][Tq_pad]
+int64_t emo_attn_bwd_tc_ws_floats(int B, int Tq, int H) {
+  const int64_t Tq_pad = (int64_t)((Tq + attn3::BM - 1) / attn3::BM) * attn3::BM;
+  return (int64_t)B * Tq * H * attn3::HD + 2 * (int64_t)B * H * Tq_pad;
+}
+int emo_attn_tc_configure_pool() {
+  static bool done = false;
+  if (done) return EMO_OK;
+  int dev = 0;
+  cudaMemPool_t pool;
+  EMO_CHECK_CUDA(cudaGetDevice(&dev));
+  EMO_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t keep = ~0ull;                        // stream-ordered workspaces are recycled, not returned to the OS
+  EMO_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  done = true;
+  return EMO_OK;
+}
+// everything of the backward except the final fp32 -> bf16 conversion of dQ: zeroes ws, row statistics, main kernel.
+// On return (stream order) ws[0 .. B*Tq*H*64) holds dQ in fp32.
+int emo_attn_bwd_tc_core(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* out, const void* dout,
+                         int64_t ld_o, const float* lse, float* ws, void* dk, void* dv, int64_t ld_dkv, int B, int Tq, int Tk, int H,
+                         float scale, float drop_p, uint64_t seed, const AttnTcRel* rel, cudaStream_t s) {
+  using namespace attn3;
+  using namespace attn3::bwd;
+  static bool configured = false;
+  if (!configured) {
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int nqt = (Tq + BM - 1) / BM, nkt = (Tk + BN - 1) / BN, Tq_pad = nqt * BM;
+  const int64_t n_acc = (int64_t)B * Tq * H * HD, n_vec = (int64_t)B * H * Tq_pad;
+  float* dqacc = ws;
+  float* lse2 = ws + n_acc;
+  float* dsum = lse2 + n_vec;
+  EMO_CHECK_CUDA(cudaMemsetAsync(dqacc, 0, (size_t)n_acc * sizeof(float), s));
+  attn_bwd_prep_kernel<<<(unsigned)((n_vec * 8 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, ld_o, lse, lse2, dsum, Tq, Tq_pad, H, n_vec, scale);
+  EMO_LAUNCH_CHECK();
+  CUtensorMap mq, mk, mv, mdo, mdq;
+  int rc;
+  if ((rc = tcp::make_map_bt(&mq, q, (int64_t)H * HD, Tq, B, ld_q, BM))) return rc;
+  if ((rc = tcp::make_map_bt(&mk, k, (int64_t)H * HD, Tk, B, ld_kv, BN))) return rc;
+  if ((rc = tcp::make_map_bt(&mv, v, (int64_t)H * HD, Tk, B, ld_kv, BN))) return rc;
+  if ((rc = tcp::make_map_bt(&mdo, dout, (int64_t)H * HD, Tq, B, ld_o, BM))) return rc;
+  if ((rc = tcp::make_map_f32_bt(&mdq, dqacc, (int64_t)H * HD, Tq, B, 32, 16))) return rc;
+  Params p;
+  p.lse2 = lse2; p.dsum = dsum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_dkv = ld_dkv;
+  p.Tq = Tq; p.Tk = Tk; p.Tq_pad = Tq_pad; p.H = H; p.nqt = nqt; p.scale = scale; p.sl2 = scale * LOG2E;
+  p.keep_scale = 1.f / (1.f - drop_p); p.drop_thr = emo_drop_thr(drop_p); p.seed = seed;
+  p.drop_fast = ((Tk & 1) == 0) && ((uint64_t)B * H * (uint64_t)Tq * (uint64_t)Tk < (1ull << 33));
+  p.biasT = rel ? (const bf16*)rel->biasT : nullptr;
+  p.dbiasT = rel ? (bf16*)rel->dbiasT : nullptr;
+  p.rel = rel ? rel->rel : 0;
+  { const char* e = getenv("EMO_ATTN_DBG_CLK"); p.dbg_clk = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  dim3 grid(nkt, B * H);
+  attn_bwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, mdo, mdq, p);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+// dq (bf16, row stride ld_dq) = fp32 accumulator (+ optional dense bf16 addend)
+int emo_attn_bwd_tc_convert(const float* dqacc, const void* add, void* dq, int64_t ld_dq, int B, int Tq, int H, cudaStream_t s) {
+  using namespace attn3;
+  const int64_t nconv = (int64_t)B * Tq * (H * HD / 8);
+  bwd::attn_bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, s>>>(dqacc, (const bf16*)add, (bf16*)dq, ld_dq, (int64_t)B * Tq, H * HD);
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
@@ -621,52 +788,16 @@ int emo_attn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t 
 int emo_attn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* out,
                            const void* dout, int64_t ld_o, const float* lse, void* dq, void* dk, void* dv, int64_t ld_dq,
                            int64_t ld_dkv, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s) {
-  using namespace attn3;
-  using namespace attn3::bwd;
-  static bool configured = false;
-  if (!configured) {
-    EMO_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    int dev = 0;
-    cudaMemPool_t pool;
-    EMO_CHECK_CUDA(cudaGetDevice(&dev));
-    EMO_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = ~0ull;                      // the stream-ordered workspace below is recycled, not returned to the OS
-    EMO_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    configured = true;
-  }
-  const int nqt = (Tq + BM - 1) / BM, nkt = (Tk + BN - 1) / BN, Tq_pad = nqt * BM;
-  const int64_t n_acc = (int64_t)B * Tq * H * HD, n_vec = (int64_t)B * H * Tq_pad;
+  int rc = emo_attn_tc_configure_pool();
+  if (rc) return rc;
   float* ws = nullptr;
-  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(n_acc + 2 * n_vec) * sizeof(float), s));
-  float* dqacc = ws;
-  float* lse2 = ws + n_acc;
-  float* dsum = lse2 + n_vec;
-  int rc = EMO_OK;
-  do {
-    if (cudaMemsetAsync(dqacc, 0, (size_t)n_acc * sizeof(float), s) != cudaSuccess) { rc = EMO_ERR_CUDA; break; }
-    attn_bwd_prep_kernel<<<(unsigned)((n_vec * 8 + 255) / 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, ld_o, lse, lse2, dsum, Tq, Tq_pad, H, n_vec, scale);
-    CUtensorMap mq, mk, mv, mdo, mdq;
-    if ((rc = tcp::make_map_bt(&mq, q, (int64_t)H * HD, Tq, B, ld_q, BM))) break;
-    if ((rc = tcp::make_map_bt(&mk, k, (int64_t)H * HD, Tk, B, ld_kv, BN))) break;
-    if ((rc = tcp::make_map_bt(&mv, v, (int64_t)H * HD, Tk, B, ld_kv, BN))) break;
-    if ((rc = tcp::make_map_bt(&mdo, dout, (int64_t)H * HD, Tq, B, ld_o, BM))) break;
-    if ((rc = tcp::make_map_f32_bt(&mdq, dqacc, (int64_t)H * HD, Tq, B, 32, 16))) break;
-    Params p;
-    p.lse2 = lse2; p.dsum = dsum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_dkv = ld_dkv;
-    p.Tq = Tq; p.Tk = Tk; p.Tq_pad = Tq_pad; p.H = H; p.nqt = nqt; p.scale = scale; p.sl2 = scale * LOG2E;
-    p.keep_scale = 1.f / (1.f - drop_p); p.drop_thr = emo_drop_thr(drop_p); p.seed = seed;
-    p.drop_fast = ((Tk & 1) == 0) && ((uint64_t)B * H * (uint64_t)Tq * (uint64_t)Tk < (1ull << 33));
-    { const char* e = getenv("EMO_ATTN_DBG_CLK"); p.dbg_clk = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-    dim3 grid(nkt, B * H);
-    attn_bwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, mdo, mdq, p);
-    const int64_t nconv = (int64_t)B * Tq * (H * HD / 8);
-    attn_bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, s>>>(dqacc, (bf16*)dq, ld_dq, (int64_t)B * Tq, H * HD);
-  } while (0);
-  cudaError_t e1 = cudaGetLastError();
+  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)emo_attn_bwd_tc_ws_floats(B, Tq, H) * sizeof(float), s));
+  rc = emo_attn_bwd_tc_core(q, k, v, ld_q, ld_kv, out, dout, ld_o, lse, ws, dk, dv, ld_dkv, B, Tq, Tk, H, scale, drop_p, seed, nullptr, s);
+  if (!rc) rc = emo_attn_bwd_tc_convert(ws, nullptr, dq, ld_dq, B, Tq, H, s);
   cudaError_t e2 = cudaFreeAsync(ws, s);
   if (rc) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    emo_set_error("emo_attn_bwd (tcgen05): CUDA error %d (%s)", (int)(e1 != cudaSuccess ? e1 : e2), cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  if (e2 != cudaSuccess) {
+    emo_set_error("emo_attn_bwd (tcgen05): CUDA error %d (%s)", (int)e2, cudaGetErrorString(e2));
     return EMO_ERR_CUDA;
   }
   return EMO_OK;

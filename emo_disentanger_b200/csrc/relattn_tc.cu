@@ -1,0 +1,238 @@
+// K9 on the 5th-gen tensor cores: the stage-1 relative-position attention (stage1_compose/model/optimus_txl_decoder.py:
+// 305-387, RelPartialLearnableMultiHeadAttn) built from the tcgen05 attention kernels of attn_tc.cu + the tcgen05 GEMM.
+//
+//   score(i, j) = scale * ( (q_i + r_w_bias) . k_j  +  (q_i + r_r_bias) . r_{p(i,j)} ),   p(i, j) = Tq - 1 - i + j
+//
+// The position term is a Toeplitz-shifted read of G = (q + r_r_bias) r^T (the reference's _rel_shift): row i of the
+// score tile needs G[i][Tq - 1 - i + j], a per-ROW column shift.  A tcgen05.ld addresses the same columns for all 32
+// lanes of a warp and an MMA cannot produce the shifted tile directly (no operand depends on i alone or j alone), so
+// the shift is done by ADDRESSING in HBM instead of in registers:
+//   forward    qw = q + r_w_bias, qv = q + r_r_bias                              (one element-wise pass)
+//              G_h [B*Tq, Tk] = qv_h r_h^T   for the 8 heads                    (tcgen05 GEMM, K = 64)
+//              BD [B*H][Tq][Tk] = shifted G                                      (row-wise copy at a row-dependent offset)
+//              attention forward with BD as an additive score tile               (attn_fwd_tc_kernel, rel mode)
+//   backward   G, BD^T [B*H][Tk][Tq] re-made (cheaper than keeping 0.5 GB per layer alive), attention backward adds
+//              BD^T to K Q^T and writes dS^T next to it; dG = un-shifted, transposed dS^T; then three GEMM families:
+//              dqv_h = dG_h r_h,  dr_h += dG_h^T qv_h,  and dq = dqw (attention) + dqv; bias gradients = column sums.
+// Position scores travel as bf16 (like every activation of the bf16 path); everything is fp32 inside the kernels.
+// Shapes that do not fit (Tq < 64, Tk % 64, Tq % 32, fp32) stay on attn.cu's mma.sync kernels.
+#include "common.cuh"
+
+struct AttnTcRel { const void* bias; const void* biasT; void* dbiasT; int rel; };
+int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
+                              float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, const AttnTcRel* rel,
+                              cudaStream_t s);
+int64_t emo_attn_bwd_tc_ws_floats(int B, int Tq, int H);
+int emo_attn_tc_configure_pool();
+int emo_attn_bwd_tc_core(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* out, const void* dout,
+                         int64_t ld_o, const float* lse, float* ws, void* dk, void* dv, int64_t ld_dkv, int B, int Tq, int Tk, int H,
+                         float scale, float drop_p, uint64_t seed, const AttnTcRel* rel, cudaStream_t s);
+int emo_attn_bwd_tc_convert(const float* dqacc, const void* add, void* dq, int64_t ld_dq, int B, int Tq, int H, cudaStream_t s);
+
+namespace {
+constexpr int RE = 64;
+
+// qw = q + r_w_bias, qv = q + r_r_bias: dense [rows][d] bf16 copies of the strided q (8 elements per thread)
+__global__ void rel_prep_kernel(const bf16* __restrict__ q, int64_t ld_q, const float* __restrict__ rwb, const float* __restrict__ rrb,
+                                bf16* __restrict__ qw, bf16* __restrict__ qv, int64_t rows, int d) {
+  const int vpr = d / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * vpr) return;
+  const int64_t row = idx / vpr;
+  const int c = (int)(idx % vpr) * 8;
+  Vec<bf16> x, a, b;
+  x.load(q + row * ld_q + c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a.v[j] = x.v[j] + rwb[c + j]; b.v[j] = x.v[j] + rrb[c + j]; }
+  a.store(qw + row * d + c);
+  b.store(qv + row * d + c);
+}
+
+// BD[bh][i][j] = G[h][b*Tq + i][Tq - 1 - i + j] for the visible keys (j <= i + off), 0 elsewhere.  8 keys per thread.
+__global__ void rel_shift_kernel(const bf16* __restrict__ G, bf16* __restrict__ BD, int B, int H, int Tq, int Tk) {
+  const int vpr = Tk / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * H * Tq * vpr;
+  if (idx >= total) return;
+  const int j0 = (int)(idx % vpr) * 8;
+  const int64_t row = idx / vpr;                 // (b*H + h)*Tq + i
+  const int i = (int)(row % Tq);
+  const int64_t bh = row / Tq;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  const int off = Tk - Tq;
+  const bf16* g = G + ((int64_t)h * B * Tq + (int64_t)b * Tq + i) * Tk + (Tq - 1 - i);
+  Vec<bf16> o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int j = j0 + e;
+    o.v[e] = (j <= i + off) ? to_f(g[j]) : 0.f;
+  }
+  o.store(BD + row * Tk + j0);
+}
+
+// BDT[bh][j][i] = G[h][b*Tq + i][Tq - 1 - i + j] (visible pairs; 0 elsewhere): 64 x 64 tiles through shared memory, raw
+// 16-bit moves (no conversion); a warp reads one query row (128 contiguous bytes at a row-dependent offset) and writes
+// one key row (128 contiguous bytes)
+__global__ void __launch_bounds__(256) rel_shift_t_kernel(const bf16* __restrict__ G, bf16* __restrict__ BDT, int B, int H, int Tq, int Tk) {
+  __shared__ unsigned short tile[64][66];
+  const unsigned short* g16 = reinterpret_cast<const unsigned short*>(G);
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.z;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  const int off = Tk - Tq;
+  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned short* gb = g16 + ((int64_t)h * B * Tq + (int64_t)b * Tq) * Tk;
+#pragma unroll
+  for (int ii = w; ii < 64; ii += 8) {
+    const int i = i0 + ii;
+    const unsigned short* row = gb + (int64_t)i * Tk + (Tq - 1 - i) + j0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int jj = tx + 32 * hh, j = j0 + jj;
+      unsigned short v = 0;
+      if (i < Tq && j < Tk && j <= i + off) v = __ldg(row + jj);
+      tile[ii][jj] = v;
+    }
+  }
+  __syncthreads();
+  if (i0 + 2 * tx >= Tq) return;                 // Tq is even (a multiple of 32)
+#pragma unroll
+  for (int jj = w; jj < 64; jj += 8) {
+    const int j = j0 + jj;
+    if (j < Tk) {
+      const uint32_t v = (uint32_t)tile[2 * tx][jj] | ((uint32_t)tile[2 * tx + 1][jj] << 16);
+      *reinterpret_cast<uint32_t*>(BDT + (bh * Tk + j) * Tq + i0 + 2 * tx) = v;
+    }
+  }
+}
+
+// dG[h][b*Tq + i][t] = dBDT[bh][j][i] with j = t - (Tq - 1) + i when 0 <= j <= min(i + off, Tk - 1), else 0.
+// Output tile 64 (i) x 64 (t); its sources are 127 rows j of 64 consecutive i.
+__global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict__ dBDT, bf16* __restrict__ dG, int B, int H, int Tq, int Tk) {
+  __shared__ unsigned short patch[127][66];
+  const int i0 = blockIdx.x * 64, t0 = blockIdx.y * 64;
+  const int64_t bh = blockIdx.z;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  const int off = Tk - Tq;
+  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int jmin = t0 - (Tq - 1) + i0;
+  for (int jr = w; jr < 127; jr += 8) {
+    const int j = jmin + jr, i = i0 + 2 * tx;
+    uint32_t v = 0;
+    if (j >= 0 && j < Tk && i < Tq) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(dBDT + (bh * Tk + j) * Tq + i));
+      if (j > i + 1 + off) v = 0;                // both queries of the pair are before the key
+      else if (j == i + 1 + off) v &= 0xffff0000u;     // only the second query of the pair sees the key
+    }
+    patch[jr][2 * tx] = (unsigned short)(v & 0xffffu);
+    patch[jr][2 * tx + 1] = (unsigned short)(v >> 16);
+  }
+  __syncthreads();
+  if (t0 + 2 * tx >= Tk) return;                 // Tk is a multiple of 64
+#pragma unroll
+  for (int ii = w; ii < 64; ii += 8) {
+    const int i = i0 + ii;
+    if (i < Tq) {
+      const uint32_t v = (uint32_t)patch[2 * tx + ii][ii] | ((uint32_t)patch[2 * tx + 1 + ii][ii] << 16);
+      *reinterpret_cast<uint32_t*>(dG + ((int64_t)h * B * Tq + (int64_t)b * Tq + i) * Tk + t0 + 2 * tx) = v;
+    }
+  }
+}
+
+int rel_scores(const bf16* qv, const void* r, int64_t ld_r, bf16* G, int B, int Tq, int Tk, int H, cudaStream_t s) {
+  const int d = H * RE;
+  for (int h = 0; h < H; ++h) {          // G_h [B*Tq, Tk] = qv_h [B*Tq, 64] . r_h [Tk, 64]^T
+    int rc = emo_gemm(EMO_GEMM_NT, (int64_t)B * Tq, Tk, RE, qv + h * RE, d, (const bf16*)r + h * RE, ld_r, G + (int64_t)h * B * Tq * Tk, Tk,
+                      EMO_BF16, EMO_BF16, nullptr, s);
+    if (rc) return rc;
+  }
+  return EMO_OK;
+}
+}  // namespace
+
+bool emo_relattn_tc_ok(int B, int Tq, int Tk, int H) {
+  // (a single short sequence is launch-bound: ~45 launches here against 3 of the mma.sync kernels)
+  return Tq >= 64 && (Tk % 64) == 0 && (Tq % 32) == 0 && (int64_t)B * Tq >= 2048 && (int64_t)B * H * Tq * (int64_t)Tk < (1ll << 40);
+}
+
+int emo_relattn_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* r, int64_t ld_r,
+                              const float* r_w_bias, const float* r_r_bias, void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk,
+                              int H, float scale, float drop_p, uint64_t seed, cudaStream_t s) {
+  int rc = emo_attn_tc_configure_pool();
+  if (rc) return rc;
+  const int d = H * RE;
+  const int64_t rows = (int64_t)B * Tq, nG = (int64_t)H * rows * Tk;
+  bf16* ws = nullptr;
+  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(2 * rows * d + 2 * nG + 512) * sizeof(bf16), s));
+  bf16 *qw = ws, *qv = qw + rows * d, *G = qv + rows * d, *BD = G + nG;
+  do {
+    rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
+    if ((rc = rel_scores(qv, r, ld_r, G, B, Tq, Tk, H, s))) break;
+    rel_shift_kernel<<<(unsigned)(((int64_t)B * H * Tq * (Tk / 8) + 255) / 256), 256, 0, s>>>(G, BD, B, H, Tq, Tk);
+    AttnTcRel ex = {BD, nullptr, nullptr, 1};
+    rc = emo_attn_fwd_tc_launch_ex(qw, k, v, d, ld_kv, out, ld_out, lse, B, Tq, Tk, H, scale, drop_p, seed, &ex, s);
+  } while (0);
+  cudaError_t e1 = cudaGetLastError(), e2 = cudaFreeAsync(ws, s);
+  if (rc) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    emo_set_error("emo_relattn_fwd (tcgen05): CUDA error %d (%s)", (int)(e1 != cudaSuccess ? e1 : e2), cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return EMO_ERR_CUDA;
+  }
+  return EMO_OK;
+}
+
+int emo_relattn_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, const void* r, int64_t ld_r,
+                              const float* r_w_bias, const float* r_r_bias, const void* out, const void* dout, int64_t ld_out,
+                              const float* lse, void* dq, void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv, float* dr, float* d_rw,
+                              float* d_rr, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, cudaStream_t s) {
+  int rc = emo_attn_tc_configure_pool();
+  if (rc) return rc;
+  const int d = H * RE;
+  const int64_t rows = (int64_t)B * Tq, nG = (int64_t)H * rows * Tk;
+  const int64_t nf = emo_attn_bwd_tc_ws_floats(B, Tq, H);
+  bf16* ws = nullptr;
+  float* wf = nullptr;
+  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(3 * rows * d + 3 * nG + 512) * sizeof(bf16), s));
+  if (cudaMallocAsync((void**)&wf, (size_t)nf * sizeof(float), s) != cudaSuccess) {
+    cudaFreeAsync(ws, s);
+    emo_set_error("emo_relattn_bwd (tcgen05): workspace allocation failed");
+    return EMO_ERR_CUDA;
+  }
+  bf16 *qw = ws, *qv = qw + rows * d, *dqv = qv + rows * d, *G = dqv + rows * d, *BDT = G + nG, *dBDT = BDT + nG;
+  bf16* dG = G;                                   // G is dead once BD^T exists
+  do {
+    rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
+    if ((rc = rel_scores(qv, r, ld_r, G, B, Tq, Tk, H, s))) break;
+    dim3 tgrid((Tq + 63) / 64, (Tk + 63) / 64, B * H);
+    rel_shift_t_kernel<<<tgrid, 256, 0, s>>>(G, BDT, B, H, Tq, Tk);
+    AttnTcRel ex = {nullptr, BDT, dBDT, 1};
+    if ((rc = emo_attn_bwd_tc_core(qw, k, v, d, ld_kv, out, dout, ld_out, lse, wf, dk, dv, ld_dkv, B, Tq, Tk, H, scale, drop_p, seed, &ex, s))) break;
+    rel_unshift_kernel<<<tgrid, 256, 0, s>>>(dBDT, dG, B, H, Tq, Tk);
+    for (int h = 0; h < H && !rc; ++h) {
+      // dqv_h [B*Tq, 64] = dG_h [B*Tq, Tk] . r_h [Tk, 64]
+      rc = emo_gemm(EMO_GEMM_NN, rows, RE, Tk, dG + (int64_t)h * rows * Tk, Tk, (const bf16*)r + h * RE, ld_r, dqv + h * RE, d, EMO_BF16,
+                    EMO_BF16, nullptr, s);
+      if (rc) break;
+      // dr_h [Tk, 64] (fp32, row stride H*64) += dG_h^T . qv_h
+      emo_epilogue ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.alpha = 1.f;
+      ep.accumulate = 1;
+      rc = emo_gemm(EMO_GEMM_TN, Tk, RE, rows, dG + (int64_t)h * rows * Tk, Tk, qv + h * RE, d, dr + h * RE, (int64_t)H * RE, EMO_BF16, EMO_F32,
+                    &ep, s);
+    }
+    if (rc) break;
+    // bias gradients: r_w_bias sees the content part of dq, r_r_bias the position part
+    if ((rc = emo_colsum(wf, d, rows, d, d_rw, EMO_F32, s))) break;
+    if ((rc = emo_colsum(dqv, d, rows, d, d_rr, EMO_BF16, s))) break;
+    rc = emo_attn_bwd_tc_convert(wf, dqv, dq, ld_dq, B, Tq, H, s);
+  } while (0);
+  cudaError_t e1 = cudaGetLastError(), e2 = cudaFreeAsync(ws, s), e3 = cudaFreeAsync(wf, s);
+  if (rc) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    emo_set_error("emo_relattn_bwd (tcgen05): CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
+    return EMO_ERR_CUDA;
+  }
+  return EMO_OK;
+}

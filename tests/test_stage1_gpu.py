@@ -156,3 +156,48 @@ def test_stage1_training_with_dropout_learns_and_checkpoint_round_trip(tmp_path)
     m2.load_state_dict(torch.load(path, map_location="cpu"))           # strict, as stage1 train.py:213-228
     assert torch.equal(m2._flat.cpu(), m._flat.cpu())
     assert len(m.state_dict()) == 6 + 11 * int(g["L"])
+
+
+@pytest.mark.parametrize("B,Tq,Tk,p", [(4, 512, 512, 0.0), (4, 512, 512, 0.1), (12, 192, 192, 0.25), (16, 128, 320, 0.0)])
+def test_relattn_tcgen05_equals_mma_sync(B, Tq, Tk, p):
+    """the stage-1 relative-position attention through the tcgen05 kernels (position scores G = (q + r_r_bias) r^T by the
+    tcgen05 GEMM, shifted by addressing in HBM, added to the score tiles inside the attention kernels) against the
+    round-1 mma.sync kernels (band GEMM + skew in shared memory): out, lse, dq / dk / dv, dr and both bias gradients,
+    with the same drop-and-renormalise mask"""
+    from emo_disentanger_b200 import ops, _lib
+    H, d = 8, 512
+    g = torch.Generator().manual_seed(Tq + Tk)
+    xq = (torch.randn(B, Tq, d, generator=g) * 0.8).to(DEV).to(torch.bfloat16)
+    xkv = (torch.randn(B, Tk, 2 * d, generator=g) * 0.8).to(DEV).to(torch.bfloat16)
+    r = (torch.randn(Tk, H, 64, generator=g) * 0.8).to(DEV).to(torch.bfloat16)
+    rw, rr = (0.3 * torch.randn(H, 64, generator=g)).to(DEV), (0.3 * torch.randn(H, 64, generator=g)).to(DEV)
+    dout = torch.randn(B, Tq, d, generator=g).to(DEV).to(torch.bfloat16)
+    q = xq.unflatten(-1, (H, 64))
+    k, v = xkv[:, :, :d].unflatten(-1, (H, 64)), xkv[:, :, d:].unflatten(-1, (H, 64))
+    res = []
+    for tc in (1, 0):
+        _lib.lib().emo_attn_set_tc(tc)
+        try:
+            out = torch.empty(B, Tq, d, device=DEV, dtype=torch.bfloat16)
+            lse = torch.empty(B, H, Tq, device=DEV)
+            ops.relattn_fwd(q, k, v, r, rw, rr, out, lse, 0.125, p, 99)
+            dxq, dxkv = torch.empty_like(xq), torch.empty_like(xkv)
+            dq = dxq.unflatten(-1, (H, 64))
+            dk, dv = dxkv[:, :, :d].unflatten(-1, (H, 64)), dxkv[:, :, d:].unflatten(-1, (H, 64))
+            dr = torch.zeros(Tk, H, 64, device=DEV)
+            drw, drr = torch.zeros(H, 64, device=DEV), torch.zeros(H, 64, device=DEV)
+            if Tq == Tk:
+                ops.relattn_bwd(q, k, v, r, rw, rr, out, dout, lse, dq, dk, dv, dr, drw, drr, 0.125, p, 99)
+            torch.cuda.synchronize()
+            res.append((out.float(), lse.clone(), dxq.float(), dxkv.float(), dr, drw, drr))
+        finally:
+            _lib.lib().emo_attn_set_tc(1)
+    a, b = res
+    assert torch.isfinite(a[0]).all()
+    assert rms_rel(a[0], b[0]) < 1e-2, "out"
+    fin = torch.isfinite(b[1])
+    assert torch.equal(torch.isfinite(a[1]), fin) and float((a[1][fin] - b[1][fin]).abs().max()) < 3e-2, "lse"
+    if Tq == Tk:
+        for i, nm in ((2, "dq"), (3, "dkv"), (4, "dr"), (5, "d_r_w_bias"), (6, "d_r_r_bias")):
+            assert torch.isfinite(a[i]).all(), nm
+            assert rms_rel(a[i], b[i]) < 2.5e-2, (nm, rms_rel(a[i], b[i]))
