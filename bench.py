@@ -247,7 +247,8 @@ def _class_roofline(ops, ms_step, tokens_step, flops_token_attn=None):
         fl = flops_token_attn * tokens_step
         ach = fl / (att_ms * 1e-3) / 1e12
         rel = any("relattn" in k for k, v in summ.items() if v[0])
-        kname = ("attn_fwd / attn_bwd_dkv / attn_bwd_dq <REL> (flash-style relative-position attention, mma.sync)" if rel else
+        kname = ("relative-position attention: attn_fwd_tc_kernel / attn_bwd_tc_kernel in rel mode + the position-score GEMMs "
+                 "and shift kernels of relattn_tc.cu (tcgen05 + TMA)" if rel else
                  "attn_fwd_tc_kernel / attn_bwd_tc_kernel (flash-style causal softmax attention, tcgen05 + TMA, attn_tc.cu)")
         roof = {"kernel": kname,
                 "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -265,7 +266,7 @@ def _class_roofline(ops, ms_step, tokens_step, flops_token_attn=None):
     return roof, shares
 
 
-def bench_gpt2_train(cpu=True, B=16, steps=6, warmup=3):
+def bench_gpt2_train(cpu=True, B=48, steps=6, warmup=3):
     """BASELINE.json configs[2]: stage-2 GPT-2 backbone, REMI representation (V = 372), seq 2048, bf16, 1 GPU."""
     import contextlib
     import torch

@@ -267,19 +267,21 @@ class Stage2Decoder:
         scale = 1.0 / (E ** 0.5)
         for l in range(m.n_layer):
             nm = "transformer_decoder.%d." % l
+            # ln_1 / ln_2 ride as the prologue of the projection that consumes them (in-kernel for these <= 8 rows):
+            # 5 launches per layer
             a = new(B, d)
-            ops.ln_fwd(h, m._wv(Wf, nm + "ln_1.weight"), m._wv(Wf, nm + "ln_1.bias"), a)
             qkv = new(B, 3 * d)
-            ops.linear_fwd(a, self.wT[nm + "attn.c_attn.weight"], qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"))
+            ops.linear_fwd(h, self.wT[nm + "attn.c_attn.weight"], qkv, bias=m._wv(Wf, nm + "attn.c_attn.bias"),
+                           ln=(m._wv(Wf, nm + "ln_1.weight"), m._wv(Wf, nm + "ln_1.bias"), a))
             att = new(B, d)
             ops.attn_decode_step(qkv, self.kv[l], self.pos_tok, att, scale)
             hx = new(B, d)
             ops.linear_fwd(att, self.wT[nm + "attn.c_proj.weight"], hx, bias=m._wv(Wf, nm + "attn.c_proj.bias"),
                            residual=h, ld_res=d)
             c = new(B, d)
-            ops.ln_fwd(hx, m._wv(Wf, nm + "ln_2.weight"), m._wv(Wf, nm + "ln_2.bias"), c)
             g = new(B, f)
-            ops.linear_fwd(c, self.wT[nm + "mlp.c_fc.weight"], g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"), act=ops.ACT_GELU_NEW)
+            ops.linear_fwd(hx, self.wT[nm + "mlp.c_fc.weight"], g, bias=m._wv(Wf, nm + "mlp.c_fc.bias"), act=ops.ACT_GELU_NEW,
+                           ln=(m._wv(Wf, nm + "ln_2.weight"), m._wv(Wf, nm + "ln_2.bias"), c))
             h = new(B, d)
             ops.linear_fwd(g, self.wT[nm + "mlp.c_proj.weight"], h, bias=m._wv(Wf, nm + "mlp.c_proj.bias"),
                            residual=hx, ld_res=d)
