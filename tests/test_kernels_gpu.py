@@ -505,7 +505,7 @@ def test_favor_backward_vs_oracle_autograd(ops, dtype, T, B):
     qo, ko, vo = _split(x, H)
     ref, _ = PO.causal_linear_attention(qo, ko, vo, omega.double())
     ref.backward(dout.double().view(B, T, H, 64))
-    tol = 1e-3 if dtype == torch.float32 else 3e-2      # north-star: 1e-3 rel in the fp32 mode
+    tol = 1e-3 if dtype == torch.float32 else 1.5e-2    # north-star: 1e-3 rel in the fp32 mode; bf16 measures 4.7e-3 .. 8.4e-3
     d = H * 64
     scale = float(x.grad[:, :, 2 * d:].float().pow(2).mean().sqrt())
     for i, name in enumerate("qkv"):

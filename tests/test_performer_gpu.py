@@ -58,7 +58,7 @@ def test_bf16_hidden_and_logits_vs_golden():
     assert abs(float(loss) - float(g["loss"])) < 2e-2
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 8e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 6e-2)])      # bf16 measures <= 3e-2 except one bias gradient (linear1.bias of layer 1, heavy cancellation: 5.1e-2)
 def test_gradients_vs_golden(dtype, tol):
     g = golden("performer_small.npz")
     m = _model(g, dtype).train()          # dropout p = 0 -> deterministic
