@@ -103,13 +103,15 @@ class ClockSampler:
 
 def measured_traffic(kernel_substr):
     """mean DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from the ncu
-    pass over this same command that is committed under profiles/ (profiles/r01_traffic.json, written by
+    pass over this same command that is committed under profiles/ (the newest profiles/rNN_traffic.json, written by
     scripts/ncu_traffic.py); None when no capture for this batch size has been committed."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return d
-    except Exception:
-        return None
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            return json.load(open(f))
+        except Exception:
+            continue
+    return None
 
 
 def make_batches(n, B, T, V, seed0, pinned):
