@@ -197,6 +197,24 @@ __device__ __forceinline__ void load_bias32(float4 (&b)[8], const float* bias, i
 #pragma unroll
   for (int j = 0; j < 8; ++j) b[j] = __ldg(b4 + j);
 }
+// gelu_new on the bf16 path: tanh.approx.f32 (one MUFU op, abs error ~5e-4, far inside a bf16 ulp of the result) instead
+// of tanhf's ~20-instruction expansion -- the c_fc epilogue and the dgrad through c_proj of the GPT-2 blocks are
+// epilogue-issue bound.  The fp32 parity path (gemm_simt.cu) keeps tanhf.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_new_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanh_fast(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float gelu_new_grad_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float t = tanh_fast(k0 * (x + k1 * x * x * x));
+  const float dt = (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+  return 0.5f * (1.0f + t) + 0.5f * x * dt;
+}
 template <int PART = 0>   // 0 = everything, 1 = linear part only (alpha, rowscale, bias), 2 = activation + dropout only
 __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32], int64_t m, int64_t nb, const EpiParams& ep,
                                            const float4* bpre = nullptr /* bias values already in registers */) {
@@ -225,13 +243,13 @@ __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32],
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (ep.act == EMO_ACT_GELU_NEW) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_new_f(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_new_fast(v[j]);
   } else if (ep.act == EMO_ACT_RELU_MASK_BWD) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (a[j] != 0.f) ? v[j] * ep.aux_scale : 0.f;
   } else if (ep.act == EMO_ACT_GELU_NEW_BWD) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_f(a[j]);
+    for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_fast(a[j]);
   }
   if (ep.drop_thr) {
     const uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
