@@ -43,6 +43,7 @@ struct Params {
   float* state_out;
   float* seg_states;
   int nseg, seg_chunks, T, H, items, omega_f16;
+  long long* dbg_clk;
 };
 
 __global__ void __launch_bounds__(NT, 2)
@@ -55,13 +56,18 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t sXQ = sb + OFF_XQ, sXK = sb + OFF_XK, sXV = sb + OFF_XV, sPK = sb + OFF_PK, sSB = sb + OFF_SB, sOM = sb + OFF_OM;
   float* z = reinterpret_cast<float*>(smem + OFF_Z);
   float* zpart = reinterpret_cast<float*>(smem + OFF_ZP);
-  const uint32_t bar_qk = sb + OFF_BAR, bar_v = bar_qk + 8, bar_mma = bar_qk + 16, bar_xf = bar_qk + 24;
+  // One mbarrier PER MMA batch (each completes once per chunk).  With a single barrier for the three batches a worker
+  // that is slow to poll for batch 3 of chunk n can be overtaken by the commit of batch 1 of chunk n + 1 (the control
+  // warp only waits for the tensor pipe, not for the workers, in between): two phase flips later its parity test reads
+  // "not yet", and it then waits for batch 2 -- which needs that very worker at [B1].  Seen as a watchdog trap.
+  const uint32_t bar_qk = sb + OFF_BAR, bar_v = bar_qk + 8, bar_m1 = bar_qk + 16, bar_xf = bar_qk + 24, bar_m2 = bar_qk + 32,
+                 bar_m3 = bar_qk + 40;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 128) {
     prefetch_map(&tmQ); prefetch_map(&tmK); prefetch_map(&tmV);
-    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_mma, 1); mbar_init(bar_xf, 128);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_m3, 1); mbar_init(bar_xf, 128);
     mbar_init_fence();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), T_COLS);
@@ -77,7 +83,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t ID_U = p.omega_f16 ? make_idesc(64, false, true, 128, true, false) : make_idesc(64, false, true);
   constexpr uint32_t ID_S = make_idesc(128, false, false),
                      ID_O = make_idesc(64, false, true), ID_ST = make_idesc(64, true, true);
-  uint32_t ph_qk = 0, ph_v = 0, ph_mma = 0, ph_xf = 0;   // parities of the next completion each role waits for
+  uint32_t ph_qk = 0, ph_v = 0, ph_m = 0, ph_xf = 0;     // parities of the next completion each role waits for (ph_m: per chunk, all three batch barriers)
   // control warp: the tensor-memory base as a warp-uniform value, operand descriptors built once
   const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
   const DescLH dXQ = make_desc_lh(sXQ, 0, 1024), dXK = make_desc_lh(sXK, 0, 1024), dOM = make_desc_lh(sOM, 8192, 1024),
@@ -145,7 +151,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_PQ, desc_at(dXQ, ks * 32), desc_at(dOM, ks * 2048), ID_U, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ss(tm + T_SC, desc_at(dXK, ks * 32), desc_at(dOM, ks * 2048), ID_U, ks > 0);
-          umma_commit(bar_mma);
+          umma_commit(bar_m1);
         }
         __syncwarp();
         // the next chunk's q, k once every worker has read its x rows (the row norms) and batch 1 is done with them
@@ -155,7 +161,6 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_3d(&tmQ, bar_qk, sXQ, h * FE, t0 + C, b);
           tma_load_3d(&tmK, bar_qk, sXK, h * FE, t0 + C, b);
         }
-        ph_mma ^= 1;                           // batch 1 (the workers wait for it; this warp only keeps count)
         __syncwarp();
         named_bar_sync<1>(NT);                 // [B1] phi(k) in smem, phi(q) in TMEM
         tc_fence_after();
@@ -163,9 +168,8 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_ts(tm + T_SC, tm + T_PQ + ks * 8, desc_at((ks >> 2) ? dPK1 : dPK0, (ks & 3) * 32), ID_S, ks > 0);
-          umma_commit(bar_mma);
+          umma_commit(bar_m2);
         }
-        ph_mma ^= 1;                           // batch 2
         __syncwarp();
         named_bar_sync<1>(NT);                 // [B2] P in TMEM (and, from the previous chunk, S'_bf16 in smem)
         mbar_wait(bar_v, ph_v); ph_v ^= 1;
@@ -177,21 +181,25 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int ks = 0; ks < 8; ++ks) umma_ts(tm + T_O, tm + T_SC + ks * 8, desc_at(dXVmn, ks * 2048), ID_O, 1u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) umma_ss(tm + T_ST, desc_at(dPKmn, ks * 2048), desc_at(dXVmn, ks * 2048), ID_ST, 1u);
-          umma_commit(bar_mma);
+          umma_commit(bar_m3);
         }
         __syncwarp();
-        mbar_wait(bar_mma, ph_mma);            // batch 3 done: v, phi(k) and the TMEM operands are free
+        mbar_wait(bar_m3, ph_m);               // batch 3 done: v, phi(k) and the TMEM operands are free
         if (t0 + C < t_end && elect_one()) {
           mbar_expect_tx(bar_v, C * FE * 2);
           tma_load_3d(&tmV, bar_v, sXV, h * FE, t0 + C, b);
         }
-        ph_mma ^= 1;
+        ph_m ^= 1;
         __syncwarp();
       } else {
         // ================================== worker warps ==================================
         const int i = tid;                     // token row of the chunk == TMEM lane
         const bool rowok = i < valid;
-        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;     // batch 1: U_q, U_k (which also means q, k have landed)
+        int wk = 0;
+#define FSTAMP() do { if (p.dbg_clk && tid == 0 && blockIdx.x == 0 && t0 == t_begin + 3 * C && wk < 16) p.dbg_clk[wk++] = clock64(); } while (0)
+        FSTAMP();
+        mbar_wait(bar_m1, ph_m);                     // batch 1: U_q, U_k (which also means q, k have landed)
+        FSTAMP();
         tc_fence_after();
         float ssq = 0.f, ssk = 0.f;
 #pragma unroll
@@ -205,12 +213,15 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         mbar_arrive_after_reads(bar_xf, ssq + ssk);
         const float oq = (0.5f * F_S2 * ssq + F_HALF_LOG_M) * K2, ok = (0.5f * F_S2 * ssk + F_HALF_LOG_M) * K2;
+        FSTAMP();
         // ---- phi(k) -> smem (rows past the end of the sequence are zero: they must not enter the state) ----
+        uint32_t uk[2][32];                     // both halves of U_k in flight at once: one TMEM round trip, not two
+        tmem_ld32_issue(tl + T_SC, uk[0]);
+        tmem_ld32_issue(tl + T_SC + 32, uk[1]);
+        tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32_issue(tl + T_SC + half * 32, r);
-          tmem_ld_wait();
+          const uint32_t (&r)[32] = uk[half];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             uint4 tp, tm;
@@ -226,6 +237,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             sts128(sPK + 16384 + sw128(i, half * 4 + cc), tm);
           }
         }
+        FSTAMP();
         // ---- phi(q) -> TMEM in place (both halves of U_q are read before anything is written) ----
         float dq = 0.f;
         {
@@ -263,10 +275,12 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st32(tl + T_PQ, pp);             // packed columns 0..31  = features 0..63   (exp(+u - o))
           tmem_st32(tl + T_PQ + 32, pm);        // packed columns 32..63 = features 64..127 (exp(-u - o))
         }
+        FSTAMP();
         tmem_st_wait();
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync<1>(NT);                 // [B1]
+        FSTAMP();
         // ---- z += column sums of phi(k), in the shadow of batch 2 ----
         {
           const int w = tid & 31, blk = (tid >> 5) & 1, hh = tid >> 6;
@@ -284,8 +298,10 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           named_bar_sync<2>(128);
           z[tid] += zpart[tid] + zpart[128 + tid];
         }
+        FSTAMP();
         // ---- P = tril(S) -> bf16 in place; row sums ----
-        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;     // batch 2
+        mbar_wait(bar_m2, ph_m);                     // batch 2
+        FSTAMP();
         tc_fence_after();
         float rs = 0.f;
 #pragma unroll
@@ -312,18 +328,23 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float den = rs + dq + F_EPS;
         tmem_st_wait();
         tc_fence_before();
+        FSTAMP();
         named_bar_sync<1>(NT);                 // [B2]
+        FSTAMP();
         // ---- out = O / den; S' -> bf16 -> smem ----
-        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;     // batch 3
+        mbar_wait(bar_m3, ph_m); ph_m ^= 1;          // batch 3
+        FSTAMP();
         tc_fence_after();
         {
           const float inv = 1.f / den;
           bf16* orow = p.out + ((int64_t)b * p.T + t0 + i) * p.ld_out + (int64_t)h * FE;
+          uint32_t ro[2][32];                   // both halves of O in flight at once
+          tmem_ld32_issue(tl + T_O, ro[0]);
+          tmem_ld32_issue(tl + T_O + 32, ro[1]);
+          tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld32_issue(tl + T_O + half * 32, r);
-            tmem_ld_wait();
+            const uint32_t (&r)[32] = ro[half];
             if (rowok) {
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
@@ -338,6 +359,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (p.den_out && rowok) p.den_out[((int64_t)b * p.T + t0 + i) * p.H + h] = den;
         }
+        FSTAMP();
         const bool last = t0 + C >= t_end;
         float* so = nullptr;                    // fp32 copy of the final state: [128][80] = [S' | z | 0]
         float* so2 = nullptr;
@@ -345,11 +367,13 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (p.state_out) so = p.state_out + (int64_t)bh * FM * FV;
           if (p.seg_states) so2 = p.seg_states + ((int64_t)bh * (p.nseg + 1) + p.nseg) * FM * FV;
         }
+        uint32_t rs_[2][32];                    // both halves of the state row in flight at once
+        tmem_ld32_issue(tl + T_ST, rs_[0]);
+        tmem_ld32_issue(tl + T_ST + 32, rs_[1]);
+        tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32_issue(tl + T_ST + half * 32, r);
-          tmem_ld_wait();
+          const uint32_t (&r)[32] = rs_[half];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             uint4 t;
@@ -380,6 +404,7 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         fence_proxy_async();
         tc_fence_before();
+        FSTAMP();
       }
     }
     if (warp < 4) {
@@ -420,6 +445,7 @@ int emo_favor_fwd_tc_launch(const void* q, const void* k, const void* v, int64_t
   Params p;
   p.out = (bf16*)out; p.ld_out = ld_out; p.den_out = den; p.omega = omega; p.state_in = state_in; p.state_out = state_out;
   p.seg_states = seg_states; p.nseg = nseg; p.seg_chunks = sc; p.T = T_; p.H = H; p.items = B * H * nseg; p.omega_f16 = favor_omega_f16();
+  { const char* e = getenv("EMO_FAVOR_DBG_CLK"); p.dbg_clk = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   const int max_ctas = 2 * emo_num_sms();
   const int grid = p.items < max_ctas ? p.items : max_ctas;
   favor_fwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, p);
