@@ -45,6 +45,7 @@ SIGNATURES = {
     "emo_attn_bwd": ([vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, f32, f32,
                       u64, i32, vp], i32),
     "emo_attn_decode_step": ([vp, i64, vp, i64, vp, vp, i64, i32, i32, f32, i32, vp], i32),
+    "emo_relattn_decode_step": ([vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, i64, i32, i32, f32, i32, vp], i32),
     "emo_relattn_fwd": ([vp, vp, vp, i64, i64, vp, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, u64, i32, vp], i32),
     "emo_relattn_bwd": ([vp, vp, vp, i64, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, vp, vp, vp,
                          i32, i32, i32, i32, f32, f32, u64, i32, vp], i32),

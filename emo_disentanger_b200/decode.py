@@ -392,3 +392,175 @@ class Stage2Decoder:
             self.graph_sample = g
         else:
             self.graph = g
+
+
+class Stage1Decoder:
+    """Incremental decode of the stage-1 lead-sheet model (PlainTransformer, Transformer-XL relative positions).
+
+    The reference loop (stage1_compose/inference_utils.py:95-104) feeds one token and the hidden-state memory
+    (n_layer + 1 tensors of the last mem_len layer inputs) to the model, which re-derives LayerNorm + K | V of EVERY
+    memory row in every layer for every generated token (optimus_txl_decoder.py:702-722, 336-367).  K | V of a position
+    never change at inference, so they are cached here; a step is 5 launches per layer on ONE row per sequence (the two
+    LayerNorms ride as prologues of the projections that consume them), the attention kernel reads the last mem_len + 1
+    cache rows and the per-layer table r[distance] = r_net(pos_emb(distance)), and the whole step (+ the sampler) is one
+    CUDA graph.  Same arithmetic as PlainTransformer.generate with its memory (tests/test_decode_gpu.py)."""
+
+    def __init__(self, model, batch=1, max_len=2560, use_graph=True, use_pdl=True):
+        if model.training:
+            raise RuntimeError("decode needs model.eval() (dropout off)")
+        self.m, self.B, self.max_len = model, batch, max_len
+        self.dev, self.dt = model._flat.device, model.compute_dtype
+        self.mem_len = int(model.dec_mem_len)
+        L, d = model.dec_n_layer, model.dec_d_model
+        self.kv = torch.zeros(L, batch, max_len, 2 * d, dtype=self.dt, device=self.dev)
+        self.pos = torch.zeros(batch, dtype=torch.int64, device=self.dev)
+        self.pos_host = [0] * batch
+        self.logits = torch.zeros(batch, model.ldv, dtype=torch.float32, device=self.dev)
+        self.use_graph, self.use_pdl = bool(use_graph), bool(use_pdl)
+        self.graph = None
+        self._sample_graphs = {}          # (temperature, top_p, greedy) -> captured step + sampler graph
+        self._ring = [torch.zeros(2, batch, dtype=torch.int64).pin_memory() for _ in range(8)]
+        self._ring_ev = [None] * 8
+        self._ring_i = 0
+        self._dev_in = torch.zeros(2, batch, dtype=torch.int64, device=self.dev)      # tokens | uniforms (as fp32)
+        self.tok_in = self._dev_in[0]
+        self.u_in = self._dev_in[1].view(torch.float32)[:batch]
+        self._sampled = torch.zeros(2 * batch, dtype=torch.int64, device=self.dev)
+        self._sampled_host = torch.zeros(2 * batch, dtype=torch.int64).pin_memory()
+        self.rtab = None
+
+    def _sync_weights(self):
+        m = self.m
+        key = (m._weights_version(), m._flat.data_ptr())
+        if key == getattr(self, "_wkey", None):
+            return
+        self._wkey = key
+        self.graph = None
+        self._sample_graphs = {}
+        # r[distance] per layer: r_net applied to the sinusoid table; _pos_table(n) lists distances n-1 .. 0
+        Wc = m.weights()
+        M = self.mem_len
+        pos = m._pos_table(M + 1, self.dev).flip(0).contiguous().to(self.dt)          # row = distance
+        L, d = m.dec_n_layer, m.dec_d_model
+        self.rtab = torch.empty(L, M + 1, d, dtype=self.dt, device=self.dev)
+        for l in range(L):
+            ops.linear_fwd(pos, m._wv(Wc, "decoder.layers.%d.dec_attn.r_net.weight" % l), self.rtab[l])
+
+    def reset(self):
+        self.pos.zero_()
+        self.pos_host = [0] * self.B
+
+    def _step_body(self):
+        m = self.m
+        B, d, f, L = self.B, m.dec_d_model, m.dec_d_ff, m.dec_n_layer
+        Wc, Wf = m.weights(), m._flat
+        new = lambda *shape, dtype=self.dt: torch.empty(*shape, dtype=dtype, device=self.dev)
+        h = new(B, d)
+        ops.embed_rows(self.tok_in, None, None, m._wv(Wf, "word_emb.emb_lookup.weight"), None, None, h, d ** 0.5)
+        rw, rr = m._wv(Wf, "decoder.r_w_bias"), m._wv(Wf, "decoder.r_r_bias")
+        scale = 1.0 / (E ** 0.5)
+        for l in range(L):
+            nm = "decoder.layers.%d." % l
+            a, heads = new(B, d), new(B, 3 * d)
+            ops.linear_fwd(h, m._wv(Wc, nm + "dec_attn.qkv_net.weight"), heads,
+                           ln=(m._wv(Wf, nm + "dec_attn.layer_norm.weight"), m._wv(Wf, nm + "dec_attn.layer_norm.bias"), a))
+            att = new(B, d)
+            ops.relattn_decode_step(heads, self.kv[l], self.pos, self.rtab[l], rw, rr, self.mem_len, att, scale)
+            h1 = new(B, d)
+            ops.linear_fwd(att, m._wv(Wc, nm + "dec_attn.o_net.weight"), h1, residual=h, ld_res=d)
+            c, ff = new(B, d), new(B, f)
+            ops.linear_fwd(h1, m._wv(Wc, nm + "pos_ff.CoreNet.0.weight"), ff, bias=m._wv(Wf, nm + "pos_ff.CoreNet.0.bias"),
+                           act=ops.ACT_RELU,
+                           ln=(m._wv(Wf, nm + "pos_ff.layer_norm.weight"), m._wv(Wf, nm + "pos_ff.layer_norm.bias"), c))
+            h = new(B, d)
+            ops.linear_fwd(ff, m._wv(Wc, nm + "pos_ff.CoreNet.3.weight"), h, bias=m._wv(Wf, nm + "pos_ff.CoreNet.3.bias"),
+                           residual=h1, ld_res=d)
+        ops.linear_fwd(h, m._wv(Wc, "dec_out_proj.weight"), self.logits[:, :m.vocab_size], bias=m._wv(Wf, "dec_out_proj.bias"))
+        self.pos.add_(1)
+
+    def _stage_inputs(self, tokens, us):
+        i = self._ring_i
+        self._ring_i = (i + 1) % len(self._ring)
+        if self._ring_ev[i] is not None:
+            self._ring_ev[i].synchronize()
+        host = self._ring[i]
+        for b in range(self.B):
+            host[0, b] = int(tokens[b])
+        if us is not None:
+            hu = host[1].view(torch.float32)
+            for b in range(self.B):
+                hu[b] = float(us[b])
+        self._dev_in.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ring_ev[i] = ev
+
+    def _check_room(self):
+        if max(self.pos_host) + 1 > self.max_len:
+            raise RuntimeError("decode cache holds max_len=%d positions" % self.max_len)
+
+    @torch.no_grad()
+    def step(self, tokens):
+        """tokens: list of B ids (one new token per sequence) -> fp32 logits [B, V] (a view of a static buffer)"""
+        self._sync_weights()
+        self._check_room()
+        self._stage_inputs(tokens, None)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._step_body()
+        for b in range(self.B):
+            self.pos_host[b] += 1
+        return self.logits[:, :self.m.vocab_size]
+
+    @torch.no_grad()
+    def step_sample(self, tokens, us, temperature, top_p, greedy=False):
+        """step() + the device sampler in one CUDA graph -> (ids, status) python lists; self.logits keeps the logits"""
+        if not self.use_graph:
+            raise RuntimeError("step_sample needs the graph path (use_graph=True)")
+        self._sync_weights()
+        self._check_room()
+        cfg = (float(temperature), float(top_p), bool(greedy))
+        if cfg not in self._sample_graphs:            # the loop alternates between two settings (first key draw / the rest)
+            self._capture(cfg)
+        self._stage_inputs(tokens, us if not greedy else [0.0] * self.B)
+        self._sample_graphs[cfg].replay()
+        self._sampled_host.copy_(self._sampled, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        for b in range(self.B):
+            self.pos_host[b] += 1
+        ids = self._sampled_host[:self.B].tolist()
+        st = self._sampled_host[self.B:].view(torch.int32)[:self.B].tolist()
+        return ids, st
+
+    def _capture(self, sample_cfg=None):
+        m = self.m
+        m.weights()
+        pos0 = self.pos.clone()
+        if int(pos0.max()) + 3 > self.max_len:
+            raise RuntimeError("capturing the step needs 3 free cache rows below max_len")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                        # warm-up outside capture; the cache rows it writes lie at / beyond pos
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        from . import _lib
+        _lib.lib().emo_set_pdl(1 if self.use_pdl else 0)
+        try:
+            with torch.cuda.graph(g):
+                self._step_body()
+                if sample_cfg is not None:
+                    t, p, greedy = sample_cfg
+                    ops.sample(self.logits, m.vocab_size, t, p, self.u_in, self._sampled[:self.B],
+                               self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy)
+        finally:
+            _lib.lib().emo_set_pdl(0)
+        self.pos.copy_(pos0)
+        if sample_cfg is not None:
+            self._sample_graphs[sample_cfg] = g
+        else:
+            self.graph = g

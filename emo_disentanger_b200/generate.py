@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .decode import Stage2Decoder
+from .decode import Stage2Decoder, Stage1Decoder
 
 MAX_DEC_INP_LEN = 2048          # stage2_accompaniment/inference.py:19
 
@@ -235,7 +235,10 @@ def match_emotion_key(emotion, key):
 def generate_plain_xl(model, event2idx, idx2event, max_bars=160,
                       max_events=2048, primer=None, temp=1.2, top_p=0.9,
                       prompt_bars=None, representation='functional', key_determine=None,
-                      greedy=False, rng=None, verbose=True):
+                      greedy=False, rng=None, verbose=True, decoder=None, incremental=True):
+    """incremental=True (default): the model call of the reference loop runs through Stage1Decoder (K | V cache, one
+    CUDA graph per token, model step + draw fused) -- the same tokens as feeding the hidden-state memory back through
+    PlainTransformer.generate, which incremental=False still does (inference_utils.py:95-104)."""
     say = print if verbose else (lambda *a, **k: None)
     if primer is None:
         generated = [event2idx['Bar_None']]
@@ -252,18 +255,41 @@ def generate_plain_xl(model, event2idx, idx2event, max_bars=160,
     cur_pos = 0
     failed_cnt = 0
     mems = tuple()
+    dec = decoder
+    if dec is None and incremental:
+        dec = Stage1Decoder(model, batch=1, max_len=max_events + 1024)
+    if dec is not None:
+        dec.reset()
     while generated_bars < target_bars:
-        if steps == 0:
-            dec_input = torch.LongTensor([generated]).to(device)
-            dec_input = dec_input.permute(1, 0) if len(generated) > 1 else dec_input
+        first_key = representation in ['functional', 'key'] and len(generated) == 1
+        t_, p_ = (1.1, 0.97) if first_key else (temp, top_p)
+        predrawn = None
+        if dec is not None:
+            # the reference feeds the whole list while no token has been accepted, the last token afterwards -- also
+            # after a rejected draw: its memory advances by a duplicate row, and so does the cache here
+            feed = generated if steps == 0 else [generated[-1]]
+            for tk in feed[:-1]:
+                dec.step([tk])
+            if dec.use_graph:                                   # model step and draw in one CUDA graph
+                u = 0.0 if greedy else (np.random if rng is None else rng).random_sample()
+                ids, st = dec.step_sample([feed[-1]], [u], t_, p_, greedy=greedy)
+                if st[0] == 1:
+                    raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+                predrawn = ids[0]
+                logits = dec.logits[0:1, :V]
+            else:
+                logits = dec.step([feed[-1]])[0:1]
         else:
-            dec_input = torch.LongTensor([[generated[-1]]]).to(device)
+            if steps == 0:
+                dec_input = torch.LongTensor([generated]).to(device)
+                dec_input = dec_input.permute(1, 0) if len(generated) > 1 else dec_input
+            else:
+                dec_input = torch.LongTensor([[generated[-1]]]).to(device)
+            logits, mems = model.generate(dec_input, mems)         # memory advances even if the draw is rejected
+            logits = logits.float().view(1, -1)
 
-        logits, mems = model.generate(dec_input, mems)         # memory advances even if the draw is rejected
-        logits = logits.float().view(1, -1)
-
-        if representation in ['functional', 'key'] and len(generated) == 1:
-            word = sampler.draw(logits, V, 1.1, 0.97, greedy=greedy, rng=rng)[0]
+        if first_key:
+            word = predrawn if predrawn is not None else sampler.draw(logits, V, 1.1, 0.97, greedy=greedy, rng=rng)[0]
             if key_determine == 'rule':
                 emotion_label = idx2event[generated[0]].split('_')[1]
                 key_event = idx2event[word]
@@ -276,7 +302,7 @@ def generate_plain_xl(model, event2idx, idx2event, max_bars=160,
                     continue
             word_event = idx2event[word]
         else:
-            word = sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
+            word = predrawn if predrawn is not None else sampler.draw(logits, V, temp, top_p, greedy=greedy, rng=rng)[0]
             word_event = idx2event[word]
 
         if 'Key' in word_event:

@@ -313,6 +313,16 @@ def attn_decode_step(qkv, kv_cache, pos, out, scale):
     return out
 
 
+def relattn_decode_step(qkv, kv_cache, pos, rtab, r_w_bias, r_r_bias, mem_len, out, scale):
+    """stage-1 decode: qkv [B, 3*H*64] of the new token, kv_cache [B, cap, 2*H*64], pos int64 [B] (device), rtab
+    [mem_len + 1, H*64] indexed by distance; attends over the last mem_len + 1 positions; out [B, H*64]"""
+    B, cap = kv_cache.shape[0], kv_cache.shape[1]
+    H = kv_cache.shape[2] // 128
+    _call("emo_relattn_decode_step", _p(qkv), qkv.stride(0), _p(kv_cache), cap, _p(pos), _p(rtab), _p(r_w_bias), _p(r_r_bias),
+          int(mem_len), _p(out), out.stride(0), B, H, float(scale), _dt(qkv), _stream())
+    return out
+
+
 def relattn_fwd(q, k, v, r, r_w_bias, r_r_bias, out, lse, scale, drop_p=0.0, seed=0):
     """r [Tk,H,64] (row p = distance Tk-1-p); biases [H,64] fp32."""
     B, Tq, H, E = q.shape

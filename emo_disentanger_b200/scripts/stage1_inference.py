@@ -79,12 +79,14 @@ def main(argv=None):
     model.eval()
     shutil.copy(args.configuration, os.path.join(out_dir, 'config_lead.yaml' if mode == 'lead_sheet' else 'config_full.yaml'))
     gen_times = []
+    from ..decode import Stage1Decoder
+    dec = Stage1Decoder(model, batch=1, max_len=max_dec_len + 1024)      # one K | V cache + step graphs for every piece
     for piece in range(int(args.n_groups)):
         for emotion in emotions:
             out_name = 'samp_{:02d}_{}'.format(piece, emotion)
             gen_words, t_sec = generate_plain_xl(model, event2idx, idx2event, max_events=max_dec_len, max_bars=args.max_bars,
                                                  primer=['Emotion_{}'.format(emotion)], temp=temp, top_p=top_p,
-                                                 representation=rep, key_determine=key_determine)
+                                                 representation=rep, key_determine=key_determine, decoder=dec)
             if gen_words is None:
                 continue
             events = [idx2event[w] for w in gen_words]

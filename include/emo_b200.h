@@ -232,6 +232,13 @@ int emo_attn_decode_step(const void* qkv, int64_t ld_qkv, void* kv_cache, int64_
  * dr [Tk,H,64], d_r_w_bias, d_r_r_bias [H,64] are fp32 and ACCUMULATED (atomics).
  * q [B,Tq,H,64]; k,v [B,Tk,H,64]; r [Tk,H,64] with row p holding distance Tk-1-p (as r_net of
  * pos_emb for pos_seq = Tk-1..0, :792-796); biases [H,64] fp32. */
+/* Decode step of the stage-1 attention (one new token per sequence): K / V of past positions are cached instead of being
+ * re-derived from the hidden-state memory on every step (stage1_compose/inference_utils.py:100-104 -> optimus_txl_decoder
+ * .py:702-722, 336-367); the new token attends over the last mem_len + 1 positions.  rtab [mem_len + 1][H*64] (compute
+ * dtype) = r_net(pos_emb(distance)) of this layer, row = distance; cache [B][cap][2*H*64]; pos int64 [B] on the device. */
+int emo_relattn_decode_step(const void* qkv, int64_t ld_qkv, void* kv_cache, int64_t cap, const int64_t* pos,
+                            const void* rtab, const float* r_w_bias, const float* r_r_bias, int mem_len, void* out,
+                            int64_t ld_out, int B, int H, float scale, int dtype, void* stream);
 int emo_relattn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
                     const void* r, int64_t ld_r, const float* r_w_bias, const float* r_r_bias,
                     void* out, int64_t ld_out, float* lse, int B, int Tq, int Tk, int H,

@@ -162,6 +162,41 @@ def test_stage1_generate_plain_xl_vs_reference_loop():
     assert n >= 20, (n, toks, ref)
 
 
+@pytest.mark.parametrize("dtype,graph", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True)])
+def test_stage1_decoder_equals_generate_with_memory(dtype, graph):
+    """Stage1Decoder (K | V cache, r[distance] table, one launch sequence per token) against PlainTransformer.generate
+    fed with its hidden-state memory, as the reference loop does -- past the point where the memory window (mem_len)
+    starts to slide, for a ragged batch of two sequences"""
+    from emo_disentanger_b200.stage1 import PlainTransformer
+    from emo_disentanger_b200.decode import Stage1Decoder
+    V, L, M = 90, 2, 12
+    m = PlainTransformer(512, V, L, 8, 512, 2048, M, M, pre_lnorm=True, compute_dtype=dtype)
+    sd = PO.seeded_state(TO.txl_state_shapes(V, L), 21, std=0.05)
+    msd = m.state_dict(); msd.update({k: v for k, v in sd.items() if k in msd}); m.load_state_dict(msd)
+    m = m.cuda().eval()
+    gen = torch.Generator().manual_seed(4)
+    tok = torch.randint(0, V - 1, (2, 40), generator=gen)
+    dec = Stage1Decoder(m, batch=2, max_len=64, use_graph=graph)
+    for s_ in range(3):                                      # sequence 0 starts three tokens ahead (ragged positions)
+        dec.pos[1] = 0
+        dec.pos_host[1] = 0
+        dec.step([int(tok[0, s_]), int(tok[1, 0])])
+    dec.pos[1] = 0
+    dec.pos_host[1] = 0
+    mems = [tuple(), tuple()]
+    for b in range(2):                                       # bring the reference memories to the same point
+        for s_ in range(3 if b == 0 else 0):
+            _, mems[b] = m.generate(tok[b, s_:s_ + 1].view(1, 1).cuda(), mems[b])
+    tol = 2e-4 if dtype == torch.float32 else 3e-2
+    for s_ in range(30):                                     # 30 > mem_len: the window slides
+        ids = [int(tok[0, 3 + s_]), int(tok[1, s_])]
+        got = dec.step(ids).clone()
+        for b in range(2):
+            want, mems[b] = m.generate(torch.tensor([[ids[b]]]).cuda(), mems[b])
+            assert rel_err(got[b], want.float()) < tol, (s_, b, rel_err(got[b], want.float()))
+    assert dec.pos_host == [33, 30]
+
+
 @pytest.mark.parametrize("B", [1, 3])
 def test_one_kernel_step_is_bit_identical_to_the_kernel_chain(B):
     """bf16 Performer decode: the cooperative one-kernel step (decode_step.cu) and the chain of embed / GEMV /
