@@ -55,6 +55,7 @@ SIGNATURES = {
     "emo_adam_step": ([vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, vp, f32, f32, i32, vp], i32),
     "emo_cast": ([vp, vp, i64, i32, i32, vp], i32),
     "emo_sample": ([vp, i64, i32, i32, f32, f32, vp, i32, vp, vp, vp, vp], i32),
+    "emo_sample_rows": ([vp, i64, i32, i32, vp, f32, vp, i32, vp, vp, vp, vp], i32),
 }
 
 _lib = None

@@ -12,7 +12,8 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
                                                              float inv_t, float top_p, const float* __restrict__ u,
                                                              int greedy, int64_t* __restrict__ out,
                                                              int32_t* __restrict__ status,
-                                                             const uint8_t* __restrict__ banned) {
+                                                             const uint8_t* __restrict__ banned,
+                                                             const float* __restrict__ t_rows) {
   __shared__ float key[SMP_N];
   __shared__ int idx[SMP_N];
   __shared__ float red[SMP_THREADS / 32];
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(const float* __rest
   const float* row = logits + (int64_t)blockIdx.x * ld;
   pdl_trigger();
   pdl_wait();                       // (no-ops unless launched as a dependent of the decode step, emo_set_pdl)
+  if (t_rows && !greedy) inv_t = 1.f / t_rows[blockIdx.x];      // one temperature per row (a batch of quadrants)
 
   // ---- max / argmax ----
   float mx = -INFINITY;
@@ -190,7 +192,19 @@ extern "C" int emo_sample(const float* logits, int64_t ld, int rows, int V, floa
   EMO_REQUIRE(greedy || (u != nullptr && temperature > 0.f), "emo_sample: sampling needs u and temperature > 0");
   if (rows == 0) return EMO_OK;
   EMO_CHECK_CUDA(emo_launch_dep(sample_kernel, dim3(rows), dim3(SMP_THREADS), 0, (cudaStream_t)stream, logits, ld, V,
-                                greedy ? 1.f : 1.f / temperature, top_p, u, greedy, out, status, banned));
+                                greedy ? 1.f : 1.f / temperature, top_p, u, greedy, out, status, banned, (const float*)nullptr));
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+
+extern "C" int emo_sample_rows(const float* logits, int64_t ld, int rows, int V, const float* temperature_rows, float top_p,
+                               const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned,
+                               void* stream) {
+  EMO_REQUIRE(V > 0 && V <= SMP_N, "emo_sample_rows: V must be in [1, %d]", SMP_N);
+  EMO_REQUIRE(greedy || (u != nullptr && temperature_rows != nullptr), "emo_sample_rows: sampling needs u and the temperatures");
+  if (rows == 0) return EMO_OK;
+  EMO_CHECK_CUDA(emo_launch_dep(sample_kernel, dim3(rows), dim3(SMP_THREADS), 0, (cudaStream_t)stream, logits, ld, V, 1.f, top_p, u,
+                                greedy, out, status, banned, temperature_rows));
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

@@ -343,7 +343,10 @@ class Stage2Decoder:
             raise RuntimeError("decode state is only valid up to max_len=%d positions" % self.max_len)
         # banned: uint8 [B, V] device mask of inadmissible tokens (its ADDRESS is baked into the graph; the caller
         # updates the contents in place)
-        cfg = (float(temperature), float(top_p), bool(greedy), None if banned is None else banned.data_ptr())
+        # temperature: a float, or an fp32 [B] device tensor (one per sequence; its ADDRESS is baked into the graph)
+        tkey = ("rows", temperature.data_ptr()) if torch.is_tensor(temperature) else float(temperature)
+        self._temperature = temperature
+        cfg = (tkey, float(top_p), bool(greedy), None if banned is None else banned.data_ptr())
         self._banned = banned
         if self.graph_sample is None or self.sample_cfg != cfg:
             self.sample_cfg = cfg
@@ -379,7 +382,8 @@ class Stage2Decoder:
             with torch.cuda.graph(g):
                 self._step_body()
                 if with_sampler:
-                    t, p, greedy, _ = self.sample_cfg
+                    _, p, greedy, _ = self.sample_cfg
+                    t = self._temperature
                     ops.sample(self.logits, m.n_token, t, p, self.u_in,
                                self._sampled[:self.B], self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy,
                                banned=self._banned)

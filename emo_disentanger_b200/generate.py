@@ -216,6 +216,126 @@ def generate_conditional(model, event2idx, idx2event, lead_sheet_events, primer,
     return generated[:-1]
 
 
+def _conditional_rules(event2idx, idx2event, lead_sheet_events, primer, max_events, skip_check, max_bars, greedy, say):
+    """The bookkeeping and rejection rules of generate_conditional (stage2_accompaniment/inference.py:231-327) as a
+    coroutine, so that several sequences can share one batched model step: yields ('step', tokens, segs) when the tokens
+    not yet seen by the model must be folded in and a token drawn from the resulting logits, ('redraw',) when the last
+    draw was rejected and another one is wanted from the SAME logits; is sent the drawn token id (-1 = every candidate
+    inadmissible).  Returns the generated list."""
+    generated = primer + [event2idx['Track_LeadSheet']] + lead_sheet_events[0] + [event2idx['Track_Full']]
+    seg_inp = [0 for _ in range(len(generated))]
+    seg_inp[-1] = 1
+    target_bars, generated_bars = len(lead_sheet_events), 0
+    if max_bars is not None:
+        target_bars = min(max_bars, target_bars)
+    fed, cur_pos, failed_cnt = 0, 0, 0
+    while generated_bars < target_bars:
+        if fed < len(generated):
+            word = yield ('step', generated[fed:], seg_inp[fed:])
+            fed = len(generated)
+        else:
+            word = yield ('redraw',)
+        if word < 0:
+            say('[FATAL] model stuck, exiting with generated events ...')
+            return generated
+        word_event = idx2event[word]
+        if not skip_check and 'Beat' in word_event:
+            event_pos = get_position_idx(word_event)
+            if not event_pos >= cur_pos:
+                failed_cnt += 1
+                if failed_cnt >= 256 or greedy:
+                    say('[FATAL] model stuck, exiting with generated events ...')
+                    return generated
+                continue
+            cur_pos, failed_cnt = event_pos, 0
+        if word_event == 'Track_LeadSheet':
+            generated.append(word)
+            seg_inp.append(0)
+            generated_bars += 1
+            if generated_bars < target_bars:
+                generated.extend(lead_sheet_events[generated_bars])
+                seg_inp.extend([0 for _ in range(len(lead_sheet_events[generated_bars]))])
+                generated.append(event2idx['Track_Full'])
+                seg_inp.append(1)
+                cur_pos = 0
+            continue
+        if word_event == 'PAD_None' or (word_event == 'EOS_None' and generated_bars < target_bars - 1):
+            if greedy:
+                say('[FATAL] greedy decode stuck on an inadmissible token')
+                return generated
+            continue
+        elif word_event == 'EOS_None' and generated_bars == target_bars - 1:
+            generated.append(word)
+            break
+        generated.append(word)
+        seg_inp.append(1)
+        if len(generated) > max_events:
+            say('[info] max events reached')
+            break
+    return generated[:-1]
+
+
+def generate_conditional_batch(model, event2idx, idx2event, lead_sheets, primers, temps, top_p=0.9, max_events=10000,
+                               skip_check=False, max_bars=None, greedy=False, decoder=None, rng=None, verbose=True):
+    """Several accompaniments decoded in LOCKSTEP -- e.g. the four emotion quadrants of a lead-sheet pair, which the
+    reference generates one after the other (stage2_accompaniment/inference.py:433-468).  Every sequence keeps its own
+    rule state (the same rules as generate_conditional); one ragged batched model step + device sampler (one temperature
+    per row) serves all of them per iteration, a rejected draw is re-drawn from that row's logits, a lead-sheet bar
+    appended mid-stream is folded into that row's state alone.  Greedy tokens equal generate_conditional's; sampled runs
+    consume the numpy RNG in a different order than four sequential calls.  Returns the list of token lists."""
+    say = print if verbose else (lambda *a, **k: None)
+    n = len(lead_sheets)
+    V = model.n_token
+    dec = decoder if decoder is not None else Stage2Decoder(model, batch=n, max_len=MAX_DEC_INP_LEN)
+    if dec.B != n:
+        raise ValueError("decoder batch %d != number of sequences %d" % (dec.B, n))
+    dec.reset()
+    r = np.random if rng is None else rng
+    sampler = DeviceSampler(dec.dev)
+    t_rows = torch.tensor([float(t) for t in temps], dtype=torch.float32, device=dec.dev)
+    gens = [_conditional_rules(event2idx, idx2event, lead_sheets[b], list(primers[b]), max_events, skip_check, max_bars, greedy, say)
+            for b in range(n)]
+    results = [None] * n
+    req = [None] * n
+
+    def advance(b, word):
+        try:
+            req[b] = gens[b].send(word) if word is not None else next(gens[b])
+        except StopIteration as stop:
+            results[b], req[b] = stop.value, None
+
+    for b in range(n):
+        advance(b, None)
+    last_tok, last_seg = [0] * n, [1] * n
+    while any(q is not None for q in req):
+        # rejected draws first: another draw from the row's own logits, until every live sequence wants a model step
+        for b in range(n):
+            while req[b] is not None and req[b][0] == 'redraw':
+                w = sampler.draw(dec.logits[b:b + 1, :V], V, float(temps[b]), top_p, greedy=greedy, rng=rng)[0]
+                advance(b, w)
+        live = [b for b in range(n) if req[b] is not None]
+        if not live:
+            break
+        if max(dec.pos_host[b] + len(req[b][1]) for b in live) > dec.max_len:
+            raise RuntimeError("sequence longer than the decode state (max_len=%d)" % dec.max_len)
+        for b in live:                          # all but the last pending token of a row: that row's own block
+            toks, segs = req[b][1], req[b][2]
+            if len(toks) > 1:
+                dec.append(b, toks[:-1], segs[:-1])
+            last_tok[b], last_seg[b] = toks[-1], segs[-1]
+        for b in range(n):                      # finished rows idle along: keep their position inside the state's range
+            if req[b] is None and dec.pos_host[b] > dec.max_len - 8:
+                dec.pos[b] = 0
+                dec.pos_host[b] = 0
+        us = [0.0 if greedy else r.random_sample() for _ in range(n)]
+        ids, st = dec.step_sample(last_tok, last_seg, us, t_rows, top_p, greedy=greedy)
+        for b in live:
+            if st[b] == 1:
+                raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+            advance(b, -1 if st[b] == 2 else ids[b])
+    return results
+
+
 # ------------------------------------------------------------------------------------------------------
 # stage 1
 # ------------------------------------------------------------------------------------------------------

@@ -388,6 +388,11 @@ def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False, ban
     rows = logits.shape[0]
     if banned is not None:
         assert banned.dtype == torch.uint8 and banned.shape[-1] == V and banned.is_contiguous()
+    if torch.is_tensor(temperature):                    # fp32 [rows] on the device: one temperature per row
+        assert temperature.dtype == torch.float32 and temperature.numel() >= rows and temperature.is_cuda
+        _call("emo_sample_rows", _p(logits), logits.stride(0), rows, V, _p(temperature), float(top_p), _p(u),
+              1 if greedy else 0, _p(out), _p(status), _p(banned), _stream())
+        return out
     _call("emo_sample", _p(logits), logits.stride(0), rows, V, float(temperature), float(top_p), _p(u),
                                1 if greedy else 0, _p(out), _p(status), _p(banned), _stream())
     return out

@@ -292,6 +292,11 @@ int emo_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype
  * inadmissible. */
 int emo_sample(const float* logits, int64_t ld, int rows, int V, float temperature, float top_p,
                const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned, void* stream);
+/* the same with one temperature per row (fp32 [rows] on the device): a batch of sequences decoded in lockstep with
+ * different settings (the four emotion quadrants of stage2_accompaniment/inference.py:455-462) */
+int emo_sample_rows(const float* logits, int64_t ld, int rows, int V, const float* temperature_rows, float top_p,
+                    const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -162,6 +162,49 @@ def test_stage1_generate_plain_xl_vs_reference_loop():
     assert n >= 20, (n, toks, ref)
 
 
+@pytest.mark.parametrize("kind", ["performer", "gpt2"])
+def test_generate_conditional_batch_lockstep_equals_sequential_greedy(kind):
+    """four accompaniments decoded in lockstep (one ragged batched step + device sampler per iteration, per-row rule state
+    and temperature) give the greedy tokens of four sequential generate_conditional calls; sampled runs obey the rules"""
+    from emo_disentanger_b200.generate import generate_conditional, generate_conditional_batch, get_position_idx
+    from emo_disentanger_b200.decode import Stage2Decoder
+    from emo_disentanger_b200.synth import synthetic_vocab, synthetic_lead_sheet
+    g = golden("decode_small.npz")
+    V, L = int(g["V"]), int(g["L"])
+    e2i, i2e = synthetic_vocab(V, 2)
+    m = _stage2(kind, V, L, 31 if kind == "performer" else 32)
+    om = torch.from_numpy(g["s2_omegas"]) if kind == "performer" else None
+    sheets = [_lead(g), synthetic_lead_sheet(e2i, 3, seed=1), _lead(g), synthetic_lead_sheet(e2i, 2, seed=2)]
+    primers = [[e2i['Emotion_Q%d' % (q + 1)], e2i['Key_C'], e2i['Tempo_110']] for q in range(4)]
+    seq = []
+    dec1 = Stage2Decoder(m, batch=1, omegas=om)
+    for b in range(4):
+        seq.append(generate_conditional(m, e2i, i2e, sheets[b], primers[b], max_events=90, skip_check=True, temp=1.1, top_p=0.99,
+                                        model_type=kind, greedy=True, decoder=dec1, verbose=False))
+    dec4 = Stage2Decoder(m, batch=4, omegas=om)
+    bat = generate_conditional_batch(m, e2i, i2e, sheets, primers, [1.1, 1.2, 1.2, 1.1], top_p=0.99, max_events=90,
+                                     skip_check=True, greedy=True, decoder=dec4, verbose=False)
+    for b in range(4):
+        assert bat[b] == seq[b], b
+    # sampled, rules on: Beat positions never go backwards inside a bar, no PAD
+    rng = np.random.RandomState(5)
+    out = generate_conditional_batch(m, e2i, i2e, sheets, primers, [1.1, 1.2, 1.2, 1.1], top_p=0.9, max_events=90, rng=rng,
+                                     decoder=dec4, verbose=False)
+    for b, toks in enumerate(out):
+        assert toks is not None and len(toks) > len(primers[b]) + len(sheets[b][0]) + 2
+        ev = [i2e[t] for t in toks]
+        assert 'PAD_None' not in ev
+        cur, full = 0, False
+        for e in ev:
+            if e == 'Track_Full':
+                full, cur = True, 0
+            elif e == 'Track_LeadSheet':
+                full = False
+            elif full and 'Beat' in e:
+                assert get_position_idx(e) >= cur
+                cur = get_position_idx(e)
+
+
 @pytest.mark.parametrize("dtype,graph", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True)])
 def test_stage1_decoder_equals_generate_with_memory(dtype, graph):
     """Stage1Decoder (K | V cache, r[distance] table, one launch sequence per token) against PlainTransformer.generate
