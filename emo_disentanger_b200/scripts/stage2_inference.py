@@ -15,7 +15,7 @@ import torch
 import yaml
 
 from ..decode import Stage2Decoder
-from ..generate import generate_conditional
+from ..generate import generate_conditional, generate_conditional_batch
 from ..synth import synthetic_vocab, synthetic_lead_sheet
 from ..data.formats import load_dictionary, read_lead_sheet, lead_sheet_files, emotions_for
 from ..data.midi_out import relative_to_absolute, full_track_bars, events_to_score, write_midi
@@ -49,6 +49,8 @@ def main(argv=None):
     ap.add_argument('-p', '--play_midi', default=False, action='store_true')
     ap.add_argument('--synthetic', type=int, default=0, help='vocabulary size of a synthetic run (no dataset needed)')
     ap.add_argument('--max_bars', type=int, default=MAX_BARS)
+    ap.add_argument('--lockstep', default=False, action='store_true',
+                    help='decode the quadrants of a lead sheet together (one batched model step per iteration)')
     args = ap.parse_args(argv)
     conf = yaml.load(open(args.configuration), Loader=yaml.FullLoader)
     tc, mc = conf['training'], conf['model']
@@ -82,8 +84,28 @@ def main(argv=None):
     print('[# pieces]', len(files))
     dec = Stage2Decoder(model, batch=1)
     n_tok, t0 = 0, time.time()
+    decs = {}
     for file in files:
         out_name = '_'.join(os.path.basename(file).split('_')[:2])
+        if getattr(args, 'lockstep', False):
+            # the quadrants of one lead sheet decoded in lockstep (generate_conditional_batch): same rules per sequence, one
+            # batched model step per iteration; the numpy RNG is consumed in a different order than sequential calls
+            todo = [e for e in emotions_for(file) if not os.path.exists(os.path.join(out_dir, out_name + '_' + e + '_full.txt'))]
+            if todo:
+                key, lead = read_lead_sheet(file, event2idx)
+                primers = [[event2idx['Emotion_{}'.format(e)]] + ([event2idx[key]] if rep == 'functional' else []) +
+                           [event2idx['Tempo_{}'.format(110)]] for e in todo]
+                if len(todo) not in decs:
+                    decs[len(todo)] = Stage2Decoder(model, batch=len(todo))
+                outs = generate_conditional_batch(model, event2idx, idx2event, [lead] * len(todo), primers, [temp] * len(todo),
+                                                  top_p=top_p, max_bars=args.max_bars, decoder=decs[len(todo)])
+                for e, generated in zip(todo, outs):
+                    n_tok += len(generated)
+                    events = [idx2event[w] for w in generated]
+                    with open(os.path.join(out_dir, out_name + '_' + e + '_full.txt'), 'w') as f:
+                        print(*events, sep='\n', file=f)
+                    write_accompaniment_midi(out_dir, out_name + '_' + e + '_full', key, events, rep, args.max_bars)
+            continue
         for e in emotions_for(file):
             out_txt = os.path.join(out_dir, out_name + '_' + e + '_full.txt')
             if os.path.exists(out_txt):
