@@ -39,7 +39,7 @@ class GradSync:
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.overlap = overlap and self.world > 1
+        self.overlap = overlap and self.world > 1 and os.environ.get("EMO_DP_OVERLAP", "1") != "0"    # A/B switch
         self._work = []
         self._ranges = []
         self._comm = None
