@@ -402,6 +402,19 @@ def bench_two_stage_generate(n_bars=8, max_events_s1=400, max_events_s2=700):
     from emo_disentanger_b200.decode import Stage1Decoder, Stage2Decoder
     dec1 = Stage1Decoder(m1, batch=1, max_len=max_events_s1 + 1024)
     dec2 = Stage2Decoder(m2, batch=1)
+    # steady-state rate of the stage-1 decode engine (what the generation loop calls per token): step + sampler graph
+    toks_ = [5]
+    for n_ in (32, 512):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_):
+            toks_, _st = dec1.step_sample(toks_, rng.random_sample(1), 1.2, 0.9)
+        torch.cuda.synchronize()
+        dts = time.perf_counter() - t0
+    out["stage1_decode"] = {"value": 512 / dts, "unit": "tokens/s", "us_per_step": 1e6 * dts / 512,
+                            "api": "Stage1Decoder.step_sample (K | V cache over the last mem_len + 1 = 513 positions, r[distance] "
+                                   "tables, step + sampler in one CUDA graph), batch 1"}
+    dec1.reset()
     n1 = n2 = 0
     t1 = t2 = 0.0
     sheets = {}
@@ -440,7 +453,8 @@ def bench_two_stage_generate(n_bars=8, max_events_s1=400, max_events_s2=700):
     with contextlib.redirect_stdout(devnull):
         outs = generate_conditional_batch(m2, e2, i2, [sheets[emo] for _, emo, _ in quads],
                                           [[e2["Emotion_" + q], e2["Key_C"], e2["Tempo_110"]] for q, _, _ in quads],
-                                          [t for _, _, t in quads], top_p=0.9, max_events=max_events_s2, decoder=dec4)
+                                          [t for _, _, t in quads], top_p=0.9, max_events=max_events_s2, decoder=dec4,
+                                          rng=np.random.RandomState(1234))
     torch.cuda.synchronize()
     t4 = time.perf_counter() - t0
     n4 = sum(len(t) for t in outs if t)
