@@ -183,6 +183,7 @@ struct Params {
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
   int tma_epi;   // bf16 output leaves through the smem-staged TMA store path
   int has_r;     // ... and the residual / aux tile arrives by TMA load (tmR)
+  int aux_store; // gelu_new forward: the pre-activation tile ALSO leaves by TMA store, through tmR (has_r == 0 then)
   int debug;     // perf triage only (emo_gemm_debug): 1 = skip the epilogue body, 2 = skip the MMAs, 4 = skip TMEM loads+math (stores only)
   EpiParams ep;
 };
@@ -392,6 +393,34 @@ __device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t b
   }
 }
 
+// gelu_new forward with its pre-activation kept for the backward (GPT-2 c_fc): one 32-column half of TWO staging
+// buffers -- bufU receives alpha * acc + bias (what aux_out gets), bufG the activation (+ dropout): both leave by TMA store.
+__device__ __forceinline__ void epi_half_tma_aux(const uint32_t (&r)[32], uint32_t bufU, uint32_t bufG, int row, int half,
+                                                 int64_t m, int64_t nb, bool row_ok, const Params& p) {
+  const EpiParams& ep = p.ep;
+  float v[32], a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); a[j] = 0.f; }
+  const int sw = row & 7;
+  const int64_t ms = row_ok ? m : 0;
+  epi_math32<1>(v, a, ms, nb, ep);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 t;
+    t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    sts128(bufU + row * 128 + (((half * 4 + c) ^ sw) << 4), t);
+  }
+  epi_math32<2>(v, a, ms, nb, ep);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 t;
+    t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    sts128(bufG + row * 128 + (((half * 4 + c) ^ sw) << 4), t);
+  }
+}
+
 // Slow path (ragged last columns, unaligned leading dims): per-element, fully guarded.
 template <typename TOut>
 __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t m, int64_t nb, const Params& p) {
@@ -441,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (p.tma_epi) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    if (p.has_r) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    if (p.has_r || p.aux_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(r_bar(w, 0), 1); mbar_init(r_bar(w, 1), 1); }
@@ -615,11 +644,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(r_bar(ew, b), (rphase >> b) & 1u);
             rphase ^= 1u << b;
           } else {
-            if (lane == 0) tma_store_wait_read<1>();   // the store of group g-2 has drained buffer b
+            if (lane == 0) {                           // the store of group g-2 has drained buffer b (aux_store: both buffers)
+              if (p.aux_store) tma_store_wait_read<0>();
+              else tma_store_wait_read<1>();
+            }
             __syncwarp();
           }
           const int64_t m = (int64_t)rowc + lane;
           const bool row_ok = m < p.M;
+          if (p.aux_store) {                           // pre-activation tile -> buffer 0 -> aux_out, activation -> buffer 1 -> C
+            epi_half_tma_aux(r0, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 0, m, col, row_ok, p);
+            epi_half_tma_aux(r1, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 1, m, col + 32, row_ok, p);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmR, mybuf_u32, col, rowc);
+              tma_store_2d(&tmC, mybuf_u32 + EPI_BUF_BYTES, col, rowc);
+            }
+            ++g;
+            continue;
+          }
           if (!(p.debug & 32)) {
             epi_half_tma(r0, buf, lane, 0, m, col, row_ok, p);
             epi_half_tma(r1, buf, lane, 1, m, col + 32, row_ok, p);
@@ -891,10 +935,14 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   const bool need_aux = (ep.act == EMO_ACT_RELU_MASK_BWD || ep.act == EMO_ACT_GELU_NEW_BWD);
   const void* rptr = need_aux ? ep.aux : ep.residual;
   const int64_t rld = need_aux ? ep.ld_aux : ep.ld_res;
+  // gelu_new forward that keeps its pre-activation: a second TMA STORE through the tmR slot (no residual / colsum then)
+  const bool gelu_aux = ep.act == EMO_ACT_GELU_NEW && ep.aux_out;
+  const bool gelu_aux_tma = gelu_aux && !ep.residual && !ep.colsum && (ep.ld_aux % 8 == 0) && al16(ep.aux_out);
   p.tma_epi = (out_dtype == EMO_BF16) && !ep.accumulate && !g_no_tma_epi && (N % 64 == 0) && (ldc % 8 == 0) && al16(C) &&
-              !(need_aux && ep.residual) && !(ep.act == EMO_ACT_GELU_NEW && ep.aux_out) &&
+              !(need_aux && ep.residual) && (!gelu_aux || gelu_aux_tma) &&
               (ep.bias == nullptr || al16(ep.bias)) && (rptr == nullptr || ((rld % 8 == 0) && al16(rptr)));
-  p.has_r = p.tma_epi && rptr != nullptr;
+  p.aux_store = p.tma_epi && gelu_aux;
+  p.has_r = p.tma_epi && rptr != nullptr && !p.aux_store;
   p.debug = g_debug;
   mp.c = mp.a;
   mp.r = mp.a;
@@ -903,6 +951,10 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
     if (rc) return rc;
     if (p.has_r) {
       rc = make_map(&mp.r, rptr, N, M, rld, 32);
+      if (rc) return rc;
+    }
+    if (p.aux_store) {
+      rc = make_map(&mp.r, ep.aux_out, N, M, ep.ld_aux, 32);
       if (rc) return rc;
     }
   }

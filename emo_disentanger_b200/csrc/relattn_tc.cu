@@ -16,7 +16,7 @@
 //              dqv_h = dG_h r_h,  dr_h += dG_h^T qv_h,  and dq = dqw (attention) + dqv; bias gradients = column sums.
 // Position scores travel as bf16 (like every activation of the bf16 path); everything is fp32 inside the kernels.
 // Shapes that do not fit (Tq < 64, Tk % 64, Tq % 32, fp32) stay on attn.cu's mma.sync kernels.
-#include "common.cuh"
+#include "block_gemm.cuh"
 
 struct AttnTcRel { const void* bias; const void* biasT; void* dbiasT; int rel; };
 int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
@@ -139,6 +139,97 @@ __global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict
   }
 }
 
+// Position scores of one 64 x 64 (query, key) tile straight into their shifted place: G = (q + r_r_bias) . band^T over the
+// 127 rows of r the tile can reach (mma.sync, 64 x 128 x 64), then BD[ii][jj] = G[ii][63 - ii + jj] read back from shared
+// memory at a row-dependent offset and stored as 16-byte vectors -- row-major (forward) or transposed (backward).
+// Replaces eight K = 64 GEMMs that wrote G to HBM plus a shifting copy that read it back.  Tiles without a visible pair
+// are skipped: the attention kernels mask those positions before they look at the value.
+struct RelScoreSmem {
+  bf16 qv[64][bg_ld<bf16>(RE)];
+  bf16 rb[128][bg_ld<bf16>(RE)];
+  float g[64][130];
+};
+template <bool TRANS>
+__global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16* __restrict__ q, int64_t ld_q, const float* __restrict__ rrb,
+                                                                      const bf16* __restrict__ r, int64_t ld_r, bf16* __restrict__ outp,
+                                                                      int H, int Tq, int Tk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RelScoreSmem& sm = *reinterpret_cast<RelScoreSmem*>(smem_raw);
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64, off = Tk - Tq;
+  if (j0 > i0 + 63 + off) return;                            // block-uniform: nothing of this tile is visible
+  const int64_t bh = blockIdx.z;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  const int tid = threadIdx.x;
+  for (int t = tid; t < 64 * 8; t += BG_THREADS) {           // q rows + r_r_bias -> bf16
+    const int rr = t >> 3, part = t & 7, i = i0 + rr;
+    Vec<bf16> x;
+    if (i < Tq) x.load(q + ((int64_t)b * Tq + i) * ld_q + h * RE + part * 8);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x.v[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm.qv[rr][part * 8 + e] = from_f<bf16>(x.v[e] + rrb[h * RE + part * 8 + e]);
+  }
+  const int pbase = Tq - i0 - 64 + j0;                       // r row of (ii, jj) is pbase + 63 - ii + jj
+  for (int t = tid; t < 128 * 8; t += BG_THREADS) {
+    const int rr = t >> 3, part = t & 7, pr = pbase + rr;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pr >= 0 && pr < Tk) v = *reinterpret_cast<const uint4*>(r + (int64_t)pr * ld_r + h * RE + part * 8);
+    *reinterpret_cast<uint4*>(&sm.rb[rr][part * 8]) = v;
+  }
+  __syncthreads();
+  {
+    BlockGemm<64, 128, bf16> gg;
+    gg.clear();
+    gg.template mma<true, true>(&sm.qv[0][0], bg_ld<bf16>(RE), &sm.rb[0][0], bg_ld<bf16>(RE), RE);
+    gg.foreach ([&](int r_, int c_, float& x) { sm.g[r_][c_] = x; });
+  }
+  __syncthreads();
+  const int row = tid >> 2, chunk = tid & 3;                 // 64 rows x 4 chunks of 16 elements
+  uint32_t w[8];
+  if (!TRANS) {
+    const int i = i0 + row;
+    if (i >= Tq) return;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int jj = 16 * chunk + 2 * e;
+      const float v0 = (j0 + jj <= i + off) ? sm.g[row][63 - row + jj] : 0.f;
+      const float v1 = (j0 + jj + 1 <= i + off) ? sm.g[row][63 - row + jj + 1] : 0.f;
+      w[e] = pack_bf16x2(v0, v1);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(outp + (bh * Tq + i) * Tk + j0 + 16 * chunk);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+    const int j = j0 + row;
+    if (j >= Tk || i0 + 16 * chunk >= Tq) return;            // (Tq is a multiple of 32: 16-element chunks are all-in or all-out)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ii = 16 * chunk + 2 * e;
+      const float v0 = (j <= i0 + ii + off) ? sm.g[ii][63 - ii + row] : 0.f;
+      const float v1 = (j <= i0 + ii + 1 + off) ? sm.g[ii + 1][62 - ii + row] : 0.f;
+      w[e] = pack_bf16x2(v0, v1);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(outp + (bh * Tk + j) * Tq + i0 + 16 * chunk);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+template <bool TRANS>
+int rel_scores_shift(const void* q, int64_t ld_q, const float* rrb, const void* r, int64_t ld_r, bf16* outp, int B, int Tq, int Tk, int H,
+                     cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(rel_scores_shift_kernel<TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RelScoreSmem)));
+    configured = true;
+  }
+  dim3 grid((Tq + 63) / 64, (Tk + 63) / 64, B * H);
+  rel_scores_shift_kernel<TRANS><<<grid, BG_THREADS, sizeof(RelScoreSmem), s>>>((const bf16*)q, ld_q, rrb, (const bf16*)r, ld_r, outp, H, Tq, Tk);
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
+}
+
 int rel_scores(const bf16* qv, const void* r, int64_t ld_r, bf16* G, int B, int Tq, int Tk, int H, cudaStream_t s) {
   const int d = H * RE;
   for (int h = 0; h < H; ++h) {          // G_h [B*Tq, Tk] = qv_h [B*Tq, 64] . r_h [Tk, 64]^T
@@ -167,8 +258,7 @@ int emo_relattn_fwd_tc_launch(const void* q, const void* k, const void* v, int64
   bf16 *qw = ws, *qv = qw + rows * d, *G = qv + rows * d, *BD = G + nG;
   do {
     rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
-    if ((rc = rel_scores(qv, r, ld_r, G, B, Tq, Tk, H, s))) break;
-    rel_shift_kernel<<<(unsigned)(((int64_t)B * H * Tq * (Tk / 8) + 255) / 256), 256, 0, s>>>(G, BD, B, H, Tq, Tk);
+    if ((rc = rel_scores_shift<false>(q, ld_q, r_r_bias, r, ld_r, BD, B, Tq, Tk, H, s))) break;
     AttnTcRel ex = {BD, nullptr, nullptr, 1};
     rc = emo_attn_fwd_tc_launch_ex(qw, k, v, d, ld_kv, out, ld_out, lse, B, Tq, Tk, H, scale, drop_p, seed, &ex, s);
   } while (0);
@@ -202,9 +292,8 @@ int emo_relattn_bwd_tc_launch(const void* q, const void* k, const void* v, int64
   bf16* dG = G;                                   // G is dead once BD^T exists
   do {
     rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
-    if ((rc = rel_scores(qv, r, ld_r, G, B, Tq, Tk, H, s))) break;
+    if ((rc = rel_scores_shift<true>(q, ld_q, r_r_bias, r, ld_r, BDT, B, Tq, Tk, H, s))) break;
     dim3 tgrid((Tq + 63) / 64, (Tk + 63) / 64, B * H);
-    rel_shift_t_kernel<<<tgrid, 256, 0, s>>>(G, BDT, B, H, Tq, Tk);
     AttnTcRel ex = {nullptr, BDT, dBDT, 1};
     if ((rc = emo_attn_bwd_tc_core(qw, k, v, d, ld_kv, out, dout, ld_out, lse, wf, dk, dv, ld_dkv, B, Tq, Tk, H, scale, drop_p, seed, &ex, s))) break;
     rel_unshift_kernel<<<tgrid, 256, 0, s>>>(dBDT, dG, B, H, Tq, Tk);

@@ -84,6 +84,20 @@ def test_gemm_epilogues_bf16(ops):
     g = 0.5 * pre * (1 + torch.tanh(math.sqrt(2 / math.pi) * (pre + 0.044715 * pre ** 3)))
     assert rms_rel(out.float(), g + res.float()) < 6e-3
     assert rms_rel(aux.float(), pre) < 6e-3
+    # the same without a residual (GPT-2 c_fc): both tiles leave by TMA store; ragged M, and the direct-store path as A/B
+    from emo_disentanger_b200 import _lib
+    for Mr in (M, 300):
+        o1, a1 = (torch.empty(Mr, N, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+        ops.linear_fwd(a[:Mr], w, o1, bias=bias, act=ops.ACT_GELU_NEW, aux_out=a1, ld_aux=N)
+        assert rms_rel(o1.float(), g[:Mr]) < 6e-3 and rms_rel(a1.float(), pre[:Mr]) < 6e-3
+        o2, a2 = torch.empty_like(o1), torch.empty_like(a1)
+        _lib.lib().emo_gemm_direct_epilogue(1)
+        try:
+            ops.linear_fwd(a[:Mr], w, o2, bias=bias, act=ops.ACT_GELU_NEW, aux_out=a2, ld_aux=N)
+        finally:
+            _lib.lib().emo_gemm_direct_epilogue(0)
+        torch.cuda.synchronize()
+        assert torch.equal(o1, o2) and torch.equal(a1, a2)
     # relu-mask backward and gelu backward
     h = _bf(torch.relu(torch.randn(M, N, device=DEV)))
     ops.linear_fwd(a, w, out, act=ops.ACT_RELU_MASK_BWD, aux=h, ld_aux=N, aux_scale=1.25)
