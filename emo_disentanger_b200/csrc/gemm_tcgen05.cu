@@ -216,20 +216,39 @@ __device__ __forceinline__ float gelu_new_grad_fast(float x) {
   const float dt = (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
   return 0.5f * (1.0f + t) + 0.5f * x * dt;
 }
-template <int PART = 0>   // 0 = everything, 1 = linear part only (alpha, rowscale, bias), 2 = activation + dropout only
+// Compile-time feature set of a specialised epilogue.  FEAT < 0: everything is decided at run time (warp-uniform
+// branches).  FEAT >= 0: the bit field below, for the combinations the three models launch at the big shapes -- one
+// kernel carrying every branch needs the whole 168-register budget, and ptxas then schedules ALL of it for minimum
+// register pressure: each element's dependent chain (dropout hash, gelu) runs through one register, and 2 epilogue
+// warps per scheduler cannot hide those latencies (ncu: 0.19 IPC per epilogue warp on the K = 512 shapes).
+constexpr int FEAT_BIAS = 8, FEAT_DROP = 16, FEAT_HAS_R = 32, FEAT_RES = 64, FEAT_COLSUM = 128, FEAT_AUX_STORE = 256;   // bits 0-2: act
+template <int FEAT> struct EF {
+  static constexpr bool G = FEAT < 0;
+  static __device__ __forceinline__ int act(const EpiParams& ep) { return G ? ep.act : (FEAT & 7); }
+  static __device__ __forceinline__ bool linear(const EpiParams& ep) { return G ? true : false; }   // alpha / rowscale
+  static __device__ __forceinline__ bool bias(const EpiParams& ep) { return G ? ep.bias != nullptr : (FEAT & FEAT_BIAS) != 0; }
+  static __device__ __forceinline__ bool drop(const EpiParams& ep) { return G ? ep.drop_thr != 0 : (FEAT & FEAT_DROP) != 0; }
+  static __device__ __forceinline__ bool res(const EpiParams& ep) { return G ? ep.residual != nullptr : (FEAT & FEAT_RES) != 0; }
+  static __device__ __forceinline__ bool colsum(const EpiParams& ep) { return G ? ep.colsum != nullptr : (FEAT & FEAT_COLSUM) != 0; }
+  template <typename P> static __device__ __forceinline__ bool has_r(const P& p) { return G ? p.has_r != 0 : (FEAT & FEAT_HAS_R) != 0; }
+  template <typename P> static __device__ __forceinline__ bool aux_store(const P& p) { return G ? p.aux_store != 0 : (FEAT & FEAT_AUX_STORE) != 0; }
+};
+template <int PART = 0, int FEAT = -1>   // 0 = everything, 1 = linear part only (alpha, rowscale, bias), 2 = activation + dropout only
 __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32], int64_t m, int64_t nb, const EpiParams& ep,
                                            const float4* bpre = nullptr /* bias values already in registers */) {
+  using F = EF<FEAT>;
+  const int act = F::act(ep);
   if (PART != 2) {
-  if (ep.alpha != 1.f) {
+  if (F::linear(ep) && ep.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
   }
-  if (ep.rowscale) {
+  if (F::linear(ep) && ep.rowscale) {
     const float rs = ep.rowscale[m];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= rs;
   }
-  if (ep.bias) {
+  if (F::bias(ep)) {
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + nb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -239,33 +258,46 @@ __device__ __forceinline__ void epi_math32(float (&v)[32], const float (&a)[32],
   }
   }
   if (PART == 1) return;
-  if (ep.act == EMO_ACT_RELU) {
+  if (act == EMO_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (ep.act == EMO_ACT_GELU_NEW) {
+  } else if (act == EMO_ACT_GELU_NEW) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_new_fast(v[j]);
-  } else if (ep.act == EMO_ACT_RELU_MASK_BWD) {
+  } else if (act == EMO_ACT_RELU_MASK_BWD) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (a[j] != 0.f) ? v[j] * ep.aux_scale : 0.f;
-  } else if (ep.act == EMO_ACT_GELU_NEW_BWD) {
+  } else if (act == EMO_ACT_GELU_NEW_BWD) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= gelu_new_grad_fast(a[j]);
   }
-  if (ep.drop_thr) {
+  if (F::drop(ep)) {
     const uint64_t e0 = (uint64_t)(m * ep.n_total + nb);
-    if ((e0 & 1) == 0 && ((e0 >> 33) == ((e0 + 31) >> 33))) {
+    // (specialised kernels only run on the TMA-store path: N % 64 == 0 and nb % 32 == 0, so e0 % 32 == 0 always)
+    if (!F::G || ((e0 & 1) == 0 && ((e0 >> 33) == ((e0 + 31) >> 33)))) {
       // same value as emo_drop_hash(seed, e0 + j): the high half of the pair index is constant here, so the key
       // is hoisted; lane tests are done on the whole word (h >= thr << 16  <=>  (h >> 16) >= thr, and the low
       // lane after a 16-bit shift) -- no field extraction
       const uint32_t key = emo_drop_key(ep.seed, (uint32_t)(e0 >> 33));
       const uint32_t lo0 = (uint32_t)(e0 >> 1);
       const uint32_t thr_hi = ep.drop_thr << 16;
+      // emo_drop_mix for the 16 pairs, written stage by stage: left as one call per pair, ptxas chains every pair's six
+      // dependent integer ops through one register (the epilogue warps then sit in fixed-latency stalls: 2 warps per
+      // scheduler cannot hide them); 16 independent chains per stage issue back to back
+      uint32_t h[16];
+      const uint32_t base = lo0 * 0x9E3779B9u + key;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const uint32_t h = emo_drop_mix(lo0 + (j >> 1), key);
-        v[j] = ((h << 16) >= thr_hi) ? v[j] * ep.keep_scale : 0.f;
-        v[j + 1] = (h >= thr_hi) ? v[j + 1] * ep.keep_scale : 0.f;
+      for (int j = 0; j < 16; ++j) h[j] = base + (uint32_t)j * 0x9E3779B9u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] ^= h[j] >> 15;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] *= 0x2C1B3C6Du;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] ^= h[j] >> 13;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[2 * j] = ((h[j] << 16) >= thr_hi) ? v[2 * j] * ep.keep_scale : 0.f;
+        v[2 * j + 1] = (h[j] >= thr_hi) ? v[2 * j + 1] * ep.keep_scale : 0.f;
       }
     } else {
 #pragma unroll
@@ -362,15 +394,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& t) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
 }
+template <int FEAT>
 __device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t buf, int row, int half,
                                              int64_t m, int64_t nb, bool row_ok, const Params& p) {
+  using F = EF<FEAT>;
   const EpiParams& ep = p.ep;
   float v[32], a[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const uint32_t rowp = buf + row * 128;
   const int sw = row & 7;
-  if (p.has_r) {
+  if (F::has_r(p)) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 t = lds128(rowp + (((half * 4 + c) ^ sw) << 4));
@@ -379,8 +413,8 @@ __device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t b
     }
   }
   const int64_t ms = row_ok ? m : 0;       // rows past M are clipped by the TMA store; keep rowscale in bounds
-  epi_math32(v, a, ms, nb, ep);
-  if (ep.residual) {
+  epi_math32<0, FEAT>(v, a, ms, nb, ep);
+  if (F::res(ep)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += a[j];
   }
@@ -389,12 +423,13 @@ __device__ __forceinline__ void epi_half_tma(const uint32_t (&r)[32], uint32_t b
     uint4 t;
     t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
     t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-    if (!(p.debug & 64)) sts128(rowp + (((half * 4 + c) ^ sw) << 4), t);
+    if (!F::G || !(p.debug & 64)) sts128(rowp + (((half * 4 + c) ^ sw) << 4), t);
   }
 }
 
 // gelu_new forward with its pre-activation kept for the backward (GPT-2 c_fc): one 32-column half of TWO staging
 // buffers -- bufU receives alpha * acc + bias (what aux_out gets), bufG the activation (+ dropout): both leave by TMA store.
+template <int FEAT>
 __device__ __forceinline__ void epi_half_tma_aux(const uint32_t (&r)[32], uint32_t bufU, uint32_t bufG, int row, int half,
                                                  int64_t m, int64_t nb, bool row_ok, const Params& p) {
   const EpiParams& ep = p.ep;
@@ -403,7 +438,7 @@ __device__ __forceinline__ void epi_half_tma_aux(const uint32_t (&r)[32], uint32
   for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); a[j] = 0.f; }
   const int sw = row & 7;
   const int64_t ms = row_ok ? m : 0;
-  epi_math32<1>(v, a, ms, nb, ep);
+  epi_math32<1, FEAT>(v, a, ms, nb, ep);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 t;
@@ -411,7 +446,7 @@ __device__ __forceinline__ void epi_half_tma_aux(const uint32_t (&r)[32], uint32
     t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
     sts128(bufU + row * 128 + (((half * 4 + c) ^ sw) << 4), t);
   }
-  epi_math32<2>(v, a, ms, nb, ep);
+  epi_math32<2, FEAT>(v, a, ms, nb, ep);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 t;
@@ -440,7 +475,7 @@ __device__ __noinline__ void epi_chunk_generic(const uint32_t (&r)[32], int64_t 
 // is what bounds the K = 512 shapes (profiles/).  Each CTA runs its own epilogue on its 128 accumulator rows.
 // TMA_EPI selects the epilogue at compile time (smem-staged TMA store vs direct stores): the two paths have very
 // different register needs, and one kernel carrying both spilled in the hot loop.
-template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI>
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI, int FEAT = -1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> 168 registers / thread at most
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -568,6 +603,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     const EpiParams& ep = p.ep;
+    using F = EF<FEAT>;
     constexpr int VEC = 16 / sizeof(TOut);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool vec_ok = ((p.ldc % VEC) == 0) && al16(p.C) &&
@@ -600,7 +636,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col_ < p.N) return true;
         }
       };
-      if (p.has_r && lane == 0) {       // residual / aux tile of the first group
+      if (F::has_r(p) && lane == 0) {       // residual / aux tile of the first group
         int it0 = unit, c0 = -1;
         if (it0 < items && next_valid(it0, c0)) {
           int col, rowc;
@@ -613,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < ((p.debug & 1) ? 0 : GROUPS); ++c) {
+        for (int c = 0; c < ((F::G && (p.debug & 1)) ? 0 : GROUPS); ++c) {
           int col, rowc;
           coords(it, c, col, rowc);
           if (col >= p.N) continue;   // warp-uniform; N % 64 == 0 on this path
@@ -622,7 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r0[32], r1[32];
           __syncwarp();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + (half * GROUPS + c) * 64;
-          if (p.debug & 4) {
+          if (F::G && (p.debug & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { r0[j] = 0x3f800000u; r1[j] = 0x3f800000u; }
           } else {
@@ -630,7 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32_issue(taddr + 32, r1);
           }
           tmem_ld_wait();
-          if (p.has_r) {
+          if (F::has_r(p)) {
             if (lane == 0) {
               tma_store_wait_read<0>();          // the store of group g-1 has drained buffer b^1
               int itn = it, cn = c;
@@ -645,16 +681,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             rphase ^= 1u << b;
           } else {
             if (lane == 0) {                           // the store of group g-2 has drained buffer b (aux_store: both buffers)
-              if (p.aux_store) tma_store_wait_read<0>();
+              if (F::aux_store(p)) tma_store_wait_read<0>();
               else tma_store_wait_read<1>();
             }
             __syncwarp();
           }
           const int64_t m = (int64_t)rowc + lane;
           const bool row_ok = m < p.M;
-          if (p.aux_store) {                           // pre-activation tile -> buffer 0 -> aux_out, activation -> buffer 1 -> C
-            epi_half_tma_aux(r0, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 0, m, col, row_ok, p);
-            epi_half_tma_aux(r1, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 1, m, col + 32, row_ok, p);
+          if (F::aux_store(p)) {                       // pre-activation tile -> buffer 0 -> aux_out, activation -> buffer 1 -> C
+            epi_half_tma_aux<FEAT>(r0, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 0, m, col, row_ok, p);
+            epi_half_tma_aux<FEAT>(r1, mybuf_u32, mybuf_u32 + EPI_BUF_BYTES, lane, 1, m, col + 32, row_ok, p);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -664,17 +700,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ++g;
             continue;
           }
-          if (!(p.debug & 32)) {
-            epi_half_tma(r0, buf, lane, 0, m, col, row_ok, p);
-            epi_half_tma(r1, buf, lane, 1, m, col + 32, row_ok, p);
+          if (!F::G || !(p.debug & 32)) {
+            epi_half_tma<FEAT>(r0, buf, lane, 0, m, col, row_ok, p);
+            epi_half_tma<FEAT>(r1, buf, lane, 1, m, col + 32, row_ok, p);
           }
-          if (!(p.debug & 16)) fence_proxy_async();
+          if (!F::G || !(p.debug & 16)) fence_proxy_async();
           __syncwarp();
-          if (ep.colsum) {
+          if (F::colsum(ep)) {
             int64_t left = p.M - rowc;
             epi_colsum_staged(buf, lane, left >= 32 ? 32 : (left > 0 ? (int)left : 0), ep.colsum + col);
           }
-          if (lane == 0 && !(p.debug & 8)) tma_store_2d(&tmC, mybuf_u32 + b * EPI_BUF_BYTES, col, rowc);
+          if (lane == 0 && (!F::G || !(p.debug & 8))) tma_store_2d(&tmC, mybuf_u32 + b * EPI_BUF_BYTES, col, rowc);
           ++g;
         }
         tc_fence_before();
@@ -786,12 +822,12 @@ static int make_map_uncached(CUtensorMap* map, const void* ptr, int64_t inner, i
 
 struct Maps { CUtensorMap a, b, c, r; };
 
-template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI>
+template <int BN, bool A_MN, bool B_MN, typename TOut, int CG, bool TMA_EPI, int FEAT = -1>
 static int launch(const Maps& mp, const Params& p, cudaStream_t s) {
   constexpr int STAGES = StageCfg<BN, CG>::STAGES;
   constexpr int smem = STAGES * StageCfg<BN, CG>::STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 512;
   static_assert(smem <= 227 * 1024, "GEMM smem exceeds the CTA limit");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, CG, TMA_EPI>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TOut, CG, TMA_EPI, FEAT>;
   static bool configured = false;
   static int max_units = 0;           // co-resident CTAs (CG 1) or CTA pairs (CG 2)
   if (!configured) {
@@ -843,8 +879,44 @@ static int launch_op(int op, const Maps& mp, const Params& p, cudaStream_t s) {
   return EMO_ERR_ARG;
 }
 
+// Specialised epilogues (EF<FEAT>) for the feature sets the three models launch at training shapes: 256-row CTA-pair
+// tiles, BN = 256, bf16 TMA-store path, alpha == 1, no rowscale.  Anything else takes the run-time kernel.
+static int feat_code(const Params& p) {
+  const EpiParams& ep = p.ep;
+  if (ep.alpha != 1.f || ep.rowscale || p.debug || !p.tma_epi) return -1;
+  return ep.act | (ep.bias ? FEAT_BIAS : 0) | (ep.drop_thr ? FEAT_DROP : 0) | (p.has_r ? FEAT_HAS_R : 0) |
+         (ep.residual ? FEAT_RES : 0) | (ep.colsum ? FEAT_COLSUM : 0) | (p.aux_store ? FEAT_AUX_STORE : 0);
+}
+static int g_no_spec = 0;
+static int launch_spec(int op, const Maps& mp, const Params& p, cudaStream_t s, bool* taken) {
+  *taken = true;
+  const int f = g_no_spec ? -1 : feat_code(p);
+#define EMO_SPEC(OP, A_MN_, B_MN_, CODE) if (op == OP && f == (CODE)) return launch<256, A_MN_, B_MN_, bf16, 2, true, (CODE)>(mp, p, s);
+  // Performer / stage 1: forward NT, dgrad NN
+  EMO_SPEC(EMO_GEMM_NT, false, false, FEAT_BIAS)                                              // qkv
+  EMO_SPEC(EMO_GEMM_NT, false, false, FEAT_BIAS | FEAT_DROP)                                  // out-proj, ffn2
+  EMO_SPEC(EMO_GEMM_NT, false, false, EMO_ACT_RELU | FEAT_BIAS | FEAT_DROP)                   // ffn1
+  EMO_SPEC(EMO_GEMM_NN, false, true, EMO_ACT_RELU_MASK_BWD | FEAT_HAS_R | FEAT_COLSUM)        // dgrad ffn2 (+ linear1 bias gradient)
+  EMO_SPEC(EMO_GEMM_NN, false, true, FEAT_HAS_R | FEAT_RES)                                   // dgrad ffn1 / qkv (+ the other gradient branch)
+  EMO_SPEC(EMO_GEMM_NN, false, true, 0)                                                       // dgrad out-proj
+  // GPT-2 (HF Conv1D weights are [in, out]): forward NN, dgrad NT
+  EMO_SPEC(EMO_GEMM_NN, false, true, FEAT_BIAS)                                               // c_attn
+  EMO_SPEC(EMO_GEMM_NN, false, true, FEAT_BIAS | FEAT_DROP | FEAT_HAS_R | FEAT_RES)           // attn.c_proj, mlp.c_proj
+  EMO_SPEC(EMO_GEMM_NN, false, true, EMO_ACT_GELU_NEW | FEAT_BIAS | FEAT_AUX_STORE)           // c_fc (pre-activation kept)
+  EMO_SPEC(EMO_GEMM_NT, false, false, EMO_ACT_GELU_NEW_BWD | FEAT_HAS_R | FEAT_COLSUM)        // dgrad mlp.c_proj (+ c_fc bias gradient)
+  EMO_SPEC(EMO_GEMM_NT, false, false, 0)                                                      // dgrad c_fc / c_attn / attn.c_proj; stage-1 qkv_net
+#undef EMO_SPEC
+  *taken = false;
+  return EMO_OK;
+}
+
 template <int CG>
 static int launch_any(int op, int BN, int out_dtype, const Maps& mp, const Params& p, cudaStream_t s) {
+  if (CG == 2 && BN == 256 && out_dtype == EMO_BF16 && p.tma_epi) {
+    bool taken;
+    int rc = launch_spec(op, mp, p, s, &taken);
+    if (taken) return rc;
+  }
   if (out_dtype == EMO_BF16) {
     if (p.tma_epi) return BN == 256 ? launch_op<256, bf16, CG, true>(op, mp, p, s) : launch_op<128, bf16, CG, true>(op, mp, p, s);
     return BN == 256 ? launch_op<256, bf16, CG, false>(op, mp, p, s) : launch_op<128, bf16, CG, false>(op, mp, p, s);
@@ -865,6 +937,7 @@ extern "C" void emo_gemm_single_cta(int on) { g_no_pair = on; }   // test / A-B 
 extern "C" void emo_gemm_no_skinny(int on) { g_no_skinny = on; }   // test hook: small-M shapes through the tensor-core kernel
 extern "C" void emo_gemm_debug(int mode) { g_debug = mode; }   // perf triage only; results are wrong when != 0
 extern "C" void emo_gemm_force_simt(int on) { g_force_simt = on; }
+extern "C" void emo_gemm_generic_epilogue(int on) { tc::g_no_spec = on; }   // test / A-B hook: never use a specialised (EF<FEAT>) kernel
 extern "C" void emo_gemm_direct_epilogue(int on) { g_no_tma_epi = on; }   // test / A-B hook: row-per-lane global stores
 
 extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,

@@ -110,6 +110,50 @@ def test_gemm_epilogues_bf16(ops):
     assert rms_rel(out.float(), (a.float() @ w.float().T) * gg) < 6e-3
 
 
+@pytest.mark.parametrize("M", [512, 300])
+def test_gemm_specialised_epilogues_equal_the_generic_kernel(ops, M):
+    """Every compile-time feature set (gemm_tcgen05.cu: EF<FEAT>, launch_spec) against the run-time-branch kernel on the
+    same inputs: bit-identical outputs, column sums to fp32 atomics' order."""
+    from emo_disentanger_b200 import _lib
+    torch.manual_seed(11)
+    d, f = 512, 2048
+    x, hid = _bf(torch.randn(M, d, device=DEV)), _bf(torch.relu(torch.randn(M, f, device=DEV)))
+    w_fd, w_df = _bf(torch.randn(f, d, device=DEV) * 0.05), _bf(torch.randn(d, f, device=DEV) * 0.05)
+    w_dd = _bf(torch.randn(d, d, device=DEV) * 0.05)
+    bd, bfv = torch.randn(d, device=DEV) * 0.1, torch.randn(f, device=DEV) * 0.1
+    res_d, pre_f = _bf(torch.randn(M, d, device=DEV)), _bf(torch.randn(M, f, device=DEV))
+    new = lambda n: torch.empty(M, n, device=DEV, dtype=torch.bfloat16)
+    cases = {
+        "nt bias": lambda o: ops.linear_fwd(x, w_dd, o["c"], bias=bd),
+        "nt bias+drop": lambda o: ops.linear_fwd(x, w_dd, o["c"], bias=bd, drop_p=0.1, seed=5),
+        "nt bias+relu+drop": lambda o: ops.linear_fwd(x, w_fd, o["cf"], bias=bfv, act=ops.ACT_RELU, drop_p=0.1, seed=6),
+        "nn relu-mask+colsum": lambda o: ops.linear_dgrad(x, w_df, o["cf"], act=ops.ACT_RELU_MASK_BWD, aux=hid, ld_aux=f, aux_scale=1 / 0.9, colsum_out=o["sf"]),
+        "nn res": lambda o: ops.linear_dgrad(hid, w_fd, o["c"], residual=res_d, ld_res=d),
+        "nn plain": lambda o: ops.linear_dgrad(x, w_dd, o["c"]),
+        "nn bias (Conv1D fwd)": lambda o: ops.linear_fwd_t(x, w_dd, o["c"], bias=bd),
+        "nn bias+drop+res": lambda o: ops.linear_fwd_t(x, w_dd, o["c"], bias=bd, drop_p=0.1, seed=7, residual=res_d, ld_res=d),
+        "nn bias+gelu+aux store": lambda o: ops.linear_fwd_t(x, w_df, o["cf"], bias=bfv, act=ops.ACT_GELU_NEW, aux_out=o["af"], ld_aux=f),
+        "nt gelu-bwd+colsum": lambda o: ops.linear_dgrad_t(x, w_fd, o["cf"], act=ops.ACT_GELU_NEW_BWD, aux=pre_f, ld_aux=f, colsum_out=o["sf"]),
+        "nt plain": lambda o: ops.linear_dgrad_t(hid, w_df, o["c"]),
+    }
+    for name, fn in cases.items():
+        outs = []
+        for generic in (0, 1):
+            o = {"c": new(d), "cf": new(f), "af": new(f), "sf": torch.zeros(f, device=DEV)}
+            for t in (o["c"], o["cf"], o["af"]):
+                t.zero_()
+            _lib.lib().emo_gemm_generic_epilogue(generic)
+            try:
+                fn(o)
+            finally:
+                _lib.lib().emo_gemm_generic_epilogue(0)
+            torch.cuda.synchronize()
+            outs.append(o)
+        a, b = outs
+        assert torch.equal(a["c"], b["c"]) and torch.equal(a["cf"], b["cf"]) and torch.equal(a["af"], b["af"]), name
+        assert rel_err(a["sf"], b["sf"]) < 1e-5 or float(b["sf"].abs().max()) == 0, name
+
+
 def test_gemm_dropout_epilogue_is_consistent_with_standalone_mask(ops):
     """GEMM-epilogue dropout == emo_dropout_apply with the same seed (what backward re-derives)."""
     torch.manual_seed(4)
