@@ -2,6 +2,7 @@
 // cross-entropy, grad-norm + Adam, casts.  All HBM-bound: 16-byte vector accesses, coalesced rows,
 // grids sized in multiples of the SM count where the kernel is persistent.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 // ---------------------------------------------------------------------------------------------
@@ -344,8 +345,8 @@ extern "C" int emo_ln_res_fwd(const void* x, const void* res, void* sum_out, con
   return ln_fwd_launch(x, res, sum_out, gamma, beta, y, mean, rstd, rows, eps, dtype, (cudaStream_t)stream);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, int DEPTH, int NTH, int MINB>
+__global__ void __launch_bounds__(NTH, MINB) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const T* __restrict__ add_in,
                                                      T* __restrict__ dx, T* __restrict__ dx_drop, uint32_t thr,
@@ -364,11 +365,55 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   for (int j = 0; j < R::NV; ++j)
 #pragma unroll
     for (int i = 0; i < R::N; ++i) { g_[j * R::N + i] = gamma[R::col(j, lane) + i]; dg[j * R::N + i] = 0.f; db[j * R::N + i] = 0.f; dxs[j * R::N + i] = 0.f; }
-  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+  // The next row of every input is requested (as packed 16-byte vectors) before this row is reduced: with 8-16 warps
+  // per SM at 128 registers, one row per warp in flight left the kernel at half of the HBM roofline (latency x
+  // bandwidth needs ~35 KB in flight per SM).  Rows are private to a warp, so dx may still alias dy / add_in.
+  uint4 qd[DEPTH][R::NV], qx[DEPTH][R::NV], qa[DEPTH][R::NV];
+  float mu_n[DEPTH], rs_n[DEPTH];
+  auto fetch = [&](int k, int64_t r) {
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < R::NV; ++j) {
+        qd[k][j] = *reinterpret_cast<const uint4*>(dy + r * LN_D + R::col(j, lane));
+        qx[k][j] = *reinterpret_cast<const uint4*>(x + r * LN_D + R::col(j, lane));
+        if (add_in) qa[k][j] = *reinterpret_cast<const uint4*>(add_in + r * LN_D + R::col(j, lane));
+      }
+      mu_n[k] = mean[r];
+      rs_n[k] = rstd[r];
+    }
+  };
+  auto unpack = [&](const uint4 (&src)[R::NV], R& r) {
+#pragma unroll
+    for (int j = 0; j < R::NV; ++j) {
+      if constexpr (sizeof(T) == 2) {
+        unpack_bf16x2(src[j].x, r.v[j * 8], r.v[j * 8 + 1]); unpack_bf16x2(src[j].y, r.v[j * 8 + 2], r.v[j * 8 + 3]);
+        unpack_bf16x2(src[j].z, r.v[j * 8 + 4], r.v[j * 8 + 5]); unpack_bf16x2(src[j].w, r.v[j * 8 + 6], r.v[j * 8 + 7]);
+      } else {
+        r.v[j * 4] = __uint_as_float(src[j].x); r.v[j * 4 + 1] = __uint_as_float(src[j].y);
+        r.v[j * 4 + 2] = __uint_as_float(src[j].z); r.v[j * 4 + 3] = __uint_as_float(src[j].w);
+      }
+    }
+  };
+  const int64_t wstride = (int64_t)gridDim.x * wpb;
+  int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) fetch(k, row + k * wstride);
+  for (; row < rows; row += wstride) {
     R rdy, rx;
-    rdy.load(dy + row * LN_D, lane);
-    rx.load(x + row * LN_D, lane);
-    float mu = mean[row], rs = rstd[row];
+    uint4 ca[R::NV];                       // add_in of this row stays packed until it is added
+    unpack(qd[0], rdy);
+    unpack(qx[0], rx);
+#pragma unroll
+    for (int j = 0; j < R::NV; ++j) ca[j] = qa[0][j];
+    const float mu = mu_n[0], rs = rs_n[0];
+#pragma unroll
+    for (int k = 0; k + 1 < DEPTH; ++k) {
+#pragma unroll
+      for (int j = 0; j < R::NV; ++j) { qd[k][j] = qd[k + 1][j]; qx[k][j] = qx[k + 1][j]; qa[k][j] = qa[k + 1][j]; }
+      mu_n[k] = mu_n[k + 1];
+      rs_n[k] = rs_n[k + 1];
+    }
+    fetch(DEPTH - 1, row + DEPTH * wstride);
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
@@ -387,7 +432,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int i = 0; i < E; ++i) rdy.v[i] = rs * (rdy.v[i] - c1 - rx.v[i] * c2);
     if (add_in) {
       R ra;
-      ra.load(add_in + row * LN_D, lane);
+      unpack(ca, ra);
 #pragma unroll
       for (int i = 0; i < E; ++i) rdy.v[i] += ra.v[i];
     }
@@ -436,15 +481,18 @@ extern "C" int emo_ln_bwd(const void* dy, const void* x, const float* mean, cons
                           void* stream) {
   EMO_REQUIRE(d == LN_D, "emo_ln_bwd: d must be 512 (got %d)", d);
   if (rows == 0) return EMO_OK;
-  int64_t want = (rows + 7) / 8;
-  int blocks = (int)(want < (int64_t)emo_num_sms() * 4 ? want : (int64_t)emo_num_sms() * 4);
   uint32_t thr = emo_drop_thr(drop_p);
   float ks = 1.f / (1.f - drop_p);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == EMO_BF16)
-    ln_bwd_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)add_in, (bf16*)dx, (bf16*)dx_drop, thr, ks, seed, dgamma, dbeta, dxsum, rows);
-  else
-    ln_bwd_kernel<float><<<blocks, 256, 0, s>>>((const float*)dy, (const float*)x, mean, rstd, gamma, (const float*)add_in, (float*)dx, (float*)dx_drop, thr, ks, seed, dgamma, dbeta, dxsum, rows);
+  // persistent, one wave: 3 resident CTAs of 4 warps per SM at 168 registers (no spills), the next row of every input
+  // in flight per warp.  Measured at 151 552 rows (scripts/ln_perf.py): no prefetch, 2 x 8 warps 165-175 us;
+  // 1 x 8 warps with 3 rows in flight 146 us; 3 x 4 warps with 2 rows in flight 157 us (spills); this one 130 us.
+  const int64_t want = (rows + 3) / 4;
+  int blocks = (int)(want < (int64_t)emo_num_sms() * 3 ? want : (int64_t)emo_num_sms() * 3);
+#define EMO_LN_BWD(T, D, N, B) ln_bwd_kernel<T, D, N, B><<<blocks, N, 0, s>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)add_in, (T*)dx, (T*)dx_drop, thr, ks, seed, dgamma, dbeta, dxsum, rows)
+  if (dtype == EMO_BF16) EMO_LN_BWD(bf16, 1, 128, 3);
+  else EMO_LN_BWD(float, 1, 128, 1);
+#undef EMO_LN_BWD
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

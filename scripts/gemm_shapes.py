@@ -18,9 +18,9 @@ dwqkv, dwo, dw1, dw2 = (torch.zeros(*w.shape, device=dev) for w in (wqkv, wo, w1
 db1 = torch.zeros(f, device=dev)
 cases = [
     ("fwd qkv       NT N=1536 K= 512 bias", 2.0 * M * 1536 * 512, lambda: ops.linear_fwd(x, wqkv, qkv, bias=bq)),
-    ("fwd out-proj  NT N= 512 K= 512 bias+drop+res", 2.0 * M * 512 * 512, lambda: ops.linear_fwd(att, wo, s1, bias=bo, drop_p=0.1, seed=1, residual=x, ld_res=d)),
+    ("fwd out-proj  NT N= 512 K= 512 bias+drop", 2.0 * M * 512 * 512, lambda: ops.linear_fwd(att, wo, s1, bias=bo, drop_p=0.1, seed=1)),
     ("fwd ffn1      NT N=2048 K= 512 bias+relu+drop", 2.0 * M * 2048 * 512, lambda: ops.linear_fwd(y1, w1, h, bias=b1, act=ops.ACT_RELU, drop_p=0.1, seed=2)),
-    ("fwd ffn2      NT N= 512 K=2048 bias+drop+res", 2.0 * M * 2048 * 512, lambda: ops.linear_fwd(hh, w2, s2, bias=b2, drop_p=0.1, seed=3, residual=y1, ld_res=d)),
+    ("fwd ffn2      NT N= 512 K=2048 bias+drop", 2.0 * M * 2048 * 512, lambda: ops.linear_fwd(hh, w2, s2, bias=b2, drop_p=0.1, seed=3)),
     ("dgrad ffn2    NN N=2048 K= 512 relu-mask aux + colsum", 2.0 * M * 2048 * 512, lambda: ops.linear_dgrad(g2, w2, da, act=ops.ACT_RELU_MASK_BWD, aux=hh, ld_aux=f, aux_scale=1 / 0.9, colsum_out=db1)),
     ("dgrad ffn1    NN N= 512 K=2048 res", 2.0 * M * 2048 * 512, lambda: ops.linear_dgrad(da, w1, dy1, residual=g2, ld_res=d)),
     ("dgrad out     NN N= 512 K= 512", 2.0 * M * 512 * 512, lambda: ops.linear_dgrad(g1, wo, datt)),
