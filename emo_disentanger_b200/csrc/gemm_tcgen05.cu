@@ -985,11 +985,23 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   p.kb_total = (int)((K + BK - 1) / BK);
   p.splits = 1;
   if (ep.accumulate) {
-    int tiles = p.m_tiles * p.n_tiles;
-    int want = (2 * (emo_num_sms() / CG) + tiles - 1) / tiles;
-    int maxs = p.kb_total / 8 > 0 ? p.kb_total / 8 : 1;
-    p.splits = want < maxs ? want : maxs;
-    if (p.splits < 1) p.splits = 1;
+    // split-K (wgrad: the reduction runs over the tokens).  The persistent kernel deals items out round-robin, so the
+    // split count is chosen to fill whole waves: minimise waves x (k-blocks per item + the item's fixed cost: pipeline
+    // fill, 256 x BN fp32 atomics) over the candidates.  (16 tiles x 10 splits on 74 CTA pairs was 2.16 waves: a third
+    // of the last wave's time idle; 37 splits is exactly 8 waves.)
+    const int tiles = p.m_tiles * p.n_tiles, units = emo_num_sms() / CG;
+    const int maxs = p.kb_total / 8 > 0 ? p.kb_total / 8 : 1;
+    const int item_overhead_kb = 6;
+    long best_cost = -1;
+    int best = 1;
+    for (int sp = 1; sp <= maxs && sp <= 4 * units; ++sp) {
+      const int kbs = (p.kb_total + sp - 1) / sp;
+      const int real = (p.kb_total + kbs - 1) / kbs;
+      const long waves = ((long)tiles * real + units - 1) / units;
+      const long cost = waves * (kbs + item_overhead_kb);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = real; }
+    }
+    p.splits = best;
   }
   p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
