@@ -56,6 +56,7 @@ SIGNATURES = {
     "emo_cast": ([vp, vp, i64, i32, i32, vp], i32),
     "emo_sample": ([vp, i64, i32, i32, f32, f32, vp, i32, vp, vp, vp, vp], i32),
     "emo_sample_rows": ([vp, i64, i32, i32, vp, f32, vp, i32, vp, vp, vp, vp], i32),
+    "emo_logits_sample": ([vp, i64, vp, vp, vp, i64, vp, i32, i32, i32, vp, i64, f32, vp, f32, vp, i32, vp, vp, vp, vp], i32),
 }
 
 _lib = None

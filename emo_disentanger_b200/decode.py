@@ -16,6 +16,8 @@ redrawn on every call; a recurrent state is only meaningful with the intended, f
 Validity: absolute positions -> state is valid while len(prefix) <= max_len (inference.py:255-257 slides
 the window after that); `generate.py` falls back to full-prefix recompute past that point.
 """
+import os
+
 import torch
 
 from . import ops
@@ -23,6 +25,8 @@ from .stage2.music_performer import MusicPerformer
 from .stage2.music_gpt2 import MusicGPT2
 
 E = 64
+# EMO_FUSED_SAMPLER=0: logits projection and sampler as two nodes of the step graph (A/B switch of emo_logits_sample)
+FUSED_SAMPLER = os.environ.get("EMO_FUSED_SAMPLER", "1") != "0"
 
 
 class Stage2Decoder:
@@ -183,6 +187,14 @@ class Stage2Decoder:
     def _logits_into(self, hid_rows, out_rows, norm=None):
         """norm = (gamma, beta): hid_rows are pre-LayerNorm sums of the last layer (Performer, post-LN)"""
         m = self.m
+        fs = getattr(self, "_fused", None)
+        if fs is not None and out_rows is self.logits:
+            # the step being captured ends in the sampler: projection + draw in ONE launch (emo_logits_sample)
+            ops.logits_sample(hid_rows, m._wv(m.weights(), "dec_out_proj.weight"), m._wv(m._flat, "dec_out_proj.bias"),
+                              self.logits, m.n_token, fs["t"], fs["p"], self.u_in, self._sampled[:self.B],
+                              self._sampled[self.B:].view(torch.int32)[:self.B], greedy=fs["greedy"], banned=fs["banned"],
+                              ln=norm)
+            return
         ln = None
         if norm is not None:
             ln = (norm[0], norm[1], torch.empty(hid_rows.shape[0], m.d_model, dtype=self.dt, device=self.dev))
@@ -380,14 +392,20 @@ class Stage2Decoder:
         _lib.lib().emo_set_pdl(1 if self.use_pdl else 0)    # programmatic dependent launches inside the step graph
         try:
             with torch.cuda.graph(g):
+                fused = (with_sampler and FUSED_SAMPLER and not self.one_kernel and self.dt == torch.bfloat16
+                         and m.d_model == 512)
+                if fused:
+                    _, p, greedy, _ = self.sample_cfg
+                    self._fused = {"t": self._temperature, "p": p, "greedy": greedy, "banned": self._banned}
                 self._step_body()
-                if with_sampler:
+                if with_sampler and not fused:
                     _, p, greedy, _ = self.sample_cfg
                     t = self._temperature
                     ops.sample(self.logits, m.n_token, t, p, self.u_in,
                                self._sampled[:self.B], self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy,
                                banned=self._banned)
         finally:
+            self._fused = None
             _lib.lib().emo_set_pdl(0)
         if state0 is not None:
             self.state.copy_(state0)                  # undo the warm-up / capture-time state advance
@@ -479,7 +497,13 @@ class Stage1Decoder:
             h = new(B, d)
             ops.linear_fwd(ff, m._wv(Wc, nm + "pos_ff.CoreNet.3.weight"), h, bias=m._wv(Wf, nm + "pos_ff.CoreNet.3.bias"),
                            residual=h1, ld_res=d)
-        ops.linear_fwd(h, m._wv(Wc, "dec_out_proj.weight"), self.logits[:, :m.vocab_size], bias=m._wv(Wf, "dec_out_proj.bias"))
+        fs = getattr(self, "_fused", None)
+        if fs is not None:         # the step being captured ends in the sampler: projection + draw in ONE launch
+            ops.logits_sample(h, m._wv(Wc, "dec_out_proj.weight"), m._wv(Wf, "dec_out_proj.bias"), self.logits, m.vocab_size,
+                              fs["t"], fs["p"], self.u_in, self._sampled[:self.B],
+                              self._sampled[self.B:].view(torch.int32)[:self.B], greedy=fs["greedy"])
+        else:
+            ops.linear_fwd(h, m._wv(Wc, "dec_out_proj.weight"), self.logits[:, :m.vocab_size], bias=m._wv(Wf, "dec_out_proj.bias"))
         self.pos.add_(1)
 
     def _stage_inputs(self, tokens, us):
@@ -556,12 +580,17 @@ class Stage1Decoder:
         _lib.lib().emo_set_pdl(1 if self.use_pdl else 0)
         try:
             with torch.cuda.graph(g):
+                fused = sample_cfg is not None and FUSED_SAMPLER and self.dt == torch.bfloat16 and m.dec_d_model == 512
+                if fused:
+                    t, p, greedy = sample_cfg
+                    self._fused = {"t": t, "p": p, "greedy": greedy}
                 self._step_body()
-                if sample_cfg is not None:
+                if sample_cfg is not None and not fused:
                     t, p, greedy = sample_cfg
                     ops.sample(self.logits, m.vocab_size, t, p, self.u_in, self._sampled[:self.B],
                                self._sampled[self.B:].view(torch.int32)[:self.B], greedy=greedy)
         finally:
+            self._fused = None
             _lib.lib().emo_set_pdl(0)
         self.pos.copy_(pos0)
         if sample_cfg is not None:

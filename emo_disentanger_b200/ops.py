@@ -398,6 +398,24 @@ def sample(logits, V, temperature, top_p, u, out, status=None, greedy=False, ban
     return out
 
 
+def logits_sample(x, w, bias, logits, V, temperature, top_p, u, out, status=None, greedy=False, banned=None, ln=None):
+    """Fused logits projection + sampler (emo_logits_sample): logits[:, :V] = LN?(x) . w[:V]^T + bias, then the draw of
+    `sample` from an on-chip copy.  x bf16 [rows, 512]; w bf16 [V, 512]; logits fp32 [rows, ld]; ln = (gamma, beta)."""
+    _need_cuda(x, w, logits)
+    rows = x.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and logits.dtype == torch.float32
+    if banned is not None:
+        assert banned.dtype == torch.uint8 and banned.shape[-1] == V and banned.is_contiguous()
+    t_rows = None
+    if torch.is_tensor(temperature):
+        assert temperature.dtype == torch.float32 and temperature.numel() >= rows and temperature.is_cuda
+        t_rows, temperature = temperature, 1.0
+    _call("emo_logits_sample", _p(x), x.stride(0), _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, _p(w), w.stride(0),
+          _p(bias), rows, V, x.shape[1], _p(logits), logits.stride(0), float(temperature), _p(t_rows), float(top_p), _p(u),
+          1 if greedy else 0, _p(out), _p(status), _p(banned), _stream())
+    return out
+
+
 def performer_decode_step(w_bf16, w_f32, layer_offs, off_tok, off_seg, off_outw, off_outb, pe, omegas, state, tok, seg, pos,
                           scratch, logits, n_layer, batch, n_token, emb_scale):
     """one cooperative kernel = one decode step of the stage-2 Performer (include/emo_b200.h)"""

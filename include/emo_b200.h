@@ -298,6 +298,20 @@ int emo_sample_rows(const float* logits, int64_t ld, int rows, int V, const floa
                     const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned,
                     void* stream);
 
+/* ---- A11/A12 fused: logits projection + sampler of the decode loop ---------------------------
+ * stage2_accompaniment/inference.py:272-276 (`logits = model(...)[-1]` -> `temperature` -> `nucleus`),
+ * stage1_compose/inference_utils.py:66-72.  One launch per generated token: a thread-block cluster per sequence
+ * computes logits[row, :V] = LN?(x[row, :K]) . W[V, K]^T + bias (bf16 operands, fp32 out; K == 512), stores them to
+ * `logits` (fp32 [rows, ld]: the host-side reject-and-redraw loops read them) and draws the token from an on-chip
+ * copy exactly as emo_sample / emo_sample_rows would (same arguments, same status words).  ln_gamma / ln_beta (NULL =
+ * off): LayerNorm of the hidden row first (the post-LN Performer's last norm2, fast_transformer_decoder.py:62-67).
+ * The logits are bit-identical to emo_gemm (NT, rows <= 8) on the same operands, hence so are the greedy tokens.
+ * temperature_rows (NULL = use `temperature`): one temperature per row. */
+int emo_logits_sample(const void* x, int64_t ldx, const float* ln_gamma, const float* ln_beta, const void* W,
+                      int64_t ldw, const float* bias, int rows, int V, int K, float* logits, int64_t ld,
+                      float temperature, const float* temperature_rows, float top_p, const float* u, int greedy,
+                      int64_t* out, int32_t* status, const uint8_t* banned, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -644,6 +644,38 @@ def test_sampler_greedy_is_argmax_bit_exact(ops):
     assert int(out[5]) == 17
 
 
+@pytest.mark.parametrize("rows,V,use_ln", [(1, 329, True), (4, 329, True), (4, 372, False), (1, 216, False), (3, 1000, True)])
+def test_fused_logits_sampler_equals_projection_then_sampler(ops, rows, V, use_ln):
+    """emo_logits_sample (one cluster launch: LayerNorm? -> logits -> draw from the on-chip copy) against the two-kernel
+    path (decode-rows GEMV with its LayerNorm prologue, then emo_sample): bit-identical logits, identical tokens and
+    status words -- sampling, one temperature per row, a grammar mask, and greedy."""
+    torch.manual_seed(40 + rows + V)
+    d, ldv = 512, (V + 7) // 8 * 8
+    x = _bf(torch.randn(rows, d, device=DEV) * 2)
+    w = _bf(torch.randn(V, d, device=DEV) * 0.08)
+    bias = torch.randn(V, device=DEV) * 0.3
+    g, b = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV) * 0.1
+    u = torch.rand(rows, device=DEV)
+    t_rows = torch.tensor([1.1, 1.2, 0.9, 1.3][:rows], device=DEV)
+    banned = (torch.rand(rows, V, device=DEV) < 0.3).to(torch.uint8).contiguous()
+    for mode in ("scalar", "rows", "banned", "greedy"):
+        kw = dict(greedy=mode == "greedy", banned=banned if mode == "banned" else None)
+        temp = t_rows if mode == "rows" else 1.2
+        lg_a = torch.zeros(rows, ldv, device=DEV)
+        ln_out = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16)
+        ops.linear_fwd(x, w, lg_a[:, :V], bias=bias, ln=(g, b, ln_out) if use_ln else None)
+        out_a, st_a = torch.empty(rows, device=DEV, dtype=torch.int64), torch.zeros(rows, device=DEV, dtype=torch.int32)
+        ops.sample(lg_a, V, temp, 0.9, u, out_a, st_a, **kw)
+        lg_b = torch.zeros(rows, ldv, device=DEV)
+        out_b, st_b = torch.empty(rows, device=DEV, dtype=torch.int64), torch.zeros(rows, device=DEV, dtype=torch.int32)
+        ops.logits_sample(x, w, bias, lg_b, V, temp, 0.9, u, out_b, st_b, ln=(g, b) if use_ln else None, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(lg_a, lg_b), mode
+        assert torch.equal(out_a, out_b) and torch.equal(st_a, st_b), mode
+    ref = (torch.nn.functional.layer_norm(x.float(), (d,), g, b).to(torch.bfloat16).float() if use_ln else x.float()) @ w.float().T + bias
+    assert rel_err(lg_b[:, :V], ref) < 2e-5
+
+
 def test_sampler_distribution(ops):
     """empirical frequencies over many uniforms follow the truncated, renormalised distribution."""
     from oracle import sampling_oracle as SO
