@@ -62,6 +62,9 @@ struct Params {
   int rel;
 };
 
+// REL / DROP (0 = none, 1 = one hash per aligned key pair, 2 = per-element hashes: odd Tk or > 2^33 scores) are
+// compile-time: with every variant in one body the kernel sat at the 168-register cap with 216 bytes of spills
+template <bool REL, int DROP>
 __global__ void __launch_bounds__(NT, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ Params p) {
@@ -152,7 +155,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32_issue(tl + T_S + 32 * c, s + 32 * c);
       tmem_ld_wait();
-      if (p.bias) {                             // + position scores of this row (256 contiguous bytes), 32 columns at a time
+      if (REL && p.bias) {                      // + position scores of this row (256 contiguous bytes), 32 columns at a time
         const int ib = i < p.Tq ? i : p.Tq - 1;
         const uint4* brow = reinterpret_cast<const uint4*>(p.bias + ((int64_t)bh * p.Tq + ib) * p.Tk + j0);
 #pragma unroll
@@ -174,10 +177,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      if (p.rel && p.drop_thr) {                // dropped keys leave the softmax
+      if (REL && DROP) {                        // dropped keys leave the softmax
         const uint64_t e0 = ((uint64_t)bh * p.Tq + i) * (uint64_t)p.Tk + j0;
         const DropRow dr = drop_row(p.seed, e0, BN);
-        if (dr.fast) {
+        if (DROP == 1) {
 #pragma unroll
           for (int c = 0; c < 64; ++c) {
             const uint32_t hsh = emo_drop_mix(dr.lo0 + c, dr.key);
@@ -211,50 +214,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         l *= alpha;
         m_used = m_new;
         if (it > 0) {                           // P V(it - 1) is complete (S(it) was committed after it)
-          uint32_t o[64];
-          tmem_ld32_issue(tl + T_O, o);
-          tmem_ld32_issue(tl + T_O + 32, o + 32);
-          tmem_ld_wait();
+          // 16 columns at a time: the 128 scores of the row are live here, and a 64-register copy of O on top of them
+          // spilled (216 bytes of local memory in the hot loop); the rescale itself is rare (lazy, above)
+#pragma unroll 1
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t o[16];
+            tmem_ld16_issue(tl + T_O + 16 * q4, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 64; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st32(tl + T_O, o);
-          tmem_st32(tl + T_O + 32, o + 32);
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(tl + T_O + 16 * q4, o);
+          }
         }
       }
       const float nm = (m_used == -INFINITY) ? 0.f : -m_used;     // every key so far masked / dropped: exp2(-inf + 0) = 0, not NaN
-      uint32_t pk[64];
       float sum0 = 0.f, sum1 = 0.f;
-      if (p.drop_thr == 0 || p.rel) {
+      const uint64_t e0 = ((uint64_t)bh * p.Tq + i) * (uint64_t)p.Tk + j0;
+      const DropRow dr = drop_row(p.seed, e0, BN);
+      (void)dr;
+      // P leaves for tensor memory 32 packed words at a time: the scores die as they are consumed, so the row never
+      // needs more than its 128 score registers
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int cl = 0; cl < 32; ++cl) {
+          const int c = 32 * hf + cl;
           const float p0 = ex2(fmaf(__uint_as_float(s[2 * c]), p.sl2, nm)), p1 = ex2(fmaf(__uint_as_float(s[2 * c + 1]), p.sl2, nm));
           sum0 += p0; sum1 += p1;
-          pk[c] = pack_bf16x2(p0, p1);
-        }
-      } else {
-        const uint64_t e0 = ((uint64_t)bh * p.Tq + i) * (uint64_t)p.Tk + j0;
-        const DropRow dr = drop_row(p.seed, e0, BN);
-        if (dr.fast) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[2 * c]), p.sl2, nm)), p1 = ex2(fmaf(__uint_as_float(s[2 * c + 1]), p.sl2, nm));
-            sum0 += p0; sum1 += p1;
+          if (DROP == 0 || REL) {
+            pk[cl] = pack_bf16x2(p0, p1);
+          } else if (DROP == 1) {
             const uint32_t hsh = emo_drop_mix(dr.lo0 + c, dr.key);
-            pk[c] = pack_bf16x2(((hsh & 0xffffu) >= p.drop_thr) ? p0 * p.keep_scale : 0.f, ((hsh >> 16) >= p.drop_thr) ? p1 * p.keep_scale : 0.f);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[2 * c]), p.sl2, nm)), p1 = ex2(fmaf(__uint_as_float(s[2 * c + 1]), p.sl2, nm));
-            sum0 += p0; sum1 += p1;
-            pk[c] = pack_bf16x2(emo_drop_keep(p.seed, e0 + 2 * c, p.drop_thr) ? p0 * p.keep_scale : 0.f,
-                                emo_drop_keep(p.seed, e0 + 2 * c + 1, p.drop_thr) ? p1 * p.keep_scale : 0.f);
+            pk[cl] = pack_bf16x2(((hsh & 0xffffu) >= p.drop_thr) ? p0 * p.keep_scale : 0.f, ((hsh >> 16) >= p.drop_thr) ? p1 * p.keep_scale : 0.f);
+          } else {
+            pk[cl] = pack_bf16x2(emo_drop_keep(p.seed, e0 + 2 * c, p.drop_thr) ? p0 * p.keep_scale : 0.f,
+                                 emo_drop_keep(p.seed, e0 + 2 * c + 1, p.drop_thr) ? p1 * p.keep_scale : 0.f);
           }
         }
+        tmem_st32(tl + T_S + 32 * hf, pk);
       }
       l += sum0 + sum1;
-      tmem_st32(tl + T_S, pk);
-      tmem_st32(tl + T_S + 32, pk + 32);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -264,7 +264,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     {
       // stage 1: P / (sum P + 1e-8) with sum P = 1, or 0 when every key of the row was dropped
-      const float inv = p.rel ? (l > 0.f ? 1.f / (l * (1.f + 1e-8f)) : 0.f) : 1.f / l;
+      const float inv = REL ? (l > 0.f ? 1.f / (l * (1.f + 1e-8f)) : 0.f) : 1.f / l;
       bf16* orow = p.out + ((int64_t)b * p.Tq + i) * p.ld_o + (int64_t)h * HD;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -693,11 +693,6 @@ int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64
                               cudaStream_t s) {
   using namespace attn3;
   using namespace attn3::fwd;
-  static bool configured = false;
-  if (!configured) {
-    EMO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = tcp::make_map_bt(&mq, q, (int64_t)H * HD, Tq, B, ld_q, BM))) return rc;
@@ -709,7 +704,20 @@ int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64
   p.bias = rel ? (const bf16*)rel->bias : nullptr;
   p.rel = rel ? rel->rel : 0;
   dim3 grid(p.nqt, B * H);
-  attn_fwd_tc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, p);
+  const bool pair_hash = ((Tk & 1) == 0) && ((uint64_t)B * H * (uint64_t)Tq * (uint64_t)Tk + 512 < (1ull << 33));
+  const int drop = p.drop_thr == 0 ? 0 : (pair_hash ? 1 : 2);
+#define EMO_ATTN_FWD(R, D)                                                                                                   \
+  do {                                                                                                                       \
+    static bool configured = false;                                                                                          \
+    if (!configured) {                                                                                                       \
+      EMO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      configured = true;                                                                                                     \
+    }                                                                                                                        \
+    attn_fwd_tc_kernel<R, D><<<grid, NT, SMEM_BYTES, s>>>(mq, mk, mv, p);                                                    \
+  } while (0)
+  if (p.rel) { if (drop == 0) EMO_ATTN_FWD(true, 0); else if (drop == 1) EMO_ATTN_FWD(true, 1); else EMO_ATTN_FWD(true, 2); }
+  else { if (drop == 0) EMO_ATTN_FWD(false, 0); else if (drop == 1) EMO_ATTN_FWD(false, 1); else EMO_ATTN_FWD(false, 2); }
+#undef EMO_ATTN_FWD
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }
