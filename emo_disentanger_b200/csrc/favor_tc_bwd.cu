@@ -27,6 +27,7 @@
 // path.  Four CTA-wide barriers per chunk separate the five MMA batches; inside a phase the workers consume the
 // batch's results in the order the control warp commits them, so tensor-core time hides behind the previous tile.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace favor3b {
 using namespace tcp;
@@ -54,6 +55,7 @@ struct Params {
   const float* seg_states; const float* seg_rstates;
   bf16* dq; bf16* dk; bf16* dv; int64_t ld_d;
   int nseg, seg_chunks, fwd_nseg, ratio, T, H, items;
+  int debug;
 };
 
 template <int ID> __device__ __forceinline__ void named_bar_arrive(int nthreads) {
@@ -216,24 +218,65 @@ __device__ __forceinline__ float dphi_half(uint32_t tp, uint32_t tm, uint32_t ph
   }
   return s0 + s1;
 }
-// columns [32 g, 32 g + 32) of a dx row = acc * ln2 + cx * x  -> global (16-byte stores)
-__device__ __forceinline__ void dx_half_out(uint32_t ta, const uint4 (&xv)[4], bf16* drow, int g, float cx, bool ok) {
+// A warp's 32 half rows (64 bytes each, one per lane) leave through a warp-private 2 KB staging block: written row per
+// lane, read back so that FOUR lanes cover one half row and one store instruction touches 8 lines instead of 32 -- the
+// row-per-lane 16-byte stores of dq / dk / dv kept the load / store unit busy for ~3000 clocks of every 20 000-clock chunk
+// (measured by switching them off: 756 -> 576 us per layer).  Chunk c of row l sits at l * 64 + ((c ^ ((l >> 1) & 3)) << 4):
+// conflict-free both ways.  `base` = element (first row of the warp, column 32 g of the head); rows >= nvalid are skipped.
+__device__ __forceinline__ void warp_rows_out(uint32_t stg, const uint4 (&t)[4], bf16* base, int64_t ld, int lane, int nvalid) {
+  const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) sts128(stg + lane * 64 + (((uint32_t)cc ^ sw) << 4), t[cc]);
+  __syncwarp();
+  const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = 8 * j + sub;
+    const uint4 v = lds128(stg + row * 64 + (((uint32_t)ch ^ (((uint32_t)row >> 1) & 3u)) << 4));
+    if (row < nvalid) *(reinterpret_cast<uint4*>(base + (int64_t)row * ld) + ch) = v;
+  }
+  __syncwarp();
+}
+// The reverse for the q / k half rows the dx epilogues need: requested with the coalesced mapping (lane = (row & 7, chunk)
+// of each group of 8 rows) a phase ahead, turned into "lane = row" through the staging block when they are used.
+__device__ __forceinline__ void warp_rows_in_issue(uint4 (&t)[4], const bf16* base, int64_t ld, int lane, int nvalid) {
+  const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = 8 * j + sub;
+    t[j] = (row < nvalid) ? __ldg(reinterpret_cast<const uint4*>(base + (int64_t)row * ld) + ch) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void warp_rows_in_finish(uint4 (&t)[4], uint32_t stg, int lane) {
+  const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = 8 * j + sub;
+    sts128(stg + row * 64 + (((uint32_t)ch ^ (((uint32_t)row >> 1) & 3u)) << 4), t[j]);
+  }
+  __syncwarp();
+  const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) t[cc] = lds128(stg + lane * 64 + (((uint32_t)cc ^ sw) << 4));
+  __syncwarp();
+}
+// columns [32 g, 32 g + 32) of a dx row = acc * ln2 + cx * x  -> global through the warp's staging block
+__device__ __forceinline__ void dx_half_out(uint32_t ta, const uint4 (&xv)[4], uint32_t stg, bf16* base, int64_t ld, int lane, int nvalid,
+                                            int g, float cx) {
   uint32_t r[32];
   tmem_ld32_issue(ta + g * 32, r);
   tmem_ld_wait();
-  if (ok) {
+  uint4 t[4];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const uint4 xx = xv[cc];
-      float x0, x1;
-      uint4 t;
-      unpack_bf16x2(xx.x, x0, x1); t.x = pack_bf16x2(__uint_as_float(r[8 * cc + 0]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 1]) * KINV + cx * x1);
-      unpack_bf16x2(xx.y, x0, x1); t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 3]) * KINV + cx * x1);
-      unpack_bf16x2(xx.z, x0, x1); t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 5]) * KINV + cx * x1);
-      unpack_bf16x2(xx.w, x0, x1); t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 7]) * KINV + cx * x1);
-      *(reinterpret_cast<uint4*>(drow) + g * 4 + cc) = t;
-    }
+  for (int cc = 0; cc < 4; ++cc) {
+    const uint4 xx = xv[cc];
+    float x0, x1;
+    unpack_bf16x2(xx.x, x0, x1); t[cc].x = pack_bf16x2(__uint_as_float(r[8 * cc + 0]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 1]) * KINV + cx * x1);
+    unpack_bf16x2(xx.y, x0, x1); t[cc].y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 3]) * KINV + cx * x1);
+    unpack_bf16x2(xx.z, x0, x1); t[cc].z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 5]) * KINV + cx * x1);
+    unpack_bf16x2(xx.w, x0, x1); t[cc].w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * KINV + cx * x0, __uint_as_float(r[8 * cc + 7]) * KINV + cx * x1);
   }
+  warp_rows_out(stg, t, base, ld, lane, nvalid);
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -459,6 +502,14 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       } else {
         // =============================== workers: thread (g, r) ===============================
         const bool rowok = r < valid;
+
+        // output staging: S_prev's bf16 tile is dead between batch E1 of this chunk and phase 2 of the next one
+        const uint32_t stg = sSB + (uint32_t)warp * 2048u;
+        const int wrow0 = 32 * wq;                                  // first tile row of this warp
+        const int nvalid_w = (p.debug & 1) ? 0 : (valid - wrow0 < 0 ? 0 : (valid - wrow0 > 32 ? 32 : valid - wrow0));
+        const int64_t obase = (tokbase + t0 + wrow0) * p.ld_d + (int64_t)h * FE + 32 * g;
+        const int64_t ibase = (tokbase + t0 + wrow0) * p.ld + (int64_t)h * FE + 32 * g;
+        const int nvalid_in = (p.debug & 2) ? 0 : (valid - wrow0 < 0 ? 0 : (valid - wrow0 > 32 ? 32 : valid - wrow0));
         const int64_t tok = tokbase + t0 + r;
         // 1 / den of this row, requested before anything waits
         const float den_r = rowok ? __ldg(p.den + tok * p.H + h) : 1.f;
@@ -537,10 +588,7 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         named_bar_sync<1>(NT);                     // [B]
         // ---- phase 3: rz of the next (earlier) chunk; d phi(q) -> dU_q; dv out ----
         uint4 xq4[4];                              // requested a phase ahead of its use
-        if (rowok) {
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) xq4[cc] = __ldg(reinterpret_cast<const uint4*>(p.q + tok * p.ld + (int64_t)h * FE) + g * 4 + cc);
-        }
+        warp_rows_in_issue(xq4, p.q + ibase, p.ld, lane, nvalid_in);
         colsum_partial<256>(sPQ, tid, gd, part);   // sum_i gd_i phi(q_i)
         named_bar_sync<6>(256);
         if (g == 0) rz_nxt[r] = rz_cur[r] + part_total(part, r);
@@ -557,31 +605,26 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint32_t v[32];
           tmem_ld32_issue(tl + T_W2 + 64 + g * 32, v);
           tmem_ld_wait();
-          if (rowok) {
-            bf16* drow = p.dv + tok * p.ld_d + (int64_t)h * FE;
+          uint4 t[4];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              uint4 t;
-              t.x = pack_bf16x2(__uint_as_float(v[8 * cc]), __uint_as_float(v[8 * cc + 1]));
-              t.y = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
-              t.z = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
-              t.w = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
-              *(reinterpret_cast<uint4*>(drow) + g * 4 + cc) = t;
-            }
+          for (int cc = 0; cc < 4; ++cc) {
+            t[cc].x = pack_bf16x2(__uint_as_float(v[8 * cc]), __uint_as_float(v[8 * cc + 1]));
+            t[cc].y = pack_bf16x2(__uint_as_float(v[8 * cc + 2]), __uint_as_float(v[8 * cc + 3]));
+            t[cc].z = pack_bf16x2(__uint_as_float(v[8 * cc + 4]), __uint_as_float(v[8 * cc + 5]));
+            t[cc].w = pack_bf16x2(__uint_as_float(v[8 * cc + 6]), __uint_as_float(v[8 * cc + 7]));
           }
+          warp_rows_out(stg, t, p.dv + obase, p.ld_d, lane, nvalid_w);
         }
         tmem_st_wait();
         tc_fence_before();
         named_bar_sync<1>(NT);                     // [C]
         // ---- phase 4: dq out; d phi(k) -> dU_k; R -> bf16 smem ----
         uint4 xk4[4];
-        if (rowok) {
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) xk4[cc] = __ldg(reinterpret_cast<const uint4*>(p.k + tok * p.ld + (int64_t)h * FE) + g * 4 + cc);
-        }
+        warp_rows_in_issue(xk4, p.k + ibase, p.ld, lane, nvalid_in);
         mbar_wait(bar(M_DXQ), cph);
         tc_fence_after();
-        dx_half_out(tl + T_W2 + 64, xq4, p.dq + tok * p.ld_d + (int64_t)h * FE, g, -(sp[r] + sp[128 + r]) * F_S2, rowok);
+        warp_rows_in_finish(xq4, stg, lane);
+        dx_half_out(tl + T_W2 + 64, xq4, stg, p.dq + obase, p.ld_d, lane, nvalid_w, g, -(sp[r] + sp[128 + r]) * F_S2);
         {
           uint32_t du[16];
           mbar_wait(bar(M_G), cph);
@@ -604,7 +647,8 @@ favor_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- phase 5: dk out ----
         mbar_wait(bar(M_DXK), cph);
         tc_fence_after();
-        dx_half_out(tl + T_W0 + 64, xk4, p.dk + tok * p.ld_d + (int64_t)h * FE, g, -(sp[256 + r] + sp[384 + r]) * F_S2, rowok);
+        warp_rows_in_finish(xk4, stg, lane);
+        dx_half_out(tl + T_W0 + 64, xk4, stg, p.dk + obase, p.ld_d, lane, nvalid_w, g, -(sp[256 + r] + sp[384 + r]) * F_S2);
         tc_fence_before();
       }
     }
@@ -644,6 +688,7 @@ int emo_favor_bwd_tc_launch(const void* q, const void* k, const void* v, int64_t
   Params p;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.ld = ld; p.omega = omega; p.den = den; p.seg_states = seg_states;
   p.seg_rstates = seg_rstates; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.ld_d = ld_d;
+  { const char* e = getenv("EMO_FAVOR_BWD_DBG"); p.debug = e ? atoi(e) : 0; }
   p.nseg = nseg; p.seg_chunks = sc; p.fwd_nseg = fwd_nseg; p.ratio = ratio; p.T = T_; p.H = H; p.items = B * H * nseg;
   const int sms = emo_num_sms();
   const int grid = p.items < sms ? p.items : sms;
