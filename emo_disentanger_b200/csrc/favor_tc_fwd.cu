@@ -337,26 +337,40 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         {
           const float inv = 1.f / den;
-          bf16* orow = p.out + ((int64_t)b * p.T + t0 + i) * p.ld_out + (int64_t)h * FE;
           uint32_t ro[2][32];                   // both halves of O in flight at once
           tmem_ld32_issue(tl + T_O, ro[0]);
           tmem_ld32_issue(tl + T_O + 32, ro[1]);
           tmem_ld_wait();
+          // The 32 output rows of this warp (128 bytes each) leave through the warp's OWN rows of the phi(k) tile (dead
+          // since batch 3 completed; only this warp ever writes them): row per lane in, 8 lanes per row out, so that
+          // a store instruction touches 4 lines instead of 32 (the load / store unit is shared by the SM's two CTAs).
+          const uint32_t stg = sPK + (uint32_t)warp * 4096u;
+          const int lane = tid & 31;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const uint32_t (&r)[32] = ro[half];
-            if (rowok) {
 #pragma unroll
-              for (int cc = 0; cc < 4; ++cc) {
-                uint4 t;
-                t.x = pack_bf16x2(__uint_as_float(r[8 * cc]) * inv, __uint_as_float(r[8 * cc + 1]) * inv);
-                t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * inv, __uint_as_float(r[8 * cc + 3]) * inv);
-                t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * inv, __uint_as_float(r[8 * cc + 5]) * inv);
-                t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * inv, __uint_as_float(r[8 * cc + 7]) * inv);
-                *reinterpret_cast<uint4*>(orow + half * 32 + cc * 8) = t;
-              }
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 t;
+              t.x = pack_bf16x2(__uint_as_float(r[8 * cc]) * inv, __uint_as_float(r[8 * cc + 1]) * inv);
+              t.y = pack_bf16x2(__uint_as_float(r[8 * cc + 2]) * inv, __uint_as_float(r[8 * cc + 3]) * inv);
+              t.z = pack_bf16x2(__uint_as_float(r[8 * cc + 4]) * inv, __uint_as_float(r[8 * cc + 5]) * inv);
+              t.w = pack_bf16x2(__uint_as_float(r[8 * cc + 6]) * inv, __uint_as_float(r[8 * cc + 7]) * inv);
+              sts128(stg + sw128(lane, half * 4 + cc), t);
             }
           }
+          __syncwarp();
+          {
+            const int sub = lane >> 3, ch = lane & 7, nv = valid - 32 * warp;
+            bf16* obase = p.out + ((int64_t)b * p.T + t0 + 32 * warp) * p.ld_out + (int64_t)h * FE;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int row = 4 * j + sub;
+              const uint4 t = lds128(stg + sw128(row, ch));
+              if (row < nv) *(reinterpret_cast<uint4*>(obase + (int64_t)row * p.ld_out) + ch) = t;
+            }
+          }
+          __syncwarp();
           if (p.den_out && rowok) p.den_out[((int64_t)b * p.T + t0 + i) * p.H + h] = den;
         }
         FSTAMP();
