@@ -155,14 +155,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32_issue(tl + T_S + 32 * c, s + 32 * c);
       tmem_ld_wait();
-      if (REL && p.bias) {                      // + position scores of this row (256 contiguous bytes), 32 columns at a time
-        const int ib = i < p.Tq ? i : p.Tq - 1;
-        const uint4* brow = reinterpret_cast<const uint4*>(p.bias + ((int64_t)bh * p.Tq + ib) * p.Tk + j0);
+      if (REL && p.bias) {                      // + position scores of this row, 32 columns at a time
+        // blocked plane (relattn_tc.cu, rel_blocked_off): chunk c of the warp's 32 rows is 512 contiguous bytes, so a load
+        // instruction touches 4 lines (row-major rows made it 32: the LSU, shared by the SM's two CTAs, was the bound)
+        const int nct = (p.Tk + BN - 1) / BN;
+        const uint4* bblk = reinterpret_cast<const uint4*>(p.bias + (((int64_t)bh * p.nqt + qt) * nct + it) * (int64_t)(BM * BN)) +
+                            (warp * 16) * 32 + lane;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           uint4 bb[4];
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) bb[k4] = __ldg(brow + 4 * c4 + k4);
+          for (int k4 = 0; k4 < 4; ++k4) bb[k4] = __ldg(bblk + (4 * c4 + k4) * 32);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint32_t w[4] = {bb[k4].x, bb[k4].y, bb[k4].z, bb[k4].w};
@@ -530,12 +533,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int cmin = j - off - i0 - 32 * ch;               // column c (query i0 + 32 ch + c) sees key j iff c >= cmin
       const uint64_t e_base = ((uint64_t)bh * p.Tq + (uint64_t)(i0 + 32 * ch)) * (uint64_t)p.Tk + (uint64_t)j;   // mask index of column 0
       const uint32_t pbase = (uint32_t)(e_base >> 1);
-      const int64_t boff = ((int64_t)bh * p.Tk + (j < p.Tk ? j : p.Tk - 1)) * p.Tq + i0 + 32 * ch;   // biasT / dbiasT: 32 queries of key row j
+      // biasT / dbiasT: the 32 queries [i0 + 32 ch, + 32) of key row j, as chunks 4 ch .. 4 ch + 3 of row r of block (key tile,
+      // query tile) of the blocked plane (relattn_tc.cu): 512 contiguous bytes per warp and chunk
+      const int nqt_all = (p.Tq + BM - 1) / BM;
+      const int64_t boff = (((int64_t)bh * ((p.Tk + BN - 1) / BN) + j0 / BN) * nqt_all + (qt0 + it)) * (int64_t)(BM * BN) +
+                           ((int64_t)((quad * 16 + 4 * ch) * 32 + lane) << 3);
       if (p.biasT) {
         const uint4* brow = reinterpret_cast<const uint4*>(p.biasT + boff);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint4 bb = __ldg(brow + k4);
+          const uint4 bb = __ldg(brow + k4 * 32);
           const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -563,7 +570,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (p.dbiasT && j < p.Tk && i0 + 32 * ch < p.Tq) {     // d(position scores)^T = dS^T: 64 contiguous bytes per thread (Tq % 32 == 0)
         uint4* drow = reinterpret_cast<uint4*>(p.dbiasT + boff);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) drow[k4] = make_uint4(dsk[4 * k4], dsk[4 * k4 + 1], dsk[4 * k4 + 2], dsk[4 * k4 + 3]);
+        for (int k4 = 0; k4 < 4; ++k4) drow[k4 * 32] = make_uint4(dsk[4 * k4], dsk[4 * k4 + 1], dsk[4 * k4 + 2], dsk[4 * k4 + 3]);
       }
       if (it > 0) {                                          // products of tile it - 1 are complete: P^T / dS^T / dQ may be reused
         mbar_wait(bar_acc, (it - 1) & 1);

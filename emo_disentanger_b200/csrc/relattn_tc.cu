@@ -7,11 +7,12 @@
 // score tile needs G[i][Tq - 1 - i + j], a per-ROW column shift.  A tcgen05.ld addresses the same columns for all 32
 // lanes of a warp and an MMA cannot produce the shifted tile directly (no operand depends on i alone or j alone), so
 // the shift is done by ADDRESSING in HBM instead of in registers:
-//   forward    qw = q + r_w_bias, qv = q + r_r_bias                              (one element-wise pass)
-//              G_h [B*Tq, Tk] = qv_h r_h^T   for the 8 heads                    (tcgen05 GEMM, K = 64)
-//              BD [B*H][Tq][Tk] = shifted G                                      (row-wise copy at a row-dependent offset)
+//   forward    qw = q + r_w_bias                                                 (one element-wise pass)
+//              BD (queries x keys, blocked planes) = shifted (q + r_r_bias) r^T  (rel_scores_shift_kernel: per 64 x 64
+//                                                                                 tile one mma.sync product over the 127
+//                                                                                 reachable rows of r, stored shifted)
 //              attention forward with BD as an additive score tile               (attn_fwd_tc_kernel, rel mode)
-//   backward   G, BD^T [B*H][Tk][Tq] re-made (cheaper than keeping 0.5 GB per layer alive), attention backward adds
+//   backward   BD^T (keys x queries) re-made (cheaper than keeping 0.5 GB per layer alive), attention backward adds
 //              BD^T to K Q^T and writes dS^T next to it; dG = un-shifted, transposed dS^T; then three GEMM families:
 //              dqv_h = dG_h r_h,  dr_h += dG_h^T qv_h,  and dq = dqw (attention) + dqv; bias gradients = column sums.
 // Position scores travel as bf16 (like every activation of the bf16 path); everything is fp32 inside the kernels.
@@ -19,6 +20,19 @@
 #include "block_gemm.cuh"
 
 struct AttnTcRel { const void* bias; const void* biasT; void* dbiasT; int rel; };
+// Layout of the bf16 score planes handed to / received from the attention kernels (BD: rows = queries, columns = keys;
+// BD^T and dBD^T: rows = keys, columns = queries): per (batch x head) a grid of 128 x 128 blocks, and inside a block the
+// 16-byte chunk (8 columns) c of row r sits at ((r / 32 * 16 + c) * 32 + r % 32) * 16 bytes -- the 32 rows a warp of the
+// attention kernels owns are contiguous for every chunk, so each of its load / store instructions touches 4 lines.  With
+// row-major planes (one row per lane) every instruction touched 32 lines and the kernels were bound by the load / store
+// unit in rel mode.
+__host__ __device__ __forceinline__ int64_t rel_plane_elems(int rows, int cols) {
+  return (int64_t)((rows + 127) / 128) * ((cols + 127) / 128) * 16384;
+}
+__device__ __forceinline__ int64_t rel_blocked_off(int row, int col, int cols) {
+  const int nct = (cols + 127) >> 7, rr = row & 127, cc = col & 127;
+  return ((int64_t)(row >> 7) * nct + (col >> 7)) * 16384 + (((rr >> 5) * 16 + (cc >> 3)) * 32 + (rr & 31)) * 8 + (cc & 7);
+}
 int emo_attn_fwd_tc_launch_ex(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out, int64_t ld_o,
                               float* lse, int B, int Tq, int Tk, int H, float scale, float drop_p, uint64_t seed, const AttnTcRel* rel,
                               cudaStream_t s);
@@ -48,64 +62,6 @@ __global__ void rel_prep_kernel(const bf16* __restrict__ q, int64_t ld_q, const 
   b.store(qv + row * d + c);
 }
 
-// BD[bh][i][j] = G[h][b*Tq + i][Tq - 1 - i + j] for the visible keys (j <= i + off), 0 elsewhere.  8 keys per thread.
-__global__ void rel_shift_kernel(const bf16* __restrict__ G, bf16* __restrict__ BD, int B, int H, int Tq, int Tk) {
-  const int vpr = Tk / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * H * Tq * vpr;
-  if (idx >= total) return;
-  const int j0 = (int)(idx % vpr) * 8;
-  const int64_t row = idx / vpr;                 // (b*H + h)*Tq + i
-  const int i = (int)(row % Tq);
-  const int64_t bh = row / Tq;
-  const int b = (int)(bh / H), h = (int)(bh % H);
-  const int off = Tk - Tq;
-  const bf16* g = G + ((int64_t)h * B * Tq + (int64_t)b * Tq + i) * Tk + (Tq - 1 - i);
-  Vec<bf16> o;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int j = j0 + e;
-    o.v[e] = (j <= i + off) ? to_f(g[j]) : 0.f;
-  }
-  o.store(BD + row * Tk + j0);
-}
-
-// BDT[bh][j][i] = G[h][b*Tq + i][Tq - 1 - i + j] (visible pairs; 0 elsewhere): 64 x 64 tiles through shared memory, raw
-// 16-bit moves (no conversion); a warp reads one query row (128 contiguous bytes at a row-dependent offset) and writes
-// one key row (128 contiguous bytes)
-__global__ void __launch_bounds__(256) rel_shift_t_kernel(const bf16* __restrict__ G, bf16* __restrict__ BDT, int B, int H, int Tq, int Tk) {
-  __shared__ unsigned short tile[64][66];
-  const unsigned short* g16 = reinterpret_cast<const unsigned short*>(G);
-  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
-  const int64_t bh = blockIdx.z;
-  const int b = (int)(bh / H), h = (int)(bh % H);
-  const int off = Tk - Tq;
-  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const unsigned short* gb = g16 + ((int64_t)h * B * Tq + (int64_t)b * Tq) * Tk;
-#pragma unroll
-  for (int ii = w; ii < 64; ii += 8) {
-    const int i = i0 + ii;
-    const unsigned short* row = gb + (int64_t)i * Tk + (Tq - 1 - i) + j0;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int jj = tx + 32 * hh, j = j0 + jj;
-      unsigned short v = 0;
-      if (i < Tq && j < Tk && j <= i + off) v = __ldg(row + jj);
-      tile[ii][jj] = v;
-    }
-  }
-  __syncthreads();
-  if (i0 + 2 * tx >= Tq) return;                 // Tq is even (a multiple of 32)
-#pragma unroll
-  for (int jj = w; jj < 64; jj += 8) {
-    const int j = j0 + jj;
-    if (j < Tk) {
-      const uint32_t v = (uint32_t)tile[2 * tx][jj] | ((uint32_t)tile[2 * tx + 1][jj] << 16);
-      *reinterpret_cast<uint32_t*>(BDT + (bh * Tk + j) * Tq + i0 + 2 * tx) = v;
-    }
-  }
-}
-
 // dG[h][b*Tq + i][t] = dBDT[bh][j][i] with j = t - (Tq - 1) + i when 0 <= j <= min(i + off, Tk - 1), else 0.
 // Output tile 64 (i) x 64 (t); its sources are 127 rows j of 64 consecutive i.
 __global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict__ dBDT, bf16* __restrict__ dG, int B, int H, int Tq, int Tk) {
@@ -120,7 +76,7 @@ __global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict
     const int j = jmin + jr, i = i0 + 2 * tx;
     uint32_t v = 0;
     if (j >= 0 && j < Tk && i < Tq) {
-      v = __ldg(reinterpret_cast<const uint32_t*>(dBDT + (bh * Tk + j) * Tq + i));
+      v = __ldg(reinterpret_cast<const uint32_t*>(dBDT + bh * rel_plane_elems(Tk, Tq) + rel_blocked_off(j, i, Tq)));
       if (j > i + 1 + off) v = 0;                // both queries of the pair are before the key
       else if (j == i + 1 + off) v &= 0xffff0000u;     // only the second query of the pair sees the key
     }
@@ -198,9 +154,9 @@ __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16
       const float v1 = (j0 + jj + 1 <= i + off) ? sm.g[row][63 - row + jj + 1] : 0.f;
       w[e] = pack_bf16x2(v0, v1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(outp + (bh * Tq + i) * Tk + j0 + 16 * chunk);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    bf16* plane = outp + bh * rel_plane_elems(Tq, Tk);
+    *reinterpret_cast<uint4*>(plane + rel_blocked_off(i, j0 + 16 * chunk, Tk)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(plane + rel_blocked_off(i, j0 + 16 * chunk + 8, Tk)) = make_uint4(w[4], w[5], w[6], w[7]);
   } else {
     const int j = j0 + row;
     if (j >= Tk || i0 + 16 * chunk >= Tq) return;            // (Tq is a multiple of 32: 16-element chunks are all-in or all-out)
@@ -211,9 +167,9 @@ __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16
       const float v1 = (j <= i0 + ii + 1 + off) ? sm.g[ii + 1][62 - ii + row] : 0.f;
       w[e] = pack_bf16x2(v0, v1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(outp + (bh * Tk + j) * Tq + i0 + 16 * chunk);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    bf16* plane = outp + bh * rel_plane_elems(Tk, Tq);
+    *reinterpret_cast<uint4*>(plane + rel_blocked_off(j, i0 + 16 * chunk, Tq)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(plane + rel_blocked_off(j, i0 + 16 * chunk + 8, Tq)) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 template <bool TRANS>
@@ -230,15 +186,6 @@ int rel_scores_shift(const void* q, int64_t ld_q, const float* rrb, const void* 
   return EMO_OK;
 }
 
-int rel_scores(const bf16* qv, const void* r, int64_t ld_r, bf16* G, int B, int Tq, int Tk, int H, cudaStream_t s) {
-  const int d = H * RE;
-  for (int h = 0; h < H; ++h) {          // G_h [B*Tq, Tk] = qv_h [B*Tq, 64] . r_h [Tk, 64]^T
-    int rc = emo_gemm(EMO_GEMM_NT, (int64_t)B * Tq, Tk, RE, qv + h * RE, d, (const bf16*)r + h * RE, ld_r, G + (int64_t)h * B * Tq * Tk, Tk,
-                      EMO_BF16, EMO_BF16, nullptr, s);
-    if (rc) return rc;
-  }
-  return EMO_OK;
-}
 }  // namespace
 
 bool emo_relattn_tc_ok(int B, int Tq, int Tk, int H) {
@@ -252,11 +199,13 @@ int emo_relattn_fwd_tc_launch(const void* q, const void* k, const void* v, int64
   int rc = emo_attn_tc_configure_pool();
   if (rc) return rc;
   const int d = H * RE;
-  const int64_t rows = (int64_t)B * Tq, nG = (int64_t)H * rows * Tk;
+  const int64_t rows = (int64_t)B * Tq, nP = (int64_t)B * H * rel_plane_elems(Tq, Tk);
+  const bool padded = (Tq % 128) != 0 || (Tk % 128) != 0;      // block rows / columns nobody writes must still be finite
   bf16* ws = nullptr;
-  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(2 * rows * d + 2 * nG + 512) * sizeof(bf16), s));
-  bf16 *qw = ws, *qv = qw + rows * d, *G = qv + rows * d, *BD = G + nG;
+  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(2 * rows * d + nP + 512) * sizeof(bf16), s));
+  bf16 *qw = ws, *qv = qw + rows * d, *BD = qv + rows * d;
   do {
+    if (padded && cudaMemsetAsync(BD, 0, (size_t)nP * sizeof(bf16), s) != cudaSuccess) break;
     rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
     if ((rc = rel_scores_shift<false>(q, ld_q, r_r_bias, r, ld_r, BD, B, Tq, Tk, H, s))) break;
     AttnTcRel ex = {BD, nullptr, nullptr, 1};
@@ -282,15 +231,17 @@ int emo_relattn_bwd_tc_launch(const void* q, const void* k, const void* v, int64
   const int64_t nf = emo_attn_bwd_tc_ws_floats(B, Tq, H);
   bf16* ws = nullptr;
   float* wf = nullptr;
-  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(3 * rows * d + 3 * nG + 512) * sizeof(bf16), s));
+  const int64_t nP = (int64_t)B * H * rel_plane_elems(Tk, Tq);
+  const bool padded = (Tq % 128) != 0 || (Tk % 128) != 0;
+  EMO_CHECK_CUDA(cudaMallocAsync((void**)&ws, (size_t)(3 * rows * d + nG + 2 * nP + 512) * sizeof(bf16), s));
   if (cudaMallocAsync((void**)&wf, (size_t)nf * sizeof(float), s) != cudaSuccess) {
     cudaFreeAsync(ws, s);
     emo_set_error("emo_relattn_bwd (tcgen05): workspace allocation failed");
     return EMO_ERR_CUDA;
   }
-  bf16 *qw = ws, *qv = qw + rows * d, *dqv = qv + rows * d, *G = dqv + rows * d, *BDT = G + nG, *dBDT = BDT + nG;
-  bf16* dG = G;                                   // G is dead once BD^T exists
+  bf16 *qw = ws, *qv = qw + rows * d, *dqv = qv + rows * d, *dG = dqv + rows * d, *BDT = dG + nG, *dBDT = BDT + nP;
   do {
+    if (padded && cudaMemsetAsync(BDT, 0, (size_t)nP * sizeof(bf16), s) != cudaSuccess) break;
     rel_prep_kernel<<<(unsigned)((rows * (d / 8) + 255) / 256), 256, 0, s>>>((const bf16*)q, ld_q, r_w_bias, r_r_bias, qw, qv, rows, d);
     if ((rc = rel_scores_shift<true>(q, ld_q, r_r_bias, r, ld_r, BDT, B, Tq, Tk, H, s))) break;
     dim3 tgrid((Tq + 63) / 64, (Tk + 63) / 64, B * H);
