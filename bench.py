@@ -545,7 +545,7 @@ def main():
 
     # ---- warm-up (also: find the dominant kernel class) -------------------------------------------
     ops.TIMER.enable(["gemm", "favor_fwd", "favor_bwd", "emo_ln_fwd", "emo_ln_res_fwd", "emo_ln_bwd", "emo_colsum", "emo_ce_fwd_bwd",
-                      "emo_embed_fwd", "emo_embed_bwd_table", "emo_adam_step", "emo_sumsq"])
+                      "emo_embed_fwd", "emo_embed_bwd", "emo_adam_step", "emo_sumsq"])
     for i in range(args.warmup):
         if i == args.warmup - 1:
             ops.TIMER.enable(list(ops.TIMER.classes))       # keep only the last warm-up step's events

@@ -31,7 +31,6 @@ SIGNATURES = {
     "emo_performer_decode_step": ([vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32,
                                    vp], i32),
     "emo_embed_bwd": ([vp, vp, i64, i64, vp, vp, vp, i32, i32, i32, f32, f32, u64, i64, i32, vp], i32),
-    "emo_embed_bwd_table": ([vp, vp, i64, i64, vp, vp, vp, i32, i32, i32, i32, f32, f32, u64, i64, i32, vp], i32),
     "emo_ln_fwd": ([vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp], i32),
     "emo_ln_res_fwd": ([vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp], i32),
     "emo_ln_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, vp, vp, vp, i64, i32, i32, vp], i32),

@@ -155,10 +155,8 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, const int64_t*
         }
       }
       int64_t id = tok[b * sb + t * st];
-      if (id != pad_idx) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(d_e_tok + id * d + col + j, g[j]);
-      }
+      if (id != pad_idx)      // one 16-byte reduction per thread and row (red.global.add.v4.f32) instead of four scalar ones
+        atomicAdd(reinterpret_cast<float4*>(d_e_tok + id * d + col), make_float4(g[0], g[1], g[2], g[3]));
       if (seg != nullptr && d_e_seg != nullptr) {
         int sidx = (int)seg[b * sb + t * st] & 1;
 #pragma unroll
@@ -172,57 +170,6 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, const int64_t*
         for (int j = 0; j < 4; ++j) atomicAdd(d_e_seg + sidx * d + col + j, acc[sidx][j]);
     }
   }
-}
-
-// Small vocabularies (the event vocabularies here have 216 - 372 entries): 77 M scalar atomics onto a 329-row table made
-// the kernel above the slowest non-GEMM launch per byte (460 us for 155 MB).  Here a CTA owns a 64-column slice of the
-// table in shared memory ((V + 2) x 64 fp32: the two segment rows ride along) and a contiguous chunk of tokens: a warp
-// reads one token's 128-byte slice (2 columns per lane), applies the embedding dropout mask of the forward pass and adds
-// into the shared table; the table is flushed with one global atomic per entry at the end (12 x fewer, and spread).
-constexpr int EB_COLS = 64;
-template <typename T>
-__global__ void __launch_bounds__(256) embed_bwd_sliced_kernel(const int64_t* __restrict__ tok, const int64_t* __restrict__ seg,
-                                                               int64_t sb, int64_t st, const T* __restrict__ dout,
-                                                               float* __restrict__ d_e_tok, float* __restrict__ d_e_seg, int B,
-                                                               int T_, int d, int V, float scale, uint32_t thr, float keep_scale,
-                                                               uint64_t seed, int64_t pad_idx, int rows_per_block) {
-  extern __shared__ float eb_tab[];                 // [(V + 2)][EB_COLS]
-  const int c0 = blockIdx.x * EB_COLS;
-  const int64_t rows = (int64_t)B * T_;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  for (int i = threadIdx.x; i < (V + 2) * EB_COLS; i += blockDim.x) eb_tab[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int col = c0 + 2 * lane;
-  const bool with_seg = seg != nullptr && d_e_seg != nullptr;
-  for (int64_t row = r0 + warp; row < r1; row += nw) {
-    const int b = (int)(row / T_), t = (int)(row % T_);
-    const int64_t id = tok[b * sb + t * st];
-    float g0 = to_f(dout[row * d + col]) * scale, g1 = to_f(dout[row * d + col + 1]) * scale;
-    if (thr) {
-      const uint32_t h = emo_drop_hash(seed, (uint64_t)row * d + col);
-      g0 = ((h & 0xffffu) >= thr) ? g0 * keep_scale : 0.f;
-      g1 = ((h >> 16) >= thr) ? g1 * keep_scale : 0.f;
-    }
-    if (id != pad_idx) {
-      atomicAdd(&eb_tab[id * EB_COLS + 2 * lane], g0);
-      atomicAdd(&eb_tab[id * EB_COLS + 2 * lane + 1], g1);
-    }
-    if (with_seg) {
-      const int sidx = (int)seg[b * sb + t * st] & 1;
-      atomicAdd(&eb_tab[(V + sidx) * EB_COLS + 2 * lane], g0);
-      atomicAdd(&eb_tab[(V + sidx) * EB_COLS + 2 * lane + 1], g1);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < V * EB_COLS; i += blockDim.x) {
-    const float v = eb_tab[i];
-    if (v != 0.f) atomicAdd(d_e_tok + (int64_t)(i / EB_COLS) * d + c0 + (i % EB_COLS), v);
-  }
-  if (with_seg)
-    for (int i = threadIdx.x; i < 2 * EB_COLS; i += blockDim.x)
-      atomicAdd(d_e_seg + (int64_t)(i / EB_COLS) * d + c0 + (i % EB_COLS), eb_tab[V * EB_COLS + i]);
 }
 
 extern "C" int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
@@ -241,40 +188,6 @@ extern "C" int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t str
     embed_bwd_kernel<bf16><<<blocks, 128, 0, s>>>(tok, seg, stride_b, stride_t, (const bf16*)dout, d_e_tok, d_e_seg, B, T, d, scale, thr, ks, seed, pad_idx, rpb);
   else
     embed_bwd_kernel<float><<<blocks, 128, 0, s>>>(tok, seg, stride_b, stride_t, (const float*)dout, d_e_tok, d_e_seg, B, T, d, scale, thr, ks, seed, pad_idx, rpb);
-  EMO_LAUNCH_CHECK();
-  return EMO_OK;
-}
-
-// the same with the table height known (V rows in d_e_tok): vocabularies whose 64-column slice fits shared memory take
-// the sliced kernel, larger ones the per-element atomics of emo_embed_bwd
-extern "C" int emo_embed_bwd_table(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
-                                   const void* dout, float* d_e_tok, float* d_e_seg, int B, int T, int d, int V,
-                                   float scale, float drop_p, uint64_t seed, int64_t pad_idx, int dtype,
-                                   void* stream) {
-  const size_t smem = (size_t)(V + 2) * EB_COLS * sizeof(float);
-  if (V <= 0 || d % EB_COLS != 0 || smem > 200 * 1024)
-    return emo_embed_bwd(tok, seg, stride_b, stride_t, dout, d_e_tok, d_e_seg, B, T, d, scale, drop_p, seed, pad_idx, dtype, stream);
-  const int64_t rows = (int64_t)B * T;
-  if (rows == 0) return EMO_OK;
-  const uint32_t thr = emo_drop_thr(drop_p);
-  const float ks = 1.f / (1.f - drop_p);
-  // row chunks so that the grid is about two CTAs per SM (shared memory allows two for V <= 380)
-  const int slices = d / EB_COLS;
-  int chunks = (2 * emo_num_sms() + slices - 1) / slices;
-  if ((int64_t)chunks > (rows + 63) / 64) chunks = (int)((rows + 63) / 64);
-  const int rpb = (int)((rows + chunks - 1) / chunks);
-  chunks = (int)((rows + rpb - 1) / rpb);
-  cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(slices, chunks);
-  if (dtype == EMO_BF16) {
-    static bool configured = false;
-    if (!configured) { EMO_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_sliced_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
-    embed_bwd_sliced_kernel<bf16><<<grid, 256, smem, s>>>(tok, seg, stride_b, stride_t, (const bf16*)dout, d_e_tok, d_e_seg, B, T, d, V, scale, thr, ks, seed, pad_idx, rpb);
-  } else {
-    static bool configured = false;
-    if (!configured) { EMO_CHECK_CUDA(cudaFuncSetAttribute(embed_bwd_sliced_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
-    embed_bwd_sliced_kernel<float><<<grid, 256, smem, s>>>(tok, seg, stride_b, stride_t, (const float*)dout, d_e_tok, d_e_seg, B, T, d, V, scale, thr, ks, seed, pad_idx, rpb);
-  }
   EMO_LAUNCH_CHECK();
   return EMO_OK;
 }

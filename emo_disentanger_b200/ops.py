@@ -107,8 +107,8 @@ def embed_bwd(tok, seg, dout, d_e_tok, d_e_seg, scale, drop_p=0.0, seed=0, pad_i
     else:
         T, B = tok.shape
         sb, st = tok.stride(1), tok.stride(0)
-    V, d = d_e_tok.shape
-    _call("emo_embed_bwd_table", _p(tok), _p(seg), sb, st, _p(dout), _p(d_e_tok), _p(d_e_seg), B, T, d, V,
+    d = d_e_tok.shape[1]
+    _call("emo_embed_bwd", _p(tok), _p(seg), sb, st, _p(dout), _p(d_e_tok), _p(d_e_seg), B, T, d,
           float(scale), float(drop_p), int(seed), int(pad_idx), _dt(dout), _stream())
 
 

@@ -101,13 +101,6 @@ int emo_embed_bwd(const int64_t* tok, const int64_t* seg, int64_t stride_b, int6
                   const void* dout, float* d_e_tok, float* d_e_seg, int B, int T, int d,
                   float scale, float drop_p, uint64_t seed, int64_t pad_idx, int dtype,
                   void* stream);
-/* the same with the height V of d_e_tok given: event vocabularies (216 - 372 entries) are accumulated per 64-column
- * slice in shared memory and flushed once per CTA instead of one global atomic per element; same result up to the
- * order of the fp32 additions.  Falls back to emo_embed_bwd when the slice does not fit shared memory. */
-int emo_embed_bwd_table(const int64_t* tok, const int64_t* seg, int64_t stride_b, int64_t stride_t,
-                        const void* dout, float* d_e_tok, float* d_e_seg, int B, int T, int d, int V,
-                        float scale, float drop_p, uint64_t seed, int64_t pad_idx, int dtype,
-                        void* stream);
 
 /* ---- A3/A7/A9: LayerNorm (eps 1e-5) over the last dim d=512 -------------------------------
  * fast_transformers TransformerEncoderLayer.norm1/norm2, HF GPT2Block.ln_1/ln_2,

@@ -419,23 +419,15 @@ def test_embedding_fwd_bwd(ops, dtype):
     rt[int(tok[0, 0])] = 0
     rs = torch.zeros_like(es).index_add_(0, seg.view(-1), dout.float() * s)
     assert rel_err(det, rt) < 1e-5 and rel_err(des, rs) < 1e-4
-    # with the embedding dropout: the sliced (shared-memory table) kernel against the per-element-atomics kernel, and
-    # against the forward's mask: gradient = sum over tokens of dropout_apply(dout) * s
-    from emo_disentanger_b200 import _lib
+    # with the embedding dropout: gradient = sum over tokens of dropout_apply(dout) * s (the forward's mask, re-derived)
     seed = 0xABCDEF12345
     d1, s1 = torch.zeros_like(et), torch.zeros_like(es)
     ops.embed_bwd(tok, seg, dout, d1, s1, s, drop_p=0.1, seed=seed, pad_idx=7)
-    d2, s2 = torch.zeros_like(et), torch.zeros_like(es)
-    _lib.check(_lib.lib().emo_embed_bwd(tok.data_ptr(), seg.data_ptr(), tok.stride(0), tok.stride(1), dout.data_ptr(), d2.data_ptr(),
-                                        s2.data_ptr(), B, T, 512, float(s), 0.1, seed, 7, ops._dt(dout),
-                                        torch.cuda.current_stream().cuda_stream), "emo_embed_bwd")
-    torch.cuda.synchronize()
-    assert rel_err(d1, d2) < 1e-5 and rel_err(s1, s2) < 1e-5
     dd = ops.dropout_apply(dout, torch.empty_like(dout), 0.1, seed)
     rtd = torch.zeros_like(et).index_add_(0, tok.view(-1), dd.float() * s)
     rtd[7] = 0
     assert rel_err(d1, rtd) < (1e-5 if dtype == torch.float32 else 1e-2)
-    # [T, B] strides through the sliced kernel
+    # [T, B] token layout through strides
     d3, s3 = torch.zeros_like(et), torch.zeros_like(es)
     ops.embed_bwd(tok.t().contiguous(), seg.t().contiguous(), dout, d3, s3, s, pad_idx=7, batch_first=False)   # rows stay (b, t)-ordered
     rt3 = torch.zeros_like(et).index_add_(0, tok.view(-1), dout.float() * s)
