@@ -292,7 +292,12 @@ def generate_conditional_batch(model, event2idx, idx2event, lead_sheets, primers
     dec.reset()
     r = np.random if rng is None else rng
     sampler = DeviceSampler(dec.dev)
-    t_rows = torch.tensor([float(t) for t in temps], dtype=torch.float32, device=dec.dev)
+    # the per-row temperatures live in a buffer owned by the decoder: its ADDRESS is part of the captured step graph's
+    # key, so a reused decoder replays the graph of the previous piece instead of capturing a new one
+    if getattr(dec, "_t_rows", None) is None:
+        dec._t_rows = torch.empty(dec.B, dtype=torch.float32, device=dec.dev)
+    dec._t_rows.copy_(torch.tensor([float(t) for t in temps], dtype=torch.float32))
+    t_rows = dec._t_rows
     gens = [_conditional_rules(event2idx, idx2event, lead_sheets[b], list(primers[b]), max_events, skip_check, max_bars, greedy, say)
             for b in range(n)]
     results = [None] * n
