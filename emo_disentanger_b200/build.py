@@ -17,6 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+FLAGS += os.environ.get("EMO_NVCC_FLAGS", "").split()      # e.g. -DEMO_KERNEL_DBG_CLK (clock64 stamps for scripts/dev/*_clk.py)
 
 
 def sources():

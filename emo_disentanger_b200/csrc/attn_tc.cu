@@ -512,7 +512,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) tma_reduce_add_3d(&tmDQ, sDQw, h * HD + 16 * ch, (qt0 + t) * BM + 32 * quad, b);
     };
     int wk = 0;
+// clock64 stamps of one worker thread (perf triage): compiled in only with -DEMO_KERNEL_DBG_CLK -- the run-time check alone
+// was ~9 % of the attention backward's executed instructions (six stamps per tile in an issue-bound loop)
+#ifdef EMO_KERNEL_DBG_CLK
 #define WSTAMP() do { if (p.dbg_clk && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && (it == 3 || it == 4) && wk < 16) p.dbg_clk[16 + wk++] = clock64(); } while (0)
+#else
+#define WSTAMP() do { } while (0)
+#endif
     for (int it = 0; it < n; ++it) {
       const uint32_t st = it % NST;
       const int i0 = (qt0 + it) * BM;

@@ -196,7 +196,13 @@ favor_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int i = tid;                     // token row of the chunk == TMEM lane
         const bool rowok = i < valid;
         int wk = 0;
+// clock64 stamps of one worker thread (perf triage): compiled in only with -DEMO_KERNEL_DBG_CLK -- the run-time check alone
+// was ~9 % of the attention backward's executed instructions (six stamps per tile in an issue-bound loop)
+#ifdef EMO_KERNEL_DBG_CLK
 #define FSTAMP() do { if (p.dbg_clk && tid == 0 && blockIdx.x == 0 && t0 == t_begin + 3 * C && wk < 16) p.dbg_clk[wk++] = clock64(); } while (0)
+#else
+#define FSTAMP() do { } while (0)
+#endif
         FSTAMP();
         mbar_wait(bar_m1, ph_m);                     // batch 1: U_q, U_k (which also means q, k have landed)
         FSTAMP();

@@ -1,3 +1,5 @@
+"""clock64 stamps of one worker thread; needs a library built with the stamps compiled in:
+    EMO_NVCC_FLAGS=-DEMO_KERNEL_DBG_CLK python -m emo_disentanger_b200.build --force"""
 import sys, os, torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 buf = torch.zeros(16, dtype=torch.int64, device="cuda")
