@@ -78,8 +78,14 @@ class FlatModule(nn.Module):
         return [n for _, n in sorted((self._ref_order_key(n, i), n) for i, n in enumerate(names))]
 
     def _named_flat_params(self):
-        d = dict(self.named_parameters())
-        return [(d[name], shape, off, n) for name, shape, off, n, _ in self._specs]
+        # cached: walking named_parameters() on every backward was ~1 ms of host time per step (the Parameter objects are
+        # stable -- .to() / .cuda() rebind their .data in _bind; _apply drops the cache before it re-reads them)
+        ps = self.__dict__.get("_nfp_cache")
+        if ps is None:
+            d = dict(self.named_parameters())
+            ps = [(d[name], shape, off, n) for name, shape, off, n, _ in self._specs]
+            self.__dict__["_nfp_cache"] = ps
+        return ps
 
     def _bind(self, flat):
         self._flat = flat
@@ -87,12 +93,14 @@ class FlatModule(nn.Module):
         self._flat_lp = None
         self._lp_version = -1
         self.__dict__.pop("_version_params", None)
+        self.__dict__.pop("_view_cache", None)            # cached views (_wv) alias the buffers that were just replaced
         for p, shape, off, n in self._named_flat_params():
             p.data = flat[off:off + n].view(shape)
             p.grad = self._flat_grad[off:off + n].view(shape)
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn)
+        self.__dict__.pop("_nfp_cache", None)
         ps = self._named_flat_params()
         if ps:
             dev = ps[0][0].device
@@ -153,6 +161,7 @@ class FlatModule(nn.Module):
         ver = self._weights_version()
         if self._flat_lp is None or self._flat_lp.device != self._flat.device:
             self._flat_lp = torch.empty(self._total, dtype=torch.bfloat16, device=self._flat.device)
+            self.__dict__.pop("_view_cache", None)
             self._lp_version = -1
         if ver != self._lp_version:
             ops.cast(self._flat, self._flat_lp)

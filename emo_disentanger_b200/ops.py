@@ -21,7 +21,9 @@ def _dt(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # the raw cudaStream_t of torch's current stream on the current device (what torch.cuda.current_stream().cuda_stream
+    # returns, without building a Stream object: ~10 us -> ~0.5 us, once per launch)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 class KernelTimer:

@@ -79,12 +79,22 @@ class MusicPerformer(Stage2Base):
         return "transformer_decoder.decoder_layers.%d." % l
 
     def _qkv_w(self, buf, l):
-        off, n, _ = self._sl[self._layer_names(l) + "attention.query_projection.weight"]
-        return buf[off:off + 3 * n].view(3 * self.d_model, self.d_model)
+        cache = self.__dict__.setdefault("_view_cache", {})
+        key = (buf.data_ptr(), "qkv_w", l)
+        v = cache.get(key)
+        if v is None:
+            off, n, _ = self._sl[self._layer_names(l) + "attention.query_projection.weight"]
+            v = cache[key] = buf[off:off + 3 * n].view(3 * self.d_model, self.d_model)
+        return v
 
     def _qkv_b(self, buf, l):
-        off, n, _ = self._sl[self._layer_names(l) + "attention.query_projection.bias"]
-        return buf[off:off + 3 * n]
+        cache = self.__dict__.setdefault("_view_cache", {})
+        key = (buf.data_ptr(), "qkv_b", l)
+        v = cache.get(key)
+        if v is None:
+            off, n, _ = self._sl[self._layer_names(l) + "attention.query_projection.bias"]
+            v = cache[key] = buf[off:off + 3 * n]
+        return v
 
     # ---- forward -------------------------------------------------------------------------------
     def _forward_hidden(self, x, seg, save):
