@@ -72,16 +72,24 @@ __global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict
   const int off = Tk - Tq;
   const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int jmin = t0 - (Tq - 1) + i0;
-  for (int jr = w; jr < 127; jr += 8) {
-    const int j = jmin + jr, i = i0 + 2 * tx;
-    uint32_t v = 0;
-    if (j >= 0 && j < Tk && i < Tq) {
-      v = __ldg(reinterpret_cast<const uint32_t*>(dBDT + bh * rel_plane_elems(Tk, Tq) + rel_blocked_off(j, i, Tq)));
-      if (j > i + 1 + off) v = 0;                // both queries of the pair are before the key
-      else if (j == i + 1 + off) v &= 0xffff0000u;     // only the second query of the pair sees the key
+  // whole 16-byte chunks of the blocked plane: lane = (row & 3, chunk of 8 queries) -- the same chunk of 4 consecutive key
+  // rows is 64 contiguous bytes there, so every sector that is fetched is used (4-byte loads per query pair used half)
+  const bf16* plane = dBDT + bh * rel_plane_elems(Tk, Tq);
+  const int rsub = tx & 3, c8 = tx >> 2;
+  for (int g4 = w; g4 < 32; g4 += 8) {
+    const int jr = 4 * g4 + rsub, j = jmin + jr, ic = i0 + 8 * c8;
+    if (jr >= 127) continue;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (j >= 0 && j < Tk && ic < Tq && j <= ic + 7 + off)          // (Tq % 32 == 0: a chunk is all-in or all-out)
+      v = __ldg(reinterpret_cast<const uint4*>(plane + rel_blocked_off(j, ic, Tq)));
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {                                  // query i sees key j iff j <= i + off
+      const int i = ic + 2 * e;
+      if (j > i + 1 + off) wv[e] = 0u;
+      else if (j == i + 1 + off) wv[e] &= 0xffff0000u;
+      *reinterpret_cast<uint32_t*>(&patch[jr][8 * c8 + 2 * e]) = wv[e];
     }
-    patch[jr][2 * tx] = (unsigned short)(v & 0xffffu);
-    patch[jr][2 * tx + 1] = (unsigned short)(v >> 16);
   }
   __syncthreads();
   if (t0 + 2 * tx >= Tk) return;                 // Tk is a multiple of 64
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(256) rel_unshift_kernel(const bf16* __restrict
 struct RelScoreSmem {
   bf16 qv[64][bg_ld<bf16>(RE)];
   bf16 rb[128][bg_ld<bf16>(RE)];
-  float g[64][130];
+  unsigned short g[64][134];      // G as bf16 bits (rounded once, here: what the planes store anyway): 45 KB per CTA -> 5 CTAs per SM
 };
 template <bool TRANS>
 __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16* __restrict__ q, int64_t ld_q, const float* __restrict__ rrb,
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16
     BlockGemm<64, 128, bf16> gg;
     gg.clear();
     gg.template mma<true, true>(&sm.qv[0][0], bg_ld<bf16>(RE), &sm.rb[0][0], bg_ld<bf16>(RE), RE);
-    gg.foreach ([&](int r_, int c_, float& x) { sm.g[r_][c_] = x; });
+    gg.foreach ([&](int r_, int c_, float& x) { sm.g[r_][c_] = __bfloat16_as_ushort(__float2bfloat16_rn(x)); });
   }
   __syncthreads();
   const int row = tid >> 2, chunk = tid & 3;                 // 64 rows x 4 chunks of 16 elements
@@ -150,9 +158,9 @@ __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int jj = 16 * chunk + 2 * e;
-      const float v0 = (j0 + jj <= i + off) ? sm.g[row][63 - row + jj] : 0.f;
-      const float v1 = (j0 + jj + 1 <= i + off) ? sm.g[row][63 - row + jj + 1] : 0.f;
-      w[e] = pack_bf16x2(v0, v1);
+      const uint32_t v0 = (j0 + jj <= i + off) ? sm.g[row][63 - row + jj] : 0u;
+      const uint32_t v1 = (j0 + jj + 1 <= i + off) ? sm.g[row][63 - row + jj + 1] : 0u;
+      w[e] = v0 | (v1 << 16);
     }
     bf16* plane = outp + bh * rel_plane_elems(Tq, Tk);
     *reinterpret_cast<uint4*>(plane + rel_blocked_off(i, j0 + 16 * chunk, Tk)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -163,9 +171,9 @@ __global__ void __launch_bounds__(BG_THREADS) rel_scores_shift_kernel(const bf16
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int ii = 16 * chunk + 2 * e;
-      const float v0 = (j <= i0 + ii + off) ? sm.g[ii][63 - ii + row] : 0.f;
-      const float v1 = (j <= i0 + ii + 1 + off) ? sm.g[ii + 1][62 - ii + row] : 0.f;
-      w[e] = pack_bf16x2(v0, v1);
+      const uint32_t v0 = (j <= i0 + ii + off) ? sm.g[ii][63 - ii + row] : 0u;
+      const uint32_t v1 = (j <= i0 + ii + 1 + off) ? sm.g[ii + 1][62 - ii + row] : 0u;
+      w[e] = v0 | (v1 << 16);
     }
     bf16* plane = outp + bh * rel_plane_elems(Tk, Tq);
     *reinterpret_cast<uint4*>(plane + rel_blocked_off(j, i0 + 16 * chunk, Tq)) = make_uint4(w[0], w[1], w[2], w[3]);
