@@ -93,6 +93,9 @@ def main(argv=None):
             todo = [e for e in emotions_for(file) if not os.path.exists(os.path.join(out_dir, out_name + '_' + e + '_full.txt'))]
             if todo:
                 key, lead = read_lead_sheet(file, event2idx)
+                if not lead:              # (the reference indexes bar 0 and dies with an IndexError here, inference.py:237)
+                    print('[info] {} holds no complete bar, skipping ...'.format(file))
+                    continue
                 primers = [[event2idx['Emotion_{}'.format(e)]] + ([event2idx[key]] if rep == 'functional' else []) +
                            [event2idx['Tempo_{}'.format(110)]] for e in todo]
                 if len(todo) not in decs:
@@ -112,6 +115,9 @@ def main(argv=None):
                 print('[info] {} exists, skipping ...'.format(out_txt))
                 continue
             key, lead = read_lead_sheet(file, event2idx)
+            if not lead:
+                print('[info] {} holds no complete bar, skipping ...'.format(file))
+                break
             primer = [event2idx['Emotion_{}'.format(e)]] + ([event2idx[key]] if rep == 'functional' else []) + \
                      [event2idx['Tempo_{}'.format(110)]]
             generated = generate_conditional(model, event2idx, idx2event, lead, primer=primer, max_bars=args.max_bars,
