@@ -663,8 +663,8 @@ def main():
                            "(the live roofline timer); the `e2e` loop does not, which is why e2e can read slightly above value"}
 
     if rank == 0 and world == 1 and not args.no_extras:
-        # the reference's own batch_size (emopia_finetune.yaml: 4): 8 192 tokens per step, where host-side launch cost
-        # (tensor-map encodes are cached, emo_gemm) rather than the GPU bounds the step
+        # the reference's own batch_size (emopia_finetune.yaml: 4): 8 192 tokens per step -- 242 launches of small grids; the
+        # host side (cached tensor maps, cached flat-buffer views, raw stream lookup) takes ~4.7 ms of it
         hb = make_batches(2, 4, T, V, 77, pinned=False)
         db = [tuple(t.to(dev) for t in b) for b in hb]
         def step_b4(i=[0]):
