@@ -554,7 +554,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also: find the dominant kernel class) -------------------------------------------
-    ops.TIMER.enable(["gemm", "favor_fwd", "favor_bwd", "emo_ln_fwd", "emo_ln_res_fwd", "emo_ln_bwd", "emo_colsum", "emo_ce_fwd_bwd",
+    ops.TIMER.enable(["gemm", "gemm_ln", "favor_fwd", "favor_bwd", "emo_ln_fwd", "emo_ln_res_fwd", "emo_ln_bwd", "emo_colsum", "emo_ce_fwd_bwd",
                       "emo_embed_fwd", "emo_embed_bwd", "emo_adam_step", "emo_sumsq"])
     for i in range(args.warmup):
         if i == args.warmup - 1:

@@ -37,6 +37,7 @@ SIGNATURES = {
     "emo_dropout_apply": ([vp, vp, i64, f32, u64, i32, vp], i32),
     "emo_gemm": ([i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, i32, C.POINTER(Epilogue), vp], i32),
     "emo_colsum": ([vp, i64, i64, i64, vp, i32, vp], i32),
+    "emo_gemm_ln_res": ([i64, i64, vp, i64, vp, i64, vp, f32, u64, vp, i64, vp, vp, f32, vp, i64, vp, i64, vp, vp, vp], i32),
     "emo_favor_nseg": ([i32, i32, i32, i32], i32),
     "emo_favor_fwd": ([vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp], i32),
     "emo_favor_bwd": ([vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp], i32),

@@ -756,6 +756,318 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Projection + residual + LayerNorm in one kernel (the post-LN encoder layer's `norm(x + dropout(sublayer(x)))`,
+// fast_transformers TransformerEncoderLayer.forward; N = d_model = 512):
+//     s = res + dropout(A W^T + bias)   (fp32, never rounded on the way into the norm)
+//     y = LN(s) * gamma + beta,  mean / rstd and (optionally) bf16(s) kept for the backward.
+// A CTA pair owns 256 rows x ALL 512 columns: two N = 256 cta_group::2 MMAs per k-step into ONE accumulator of 512
+// TMEM columns (no double buffer: the row statistics need the whole row).  The epilogue makes two passes over its
+// 128 x 512 block: pass 1 forms s (bias, dropout hash, residual tile TMA-loaded into the warp's staging buffer), sums
+// s and s^2 per row, stores bf16(s) by TMA and parks fp32 s back in tensor memory; the two warps that share a row
+// quadrant exchange their half-row sums through shared memory; pass 2 re-reads s from tensor memory, normalises and
+// stores y by TMA.  Replaces a GEMM launch + ln_fwd_kernel<RES> (which moved 620 MB per call at the HBM roofline).
+namespace ln {
+constexpr int LBN = 512, LSTAGES = 3;
+constexpr int L_STAGE_BYTES = A_STAGE_BYTES + 2 * 128 * BK * 2;          // A rows + two 128-row halves of B: 48 KB
+constexpr int L_STAT_BYTES = 2 * 2 * 128 * 8;                           // [tile parity][column half][row] (sum, sumsq)
+constexpr int L_SMEM = LSTAGES * L_STAGE_BYTES + EPI_STAGE_BYTES + L_STAT_BYTES + 1024 + 512;
+static_assert(L_SMEM <= 227 * 1024, "fused LN GEMM smem exceeds the CTA limit");
+
+struct LnParams {
+  int64_t M, K;
+  int m_tiles, kb_total;
+  const float* bias; const float* gamma; const float* beta;
+  float* mean; float* rstd;
+  uint32_t drop_thr; float keep_scale; uint64_t seed;
+  float eps;
+  int store_sum;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmS, const __grid_constant__ LnParams p) {
+  const int rank = (int)cluster_ctarank();
+  const int unit = blockIdx.x / 2, nunits = gridDim.x / 2;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* epi_smem = smem + LSTAGES * L_STAGE_BYTES;
+  float2* stat = reinterpret_cast<float2*>(epi_smem + EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_STAGE_BYTES + L_STAT_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LSTAGES + 2 + 2 * EPI_WARPS);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (LSTAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * LSTAGES), tempty_bar = bar_base + 8u * (2 * LSTAGES + 1);
+  auto r_bar = [&](int w, int b) { return bar_base + 8u * (2 * LSTAGES + 2 + 2 * w + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    if (p.store_sum) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
+    for (int s = 0; s < LSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, EPI_WARPS * 2);
+    for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(r_bar(w, 0), 1); mbar_init(r_bar(w, 1), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = unit; it < p.m_tiles; it += nunits) {
+        const int m0 = it * 256 + rank * BM;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * L_STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), L_STAGE_BYTES * 2);
+          const int k0 = kb * BK;
+          tma_load_2d_pair(&tmA, full_bar(stage), sa, k0, m0);
+          tma_load_2d_pair(&tmB, full_bar(stage), sb, k0, rank * 128);                 // output columns [0, 256): this CTA's half
+          tma_load_2d_pair(&tmB, full_bar(stage), sb + 16384, k0, 256 + rank * 128);   // output columns [256, 512)
+          if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int it = unit; it < p.m_tiles; it += nunits) {
+        mbar_wait(tempty_bar, aphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L_STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_desc(sa + k * 32, 0, 1024);
+            umma_bf16_2(tmem_base, ad, make_desc(sb + k * 32, 0, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_2(tmem_base + 256, ad, make_desc(sb + 16384 + k * 32, 0, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit2(empty_bar(stage));
+          if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit2(tfull_bar);
+        aphase ^= 1;
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9: rows quad*32 + lane of the CTA's 128, columns [half*256, half*256 + 256) in 4 groups ----
+    const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+    const uint32_t mybuf = smem_u32(epi_smem + ew * 2 * EPI_BUF_BYTES);
+    const int sw = lane & 7;
+    uint32_t aphase = 0, rphase = 0, tpar = 0;
+    auto coords = [&](int it_, int c_, int& col, int& rowc) {
+      rowc = it_ * 256 + rank * BM + quad * 32;
+      col = (half * 4 + c_) * 64;
+    };
+    // residual tiles of a row block's first TWO groups are requested while the tensor core still works on the block (both
+    // staging buffers are free then); groups 2 and 3 follow one group ahead, as soon as the buffer's store has drained
+    auto prefetch_res01 = [&](int it_) {
+#pragma unroll
+      for (int c_ = 0; c_ < 2; ++c_) {
+        int col, rowc;
+        coords(it_, c_, col, rowc);
+        mbar_expect_tx(r_bar(ew, c_), EPI_BUF_BYTES);
+        tma_load_2d(&tmR, r_bar(ew, c_), mybuf + c_ * EPI_BUF_BYTES, col, rowc);
+      }
+    };
+    if (lane == 0 && unit < p.m_tiles) prefetch_res01(unit);
+    for (int it = unit; it < p.m_tiles; it += nunits) {
+      mbar_wait(tfull_bar, aphase);
+      tc_fence_after();
+      aphase ^= 1;
+      int rowc0, col0;
+      coords(it, 0, col0, rowc0);
+      const int64_t m = (int64_t)rowc0 + lane;
+      const bool row_ok = m < p.M;
+      const int64_t ms = row_ok ? m : 0;
+      float rsum = 0.f, rsq = 0.f;
+      // ---------------- pass 1: s = res + dropout(acc + bias); row sums; bf16(s) out; fp32 s back to TMEM ----------------
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        int col, rowc;
+        coords(it, c, col, rowc);
+        const int b = c & 1;
+        const uint32_t buf = mybuf + b * EPI_BUF_BYTES;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col;
+        uint32_t r0[32], r1[32];
+        __syncwarp();
+        tmem_ld32_issue(taddr, r0);
+        tmem_ld32_issue(taddr + 32, r1);
+        tmem_ld_wait();
+        if (lane == 0 && (c == 1 || c == 2)) {
+          tma_store_wait_read<0>();                      // the store of group c - 1 has left buffer b ^ 1
+          int coln, rown;
+          coords(it, c + 1, coln, rown);
+          mbar_expect_tx(r_bar(ew, b ^ 1), EPI_BUF_BYTES);
+          tma_load_2d(&tmR, r_bar(ew, b ^ 1), mybuf + (b ^ 1) * EPI_BUF_BYTES, coln, rown);
+        }
+        mbar_wait(r_bar(ew, b), (rphase >> b) & 1u);
+        rphase ^= 1u << b;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t (&r)[32] = hf ? r1 : r0;
+          const int nb = col + 32 * hf;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          }
+          if (p.drop_thr) {                              // same (seed, element index) mask as the unfused epilogue / ln_bwd
+            const uint64_t e0 = (uint64_t)(ms * LBN + nb);
+            const uint32_t key = emo_drop_key(p.seed, (uint32_t)(e0 >> 33));
+            const uint32_t base = (uint32_t)(e0 >> 1) * 0x9E3779B9u + key, thr_hi = p.drop_thr << 16;
+            uint32_t h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = base + (uint32_t)j * 0x9E3779B9u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] ^= h[j] >> 15;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] *= 0x2C1B3C6Du;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] ^= h[j] >> 13;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = ((h[j] << 16) >= thr_hi) ? v[2 * j] * p.keep_scale : 0.f;
+              v[2 * j + 1] = (h[j] >= thr_hi) ? v[2 * j + 1] * p.keep_scale : 0.f;
+            }
+          }
+          const uint32_t rowp = buf + lane * 128;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {               // + residual (bf16 tile in the staging buffer)
+            const uint4 t = lds128(rowp + (((hf * 4 + cc) ^ sw) << 4));
+            float a0, a1;
+            unpack_bf16x2(t.x, a0, a1); v[8 * cc] += a0; v[8 * cc + 1] += a1;
+            unpack_bf16x2(t.y, a0, a1); v[8 * cc + 2] += a0; v[8 * cc + 3] += a1;
+            unpack_bf16x2(t.z, a0, a1); v[8 * cc + 4] += a0; v[8 * cc + 5] += a1;
+            unpack_bf16x2(t.w, a0, a1); v[8 * cc + 6] += a0; v[8 * cc + 7] += a1;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { rsum += v[j]; rsq = fmaf(v[j], v[j], rsq); }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 t;
+            t.x = pack_bf16x2(v[8 * cc], v[8 * cc + 1]); t.y = pack_bf16x2(v[8 * cc + 2], v[8 * cc + 3]);
+            t.z = pack_bf16x2(v[8 * cc + 4], v[8 * cc + 5]); t.w = pack_bf16x2(v[8 * cc + 6], v[8 * cc + 7]);
+            sts128(rowp + (((hf * 4 + cc) ^ sw) << 4), t);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+          tmem_st32(taddr + 32 * hf, r);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && p.store_sum) tma_store_2d(&tmS, buf, col, rowc);
+      }
+      tmem_st_wait();
+      // ---------------- the two column halves of a row meet ----------------
+      stat[(tpar * 2 + half) * 128 + quad * 32 + lane] = make_float2(rsum, rsq);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 o = stat[(tpar * 2 + (half ^ 1)) * 128 + quad * 32 + lane];
+      tpar ^= 1;
+      const float mu = (rsum + o.x) * (1.f / LBN);
+      const float var = fmaxf((rsq + o.y) * (1.f / LBN) - mu * mu, 0.f);
+      const float rs = rsqrtf(var + p.eps);
+      if (half == 0 && row_ok) {
+        if (p.mean) p.mean[m] = mu;
+        if (p.rstd) p.rstd[m] = rs;
+      }
+      // ---------------- pass 2: y = (s - mu) * rstd * gamma + beta ----------------
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        int col, rowc;
+        coords(it, c, col, rowc);
+        const int b = c & 1;
+        const uint32_t buf = mybuf + b * EPI_BUF_BYTES;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col;
+        uint32_t r0[32], r1[32];
+        __syncwarp();
+        tmem_ld32_issue(taddr, r0);
+        tmem_ld32_issue(taddr + 32, r1);
+        tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<1>();         // the store that last used buffer b has drained it
+        __syncwarp();
+        const uint32_t rowp = buf + lane * 128;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint32_t (&r)[32] = hf ? r1 : r0;
+          const int nb = col + 32 * hf;
+          const float4* g4 = reinterpret_cast<const float4*>(p.gamma + nb);
+          const float4* b4 = reinterpret_cast<const float4*>(p.beta + nb);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float4 ga = __ldg(g4 + 2 * cc), gb = __ldg(g4 + 2 * cc + 1), ba = __ldg(b4 + 2 * cc), bb = __ldg(b4 + 2 * cc + 1);
+            const float gq[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (__uint_as_float(r[8 * cc + j]) - mu) * rs * gq[j] + bq[j];
+            uint4 t;
+            t.x = pack_bf16x2(y[0], y[1]); t.y = pack_bf16x2(y[2], y[3]); t.z = pack_bf16x2(y[4], y[5]); t.w = pack_bf16x2(y[6], y[7]);
+            sts128(rowp + (((hf * 4 + cc) ^ sw) << 4), t);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&tmY, buf, col, rowc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_leader(tempty_bar);
+        const int itn = it + nunits;                     // residual tiles of the next row block's first two groups
+        if (itn < p.m_tiles) {
+          tma_store_wait_read<0>();                      // (the epilogue warps idle through the block's MMAs anyway)
+          prefetch_res01(itn);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+}  // namespace ln
+
 // ---- host side -----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1049,4 +1361,54 @@ extern "C" int emo_gemm(int op, int64_t M, int64_t N, int64_t K, const void* A, 
   }
 
   return CG == 2 ? launch_any<2>(op, BN, out_dtype, mp, p, s) : launch_any<1>(op, BN, out_dtype, mp, p, s);
+}
+
+// y = LayerNorm(res + dropout(A W^T + bias)) (+ mean, rstd, bf16 copy of the sum) in one launch: see tc::ln::gemm_ln_kernel.
+extern "C" int emo_gemm_ln_res(int64_t M, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                               float drop_p, uint64_t seed, const void* res, int64_t ld_res, const float* gamma,
+                               const float* beta, float eps, void* y, int64_t ldy, void* sum_out, int64_t ld_sum, float* mean,
+                               float* rstd, void* stream) {
+  using namespace tc;
+  using namespace tc::ln;
+  EMO_REQUIRE(A && W && bias && res && gamma && beta && y, "emo_gemm_ln_res: null operand");
+  EMO_REQUIRE(M > 0 && K > 0 && K % BK == 0, "emo_gemm_ln_res: K must be a positive multiple of %d", BK);
+  auto ok = [](const void* q, int64_t ld) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && ld % 8 == 0; };
+  EMO_REQUIRE(ok(A, lda) && ok(W, ldw) && ok(res, ld_res) && ok(y, ldy) && (!sum_out || ok(sum_out, ld_sum)),
+              "emo_gemm_ln_res: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+  EMO_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(beta) & 15) == 0, "emo_gemm_ln_res: bias / gamma / beta must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUtensorMap ma, mb, my, mr, ms;
+  int rc;
+  if ((rc = make_map(&ma, A, K, M, lda, BM))) return rc;
+  if ((rc = make_map(&mb, W, K, LBN, ldw, 128))) return rc;
+  if ((rc = make_map(&my, y, LBN, M, ldy, 32))) return rc;
+  if ((rc = make_map(&mr, res, LBN, M, ld_res, 32))) return rc;
+  ms = my;
+  if (sum_out && (rc = make_map(&ms, sum_out, LBN, M, ld_sum, 32))) return rc;
+  LnParams p;
+  p.M = M; p.K = K; p.m_tiles = (int)((M + 255) / 256); p.kb_total = (int)(K / BK);
+  p.bias = bias; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd;
+  p.drop_thr = emo_drop_thr(drop_p); p.keep_scale = 1.f / (1.f - drop_p); p.seed = seed; p.eps = eps;
+  p.store_sum = sum_out != nullptr;
+  static bool configured = false;
+  static int max_units = 0;
+  if (!configured) {
+    EMO_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));
+    max_units = emo_num_sms() / 2;
+    configured = true;
+  }
+  const int units = p.m_tiles < max_units ? p.m_tiles : max_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * 2);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  EMO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_kernel, ma, mb, my, mr, ms, p));
+  EMO_LAUNCH_CHECK();
+  return EMO_OK;
 }

@@ -129,6 +129,19 @@ def ln_res_fwd(x, res, gamma, beta, y, mean=None, rstd=None, sum_out=None, eps=1
     return y
 
 
+def linear_ln_res_fwd(x, w, bias, res, gamma, beta, y, mean=None, rstd=None, sum_out=None, drop_p=0.0, seed=0, eps=1e-5):
+    """y = LN(res + dropout(x . w^T + bias)) in one launch (emo_gemm_ln_res): bf16, w [512, K]; sum_out = the pre-LN sum"""
+    _need_cuda(x, w, res, y)
+    M, K = x.shape
+    assert w.shape[0] == 512 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    tk = TIMER.start("gemm_ln")          # its own class: gemm_ln_kernel is a projection AND a LayerNorm (HBM-bound half the time)
+    L.check(L.lib().emo_gemm_ln_res(M, K, _p(x), x.stride(0), _p(w), w.stride(0), _p(bias), float(drop_p), int(seed), _p(res),
+                                    res.stride(0), _p(gamma), _p(beta), float(eps), _p(y), y.stride(0), _p(sum_out),
+                                    sum_out.stride(0) if sum_out is not None else 0, _p(mean), _p(rstd), _stream()), "emo_gemm_ln_res")
+    TIMER.stop(tk, 2.0 * M * 512 * K)
+    return y
+
+
 def ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, add_in=None, dx_drop=None, drop_p=0.0, seed=0, dxsum=None):
     """dxsum (fp32 [d]) += column sums of dx_drop (or dx): the bias gradient of the projection below."""
     rows = x.numel() // x.shape[-1]

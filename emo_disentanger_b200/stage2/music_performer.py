@@ -15,11 +15,15 @@ Per layer (post-LN TransformerEncoderLayer):
   s2   = y1 + drop(h W2^T + b2)             GEMM epilogue
   out  = LN2(s2)
 """
+import os
+
 import torch
 
 from .. import ops
 from ..engine import site_seed
 from .base import Stage2Base, _normal, _zeros
+
+FUSE_LN = os.environ.get("EMO_FUSE_LN", "1") != "0"
 
 E = 64  # head dim
 
@@ -109,6 +113,8 @@ class MusicPerformer(Stage2Base):
         h_in = self._embed(x, seg, seed)
         layers = []
         new = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, device=dev)
+        # EMO_FUSE_LN=0: out-projection / linear2 and their residual + LayerNorm as two launches each (A/B switch)
+        fuse_ln = FUSE_LN and dt == torch.bfloat16 and d == 512 and R > 128
         for l in range(self.n_layer):
             nm = self._layer_names(l)
             qkv = new(R, 3 * d)
@@ -121,22 +127,37 @@ class MusicPerformer(Stage2Base):
             ops.favor_fwd(q, k, v, omegas[l], att.view(B, T, d), den, seg_states=state)
             # the residual joins inside the LN kernel, in fp32: x + dropout(attn) is never rounded to bf16 on the
             # way into norm1 / norm2 (s1 / s2 below are the copies the backward re-normalises)
-            b1 = new(R, d)
-            ops.linear_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"), b1,
-                           bias=self._wv(Wf, nm + "attention.out_projection.bias"),
-                           drop_p=p, seed=site_seed(seed, 4 * l + 1))
             y1, m1, r1 = new(R, d), new(R, dtype=torch.float32), new(R, dtype=torch.float32)
-            s1 = b1 if save else None            # in place: each lane rewrites exactly the elements it has read
-            ops.ln_res_fwd(b1, h_in, self._wv(Wf, nm + "norm1.weight"), self._wv(Wf, nm + "norm1.bias"), y1, m1, r1, sum_out=s1)
+            if fuse_ln:
+                # projection + dropout + residual + LayerNorm in ONE kernel (emo_gemm_ln_res): whole rows live in tensor
+                # memory, the sum is never rounded on its way into the norm and never makes the HBM round trip
+                s1 = new(R, d) if save else None
+                ops.linear_ln_res_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"),
+                                      self._wv(Wf, nm + "attention.out_projection.bias"), h_in,
+                                      self._wv(Wf, nm + "norm1.weight"), self._wv(Wf, nm + "norm1.bias"), y1, m1, r1,
+                                      sum_out=s1, drop_p=p, seed=site_seed(seed, 4 * l + 1))
+            else:
+                b1 = new(R, d)
+                ops.linear_fwd(att, self._wv(Wc, nm + "attention.out_projection.weight"), b1,
+                               bias=self._wv(Wf, nm + "attention.out_projection.bias"),
+                               drop_p=p, seed=site_seed(seed, 4 * l + 1))
+                s1 = b1 if save else None            # in place: each lane rewrites exactly the elements it has read
+                ops.ln_res_fwd(b1, h_in, self._wv(Wf, nm + "norm1.weight"), self._wv(Wf, nm + "norm1.bias"), y1, m1, r1, sum_out=s1)
             hh = new(R, f)
             ops.linear_fwd(y1, self._wv(Wc, nm + "linear1.weight"), hh, bias=self._wv(Wf, nm + "linear1.bias"),
                            act=ops.ACT_RELU, drop_p=p, seed=site_seed(seed, 4 * l + 2))
-            b2 = new(R, d)
-            ops.linear_fwd(hh, self._wv(Wc, nm + "linear2.weight"), b2, bias=self._wv(Wf, nm + "linear2.bias"),
-                           drop_p=p, seed=site_seed(seed, 4 * l + 3))
             out, m2, r2 = new(R, d), new(R, dtype=torch.float32), new(R, dtype=torch.float32)
-            s2 = b2 if save else None
-            ops.ln_res_fwd(b2, y1, self._wv(Wf, nm + "norm2.weight"), self._wv(Wf, nm + "norm2.bias"), out, m2, r2, sum_out=s2)
+            if fuse_ln:
+                s2 = new(R, d) if save else None
+                ops.linear_ln_res_fwd(hh, self._wv(Wc, nm + "linear2.weight"), self._wv(Wf, nm + "linear2.bias"), y1,
+                                      self._wv(Wf, nm + "norm2.weight"), self._wv(Wf, nm + "norm2.bias"), out, m2, r2,
+                                      sum_out=s2, drop_p=p, seed=site_seed(seed, 4 * l + 3))
+            else:
+                b2 = new(R, d)
+                ops.linear_fwd(hh, self._wv(Wc, nm + "linear2.weight"), b2, bias=self._wv(Wf, nm + "linear2.bias"),
+                               drop_p=p, seed=site_seed(seed, 4 * l + 3))
+                s2 = b2 if save else None
+                ops.ln_res_fwd(b2, y1, self._wv(Wf, nm + "norm2.weight"), self._wv(Wf, nm + "norm2.bias"), out, m2, r2, sum_out=s2)
             if save:
                 layers.append((h_in, qkv, att, den, state, s1, m1, r1, y1, hh, s2, m2, r2))
             h_in = out

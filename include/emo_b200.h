@@ -298,6 +298,18 @@ int emo_sample_rows(const float* logits, int64_t ld, int rows, int V, const floa
                     const float* u, int greedy, int64_t* out, int32_t* status, const uint8_t* banned,
                     void* stream);
 
+/* ---- A3 fused: projection + dropout + residual + LayerNorm of the post-LN encoder layer -----------------------
+ * fast_transformers TransformerEncoderLayer.forward (`x = norm1(x + dropout(attn_out))`, `norm2(x + dropout(ff))`),
+ * N = d_model = 512, bf16 operands:   s = res + dropout(A[M,K] . W[512,K]^T + bias);  y = LN(s) * gamma + beta.
+ * s is formed and normalised in fp32 inside the kernel (a CTA pair owns whole rows: 512 TMEM columns); mean / rstd
+ * (fp32 [M], may be NULL) and sum_out (bf16 [M, ld_sum], may be NULL: the tensor emo_ln_bwd re-normalises) are kept for
+ * the backward.  Same dropout mask as emo_gemm with the same seed (element index m * 512 + n).  Equivalent to emo_gemm
+ * (NT, bias, drop_p) followed by emo_ln_res_fwd, without the 620 MB that pair moves through HBM per call. */
+int emo_gemm_ln_res(int64_t M, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                    float drop_p, uint64_t seed, const void* res, int64_t ld_res, const float* gamma,
+                    const float* beta, float eps, void* y, int64_t ldy, void* sum_out, int64_t ld_sum, float* mean,
+                    float* rstd, void* stream);
+
 /* ---- A11/A12 fused: logits projection + sampler of the decode loop ---------------------------
  * stage2_accompaniment/inference.py:272-276 (`logits = model(...)[-1]` -> `temperature` -> `nucleus`),
  * stage1_compose/inference_utils.py:66-72.  One launch per generated token: a thread-block cluster per sequence

@@ -154,6 +154,43 @@ def test_gemm_specialised_epilogues_equal_the_generic_kernel(ops, M):
         assert rel_err(a["sf"], b["sf"]) < 1e-5 or float(b["sf"].abs().max()) == 0, name
 
 
+@pytest.mark.parametrize("M,K,p", [(512, 512, 0.1), (600, 2048, 0.1), (300, 512, 0.0), (151552 // 8, 512, 0.1)])
+def test_gemm_residual_layernorm_fused(ops, M, K, p):
+    """emo_gemm_ln_res (projection + dropout + residual + LayerNorm in one CTA-pair kernel: whole rows in tensor memory,
+    two-pass epilogue) against fp32 torch with the mask the stand-alone dropout kernel derives from the same seed, and
+    against the two-kernel path (emo_gemm, then emo_ln_res_fwd)."""
+    torch.manual_seed(100 + M + K)
+    d = 512
+    x, w = _bf(torch.randn(M, K, device=DEV)), _bf(torch.randn(d, K, device=DEV) * (1.5 / K ** 0.5))
+    bias, res = torch.randn(d, device=DEV) * 0.2, _bf(torch.randn(M, d, device=DEV) * 1.5 + 0.3)
+    g, b = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV) * 0.2
+    seed = 0x1234567 + M
+    y, ssum = (torch.full((M + 3, d), 7.0, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.linear_ln_res_fwd(x, w, bias, res, g, b, y[:M], mean, rstd, sum_out=ssum[:M], drop_p=p, seed=seed)
+    torch.cuda.synchronize()
+    assert float(y[M:].float().min()) == 7.0 and float(ssum[M:].float().min()) == 7.0          # nothing written past M
+    pre = x.float() @ w.float().T + bias
+    if p > 0:
+        pre = ops.dropout_apply(pre.contiguous(), torch.empty_like(pre), p, seed)
+    s_ref = res.float() + pre
+    y_ref = torch.nn.functional.layer_norm(s_ref, (d,), g, b, 1e-5)
+    assert rms_rel(ssum[:M].float(), s_ref) < 4e-3
+    assert rms_rel(y[:M].float(), y_ref) < 5e-3
+    assert rel_err(mean, s_ref.mean(1)) < 2e-3 and rel_err(rstd, 1.0 / torch.sqrt(s_ref.var(1, unbiased=False) + 1e-5)) < 2e-3
+    # the two-kernel path on the same inputs: same mask (kept / dropped positions), values within bf16 rounding of b1
+    b1 = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    ops.linear_fwd(x, w, b1, bias=bias, drop_p=p, seed=seed)
+    y2, m2, r2 = torch.empty_like(b1), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    s2 = torch.empty_like(b1)
+    ops.ln_res_fwd(b1, res, g, b, y2, m2, r2, sum_out=s2)
+    assert rms_rel(y[:M].float(), y2.float()) < 6e-3 and rel_err(mean, m2) < 2e-3 and rel_err(rstd, r2) < 2e-3
+    # without the kept sum / statistics (inference)
+    y3 = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    ops.linear_ln_res_fwd(x, w, bias, res, g, b, y3, drop_p=p, seed=seed)
+    assert torch.equal(y3, y[:M])
+
+
 def test_gemm_dropout_epilogue_is_consistent_with_standalone_mask(ops):
     """GEMM-epilogue dropout == emo_dropout_apply with the same seed (what backward re-derives)."""
     torch.manual_seed(4)
